@@ -1,0 +1,112 @@
+/* transgo_b200.h -- C ABI of libtransgo_b200.so (B200 / sm_100a batched self-play engine for Transgo).
+ *
+ * Two groups of entry points, both plain C (pointers + sizes, no torch / C++ types):
+ *
+ *  (1) The reference's own 15 symbols (GoEnv/cpp_src/go_env.h:23-71), so that the unmodified
+ *      GoEnv/environment.py can `ctypes.cdll.LoadLibrary` this library in place of go_env.so
+ *      (environment.py:42).  They take ONE host-side state blob (the caller's >=1188-byte c_GoState;
+ *      this library uses its first tg_state_bytes(n) bytes) and run the same CUDA kernels as (2) with
+ *      G = 1: copy in, launch, copy out.  There is no CPU implementation behind them.
+ *
+ *  (2) Batched entry points `tg_*` over DEVICE memory + a CUDA stream, called from PyTorch host code
+ *      with tensor.data_ptr().  These are the hot path.
+ *
+ * Error convention for tg_*: return 0 on success, otherwise a cudaError_t (or -1 for bad arguments);
+ * tg_last_error() returns a static description.  The 15 reference symbols keep the reference convention
+ * (bool results, messages printed to stdout: go_env.cc:23,53,77, board.cc:449-460).
+ *
+ * State layout (n = 9: 48 B, n = 19: 128 B), little-endian u32 words:
+ *   [black bitboard][white bitboard][pad to a multiple of 16 B][4 meta words]
+ *   bitboard word = RPW rows of (n+1) bits each (guard bit per row); n=9: 3 x u32, n=19: 7 x u64
+ *   meta[0] = last_move1 (i16) | last_move2 (i16) << 16        (board.h:43-44; -1 pass, -3 none)
+ *   meta[1] = ko_location (i16) | ko_age (i16) << 16           (board.h:47,49)
+ *   meta[2] = step_count (u16) | next_player (u8) << 16 | ko_color (u8) << 24   (board.h:41-42,48)
+ *   meta[3] = terminated (bit 0)                               (go_env.h:16)
+ * A batch of G states is stored as SQ = bytes/16 planes of uint4[G] (plane k holds the k-th 16 B of every
+ * state) so that consecutive lanes read consecutive 128-bit words.
+ *
+ * Legal masks are "dense": bit a of a little-endian u32 string is action a; n=9: 4 x u32 (16 B),
+ * n=19: 12 x u32 (48 B).  Bit P (PASS) is set only when no board point is legal -- the rule
+ * GoEnv/environment.py:121-129 applies on top of go_env.cc:154-171 (which always appends PASS).
+ */
+#ifndef TRANSGO_B200_H_
+#define TRANSGO_B200_H_
+#include <stdbool.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---------------------------------------------------------------- (1) reference symbols, go_env.h:23-71 */
+typedef void TgState;   /* opaque host blob, >= tg_state_bytes(board size) bytes */
+
+bool    Init(int history_dim, int encode_dim, int max_step, float komi);     /* go_env.h:27  */
+bool    Reset(TgState* state);                                               /* go_env.h:30  */
+bool    Step(const TgState* state, TgState* next_state, int16_t action);     /* go_env.h:34  */
+bool    Step_(TgState* state, int16_t action);                               /* go_env.h:35  */
+bool    checkAction(const TgState* state, int16_t action);                   /* go_env.h:38  */
+bool    isTerminated(const TgState* state);                                  /* go_env.h:41  */
+bool    Encode(const TgState* state, float* encode_state);                   /* go_env.h:44  */
+float   getScore(const TgState* state);                                      /* go_env.h:47  */
+float   getTerritory(const TgState* state, float* territory);                /* go_env.h:50  */
+int     getLegalAction(const TgState* state, int* actions);                  /* go_env.h:53  */
+int     getLegalNoEye(const TgState* state, int* actions);                   /* go_env.h:56  */
+void    Show(const TgState* state);                                          /* go_env.h:59  */
+uint8_t getPlayer(const TgState* state);                                     /* go_env.h:62  */
+int     getStep(const TgState* state);                                       /* go_env.h:65  */
+void    getSubEncode(int* encode_state, int* sub_encode_state, int sub_board_size,
+                     int encode_state_channels, int cut_num);                /* go_env.h:68  */
+
+/* The reference fixes the board size at compile time (go_comm.h:20); here it is a process setting
+ * for the single-state symbols above (default 9).  Returns false for an unsupported size. */
+bool    tg_set_board_size(int n);
+
+/* ---------------------------------------------------------------- (2) batched device entry points */
+int         tg_version(void);
+const char* tg_last_error(void);
+int         tg_supported_board(int n);          /* 1 for n in {9, 19} */
+int         tg_state_bytes(int n);              /* 48 / 128 */
+int         tg_legal_words(int n);              /* u32 words of a dense legal mask, padded to 16 B: 4 / 12 */
+
+/* All pointers are device pointers; `stream` is a cudaStream_t (NULL = default stream).
+ * `tile` = lanes cooperating on one game: 32 (lowest latency, small batches) ... 1 (highest throughput,
+ * very large batches); 0 lets the library choose from G. */
+
+/* board.cc:13-26 + go_env.cc:34-41 */
+int tg_env_reset(int n, void* states, int64_t G, void* stream);
+
+/* go_env.cc:44-80 for every game: states are updated in place.
+ *   actions   int16[G]         0..P-1 point, P or -1 pass, -2 resign
+ *   legal_out u32[G][LW]       dense legal mask of the NEW position (may be NULL)
+ *   done_out  u8[G]            the bool Step returns (may be NULL)
+ *   acc_out   u8[G]            0 where the reference prints "Fail to Step: invalid action" (may be NULL) */
+int tg_env_step(int n, void* states, int64_t G, const int16_t* actions, uint32_t* legal_out,
+                uint8_t* done_out, uint8_t* acc_out, int max_step, int tile, void* stream);
+
+/* go_env.cc:154-171 (no_eye = 0) / :178-188 (no_eye = 1) as dense masks */
+int tg_env_legal(int n, const void* states, int64_t G, uint32_t* legal_out, int no_eye, int tile, void* stream);
+
+/* go_env.cc:96-115 with encode_dim 10: planes float32[G][10][n][n], written in place (e.g. the net's input) */
+int tg_env_encode(int n, const void* states, int64_t G, float* planes, int tile, void* stream);
+
+/* go_env.cc:126-149: score float32[G] = area(black) - area(white) - komi; territory float32[G][P] in
+ * {+1 black, 0 dame, -1 white} (may be NULL) */
+int tg_env_score(int n, const void* states, int64_t G, float komi, float* score, float* territory,
+                 int tile, void* stream);
+
+/* SURVEY.md 8d C2 workload: every game plays up to `plies` moves in ONE launch.  Move rule: the k-th legal
+ * board point in ascending order, k = (mix32(seed, game_id0 + g, step_count) * n_legal) >> 32; PASS iff none
+ * (environment.py:121-129).  no_eye = 1 draws from getLegalNoEye's points instead.
+ *   trace_actions int16[plies][G]  chosen action per ply, -3 after the game ended (may be NULL)
+ *   plies_done    u64[1]           += number of moves actually played (may be NULL) */
+int tg_env_playout(int n, void* states, int64_t G, int plies, int max_step, uint64_t seed, int64_t game_id0,
+                   int no_eye, int16_t* trace_actions, unsigned long long* plies_done, int tile, void* stream);
+
+/* board.cc:1166-1271: float32[B][C][n][n] -> float32[B][cuts][C][sub][sub] */
+int tg_sub_encode(int n, const float* enc, int64_t B, int channels, int sub, int cuts, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,224 @@
+"""GPU parity tests of the board kernels, all through the C ABI (include/transgo_b200.h).
+
+Checker = oracle/ (C restatement, pinned to the reference by tests/test_oracle.py) and the reference's own golden
+traces in tests/golden/.  Bar: bit-exact (integer / 0-1 float work).
+"""
+import numpy as np
+import pytest
+
+from helpers import load_golden, replay_golden, playout_action
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+def _oracle(n, **kw):
+    from oracle.go_oracle import OracleEnv
+    return OracleEnv(n, **kw)
+
+
+def _unpack_states(env):
+    return env.states.cpu().numpy()
+
+
+# ------------------------------------------------------------------ the reference-named single-state symbols
+@pytest.mark.parametrize("n,games", [(9, 12), (19, 1)])
+def test_compat_symbols_reproduce_reference_golden(oracle_built, n, games, capfd):
+    """Unmodified-environment.py view: GoEnv -> Reset/Step/Encode/... -> CUDA, against traces the reference produced."""
+    from transgo_b200.environment import GoEnv
+    t = load_golden(n)
+    env = GoEnv(board_size=n)
+    assert env.max_step == int(t["max_step"])
+    checked = replay_golden(env, t, games)
+    assert checked > 100 * games
+    capfd.readouterr()
+
+
+def test_compat_misc_semantics(oracle_built, capfd):
+    from transgo_b200.environment import GoEnv
+    env = GoEnv(board_size=9)
+    o = _oracle(9)
+    s, done = env.reset()
+    assert done is False and env.justStarted(s) and env.getPlayer(s) == 1 and env.getStep(s) == 1
+    assert env.getScore(s) == -7.5                                   # stone-less board (board.cc:932-935)
+    sc, terr = env.getScoreAndTerritory(s)
+    assert sc == -7.5 and not terr.any()
+    # occupied point is rejected, state unchanged, done False (go_env.cc:75-79)
+    s1, d = env.step(s, 40)
+    s2, d2 = env.step(s1, 40)
+    assert d2 is False and bytes(s2.raw[:48]) == bytes(s1.raw[:48])
+    assert env.checkAction(s1, 40) is False and env.checkAction(s1, 41) is True and env.checkAction(s1, -1) is True
+    # pass / pass ends the game; stepping a finished game returns True and keeps the state (go_env.cc:52-55)
+    p1, d = env.step(s1, 81); assert d is False
+    p2, d = env.step(p1, 81); assert d is True and env.isTerminated(p2)
+    p3, d = env.step(p2, 3); assert d is True and bytes(p3.raw[:48]) == bytes(p2.raw[:48])
+    # resign (-2) ends at once (board.cc:656-661)
+    r1, d = env.step(s1, -2); assert d is True
+    # sub-board crops (board.cc:1166-1271)
+    enc = np.arange(810, dtype=np.float32).reshape(10, 9, 9)
+    assert np.array_equal(env.subEncode(enc), o.subEncode(enc, 7, 4))
+    assert env.action_to_location(40) == [4, 4] and env.location_to_action([4, 4]) == 40
+    env.show(s1)
+    out = capfd.readouterr().out
+    assert "Fail to Step: invalid action" in out and "Fail to Step: game is done!!" in out and "next_player" in out
+
+
+# ------------------------------------------------------------------ batched kernels
+def _replay_trace_with_oracle(n, trace, game_ids, seed, max_step, no_eye=False):
+    """Replays device-chosen actions through the oracle, checking the move rule itself on the way."""
+    o = _oracle(n, max_step=max_step)
+    P = n * n
+    finals = []
+    for col, g in enumerate(game_ids):
+        s, _ = o.reset()
+        for tply in range(trace.shape[0]):
+            a = int(trace[tply, col])
+            if o.isTerminated(s):
+                assert a == -3
+                continue
+            pts = [x for x in (o.getLegalNoEye(s) if no_eye else o.legal_c(s)) if x != P]
+            assert a == playout_action(seed, g, o.getStep(s), pts, P), (g, tply, a)
+            s, _ = o.step(s, a)
+        finals.append(s)
+    return o, finals
+
+
+@pytest.mark.parametrize("n,G,tile,no_eye", [(9, 4096, 32, False), (9, 4096, 8, False), (9, 4096, 1, False),
+                                             (9, 1024, 32, True), (19, 256, 32, False), (19, 256, 1, False)])
+def test_playout_matches_oracle(oracle_built, n, G, tile, no_eye):
+    """G concurrent random playouts in one launch; a sample of games is replayed on the CPU."""
+    from transgo_b200.environment import BatchedGoEnv
+    seed = 0x7261
+    env = BatchedGoEnv(G, board_size=n, tile=tile)
+    plies = env.max_step + 2
+    trace = torch.full([plies, G], -9, dtype=torch.int16, device="cuda")
+    counter = torch.zeros([1], dtype=torch.int64, device="cuda")
+    env.playout(plies, seed=seed, no_eye=no_eye, trace=trace, counter=counter)
+    torch.cuda.synchronize()
+    tr = trace.cpu().numpy()
+    assert int(counter.item()) == int((tr != -3).sum())
+    meta = {k: v.cpu().numpy() for k, v in env.meta().items()}
+    assert meta["terminated"].all()
+    sample = np.unique(np.concatenate([np.arange(0, 24), np.random.default_rng(1).integers(0, G, 40 if n == 9 else 6)]))
+    o, finals = _replay_trace_with_oracle(n, tr[:, sample], sample, seed, env.max_step, no_eye)
+    sc, terr = env.score(want_territory=True)
+    planes = env.encode()
+    legal = env.unpack_legal(env.legal_mask()).cpu().numpy()
+    noeye = env.unpack_legal(env.legal_mask(no_eye=True)).cpu().numpy()
+    torch.cuda.synchronize()
+    sc, terr, planes = sc.cpu().numpy(), terr.cpu().numpy(), planes.cpu().numpy()
+    P = n * n
+    for col, g in enumerate(sample):
+        s = finals[col]
+        osc, oterr = o.getScoreAndTerritory(s)
+        assert sc[g] == osc and np.array_equal(terr[g], oterr), g
+        assert np.array_equal(planes[g], o.encode(s)), g
+        acts = np.asarray(o.getLegalAction(s)); row = np.zeros(P + 1, bool); row[acts] = True
+        assert np.array_equal(legal[g], row), g
+        ne = [x for x in o.getLegalNoEye(s) if x != P] or [P]
+        row2 = np.zeros(P + 1, bool); row2[ne] = True
+        assert np.array_equal(noeye[g], row2), g
+        assert meta["step"][g] == o.getStep(s) and meta["player"][g] == o.getPlayer(s)
+
+
+@pytest.mark.parametrize("n,G,tile", [(9, 96, 32), (9, 96, 8), (9, 96, 1), (19, 8, 32)])
+def test_step_kernel_per_ply_against_oracle(oracle_built, n, G, tile):
+    """Per ply: tg_env_step with oracle-chosen (sometimes illegal / pass / resign) actions; legal mask, done, accepted,
+    planes, score and territory must match the oracle after every move."""
+    from transgo_b200.environment import BatchedGoEnv
+    rng = np.random.default_rng(11)
+    env = BatchedGoEnv(G, board_size=n, tile=tile)
+    o = _oracle(n)
+    P = n * n
+    states = [o.reset()[0] for _ in range(G)]
+    nply = 140 if n == 9 else 60
+    for ply in range(nply):
+        acts = np.zeros(G, np.int16)
+        for g in range(G):
+            s = states[g]
+            la = list(o.getLegalAction(s))
+            r = rng.random()
+            if r < 0.04:
+                a = int(rng.integers(0, P))            # may be illegal
+            elif r < 0.10:
+                a = P if rng.random() < 0.5 else -1     # both spellings of PASS
+            elif r < 0.102:
+                a = -2                                  # resign
+            else:
+                a = int(la[rng.integers(0, len(la))])
+            acts[g] = a
+        legal, done = env.step(torch.from_numpy(acts).cuda())
+        lg = env.unpack_legal(legal).cpu().numpy(); dn = done.cpu().numpy(); acc = env.accepted.cpu().numpy()
+        check_planes = ply % 7 == 0
+        if check_planes:
+            planes = env.encode().cpu().numpy()
+            sc, terr = env.score(want_territory=True); sc = sc.cpu().numpy(); terr = terr.cpu().numpy()
+        for g in range(G):
+            before = states[g]
+            was_term = o.isTerminated(before)
+            s2, d = o.step(before, int(acts[g]))
+            assert bool(dn[g]) == d, (ply, g, acts[g])
+            changed = o.getStep(s2) != o.getStep(before)
+            assert bool(acc[g]) == changed, (ply, g, acts[g], was_term)
+            states[g] = s2
+            row = np.zeros(P + 1, bool); row[np.asarray(o.getLegalAction(s2))] = True
+            assert np.array_equal(lg[g], row), (ply, g)
+            if check_planes:
+                assert np.array_equal(planes[g], o.encode(s2)), (ply, g)
+                osc, oterr = o.getScoreAndTerritory(s2)
+                assert sc[g] == osc and np.array_equal(terr[g], oterr), (ply, g)
+        meta = {k: v.cpu().numpy() for k, v in env.meta().items()}
+        for g in range(G):
+            s = states[g]
+            assert (meta["step"][g], meta["player"][g], meta["terminated"][g]) == (s.step_count, s.next_player, s.terminated)
+            assert (meta["last1"][g], meta["last2"][g]) == (s.last1, s.last2)
+            if s.ko_age == 0:
+                assert (meta["ko_loc"][g], meta["ko_color"][g], meta["ko_age"][g]) == (s.ko_loc, s.ko_color, 0)
+
+
+def test_tiles_agree_bit_for_bit_at_full_size():
+    """Size-independent property at the BASELINE C2 size and beyond: the three tile widths are different programs
+    (32, 8, 1 lanes per game) and must produce identical final states, scores and planes."""
+    from transgo_b200.environment import BatchedGoEnv
+    G = 65536
+    ref = None
+    for tile in (32, 8, 1):
+        env = BatchedGoEnv(G, board_size=9, tile=tile)
+        env.playout(122, seed=99)
+        out = (env.states.clone(), env.score(), env.encode(), env.legal_mask().clone())
+        torch.cuda.synchronize()
+        if ref is None:
+            ref = out
+        else:
+            for a, b in zip(ref, out):
+                assert torch.equal(a, b)
+    st, sc, planes, _ = ref
+    # every game ran to termination; area scores are odd multiples of .5 within the board
+    assert bool(((st[-1][:, 3] & 1) == 1).all())
+    assert bool((sc.abs() <= 81 + 7.5).all()) and bool(((sc * 2) % 2 == 1).all())
+    # planes are exactly 0/1 and the six stone planes partition the stones
+    assert bool(((planes == 0) | (planes == 1)).all())
+    assert bool((planes[:, :6].sum(1) <= 1).all())
+
+
+def test_playout_is_resumable_and_deterministic():
+    """Playing 50 + 72 plies in two launches equals 122 plies in one (the hash is keyed by step_count, not launch)."""
+    from transgo_b200.environment import BatchedGoEnv
+    a = BatchedGoEnv(2048, tile=32); a.playout(122, seed=5)
+    b = BatchedGoEnv(2048, tile=32); b.playout(50, seed=5); b.playout(72, seed=5)
+    c = BatchedGoEnv(1024, tile=32); c.playout(122, seed=5, game_id0=1024)
+    torch.cuda.synchronize()
+    assert torch.equal(a.states, b.states)
+    assert torch.equal(a.states[:, 1024:], c.states)      # sharding by game id gives the same games (multi-GPU rule)
+
+
+def test_encode_writes_in_place_into_a_larger_tensor():
+    from transgo_b200.environment import BatchedGoEnv
+    env = BatchedGoEnv(37, tile=32)                       # odd count exercises the unaligned tail
+    env.playout(60, seed=3)
+    big = torch.full([2, 37, 10, 9, 9], 7.0, device="cuda")
+    env.encode(out=big[1])
+    ref = env.encode()
+    torch.cuda.synchronize()
+    assert torch.equal(big[1], ref) and bool((big[0] == 7.0).all())

@@ -1,0 +1,57 @@
+// tg_common.cuh -- launch constants and the shared-memory staging used to turn feature bitboards into the
+// float32 [10][n][n] planes of board_feature.cc:213-223 with coalesced 128-bit stores.
+#pragma once
+#include "tg_board.cuh"
+
+namespace tg {
+
+constexpr int kThreads = 128;     // threads per CTA for every tile-cooperative kernel
+
+int set_err(int code, const char* what);
+const char* last_err();
+int pick_tile(int tile, long long G);
+
+// The CTA keeps ONE contiguous bit string: game `local` of the CTA owns bits [local*10P, (local+1)*10P), plane k
+// of that game bits [k*P, (k+1)*P) inside it, in action order -- i.e. exactly the order of the output floats.
+template <int N> __host__ __device__ constexpr size_t planes_smem_bytes(int games_per_cta) {
+    return (size_t)((games_per_cta * Geo<N>::PLANE_BITS + 31) / 32 + 1) * 4;
+}
+
+template <int N> __device__ __forceinline__ void planes_smem_clear(uint32_t* sm, int games_per_cta) {
+    const int words = (games_per_cta * Geo<N>::PLANE_BITS + 31) / 32 + 1;
+    for (int i = threadIdx.x; i < words; i += blockDim.x) sm[i] = 0;
+}
+
+template <int N, int T> __device__ __forceinline__ void planes_to_smem(const BB<N>* pl, uint32_t* sm, int local) {
+    using G = Geo<N>;
+    const int lane = Tile<T>::lane();
+    const int base = local * G::PLANE_BITS;
+#pragma unroll
+    for (int k = 0; k < 10; ++k) {
+#pragma unroll
+        for (int y = 0; y < N; ++y) {
+            if (((k * N + y) & (T - 1)) != lane) continue;
+            const int wi = y / G::RPW, sh = (y % G::RPW) * G::STRIDE;
+            const uint32_t rowbits = (uint32_t)((pl[k].w[wi] >> sh) & G::row());
+            if (!rowbits) continue;
+            const int off = base + k * G::P + y * N;
+            const int ds = off & 31;
+            atomicOr(&sm[off >> 5], rowbits << ds);
+            if (ds + N > 32) atomicOr(&sm[(off >> 5) + 1], rowbits >> (32 - ds));
+        }
+    }
+}
+
+// out must be 16-byte aligned; ngames * PLANE_BITS floats are written by the whole CTA.
+template <int N> __device__ __forceinline__ void planes_smem_to_global(const uint32_t* sm, float* __restrict__ out, int ngames) {
+    const int total = ngames * Geo<N>::PLANE_BITS;
+    const int quads = total >> 2;
+    float4* o4 = reinterpret_cast<float4*>(out);
+    for (int f = threadIdx.x; f < quads; f += blockDim.x) {
+        const uint32_t nib = (sm[f >> 3] >> ((f & 7) * 4)) & 15u;
+        o4[f] = make_float4((float)(nib & 1u), (float)((nib >> 1) & 1u), (float)((nib >> 2) & 1u), (float)((nib >> 3) & 1u));
+    }
+    for (int e = (quads << 2) + threadIdx.x; e < total; e += blockDim.x) out[e] = (float)((sm[e >> 5] >> (e & 31)) & 1u);
+}
+
+}  // namespace tg

@@ -1,0 +1,209 @@
+"""Host-side mirror of the reference environment binding (GoEnv/environment.py:32-198).
+
+``GoEnv``         same constructor, method names, argument meaning, return conventions and error behaviour as
+                  the reference class, for ONE state at a time; every rules call runs the sm_100a kernels
+                  through the reference-named C symbols of libtransgo_b200.so.
+``BatchedGoEnv``  the B200 hot path: G games resident in HBM, one kernel launch per call, torch tensors in/out.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+
+BLACK = 1     # environment.py:14-15
+WHITE = 2
+
+DEFAULT_MAX_STEP = {9: 120, 19: 722}   # environment.py:37; 19x19 has no reference default (SURVEY.md 8d C4 note)
+
+
+class GoState(ctypes.Structure):
+    """Opaque state value.  The reference blob (environment.py:17-29) is 1196 bytes and never field-accessed;
+    this one is padded to the same size at 9x9 so either library can be handed either buffer."""
+    _fields_ = [("raw", ctypes.c_uint8 * 1196)]
+
+
+class GoEnv:
+    def __init__(self, config=None, board_size=None):
+        self.config = config
+        self.history_dim = 1            # environment.py:35-40
+        self.encoded_dim = 10
+        self.board_size = board_size or (getattr(config, "board_size", 9) if config is not None else 9)
+        self.max_step = DEFAULT_MAX_STEP.get(self.board_size, 2 * self.board_size ** 2)
+        self.komi = 7.5
+        self.sub_board_size = 7
+        self.lib = _lib.lib()
+        if not self.lib.tg_set_board_size(self.board_size):
+            raise ValueError("unsupported board size %d" % self.board_size)
+        self.lib.Init(self.history_dim, self.encoded_dim, self.max_step, self.komi)
+        self._P = self.board_size ** 2
+
+    # -- environment.py:92-103
+    def reset(self):
+        new_state = GoState()
+        self.lib.Reset(ctypes.byref(new_state))
+        return new_state, False
+
+    def step(self, state, action):
+        new_state = GoState()
+        done = self.lib.Step(ctypes.byref(state), ctypes.byref(new_state), int(action))
+        return new_state, done
+
+    # -- environment.py:105-113
+    def encode(self, state):
+        out = np.zeros([self.history_dim * self.encoded_dim, self.board_size, self.board_size], dtype="float32")
+        self.lib.Encode(ctypes.byref(state), out.ctypes.data)
+        return out
+
+    def subEncode(self, encode):
+        encode = np.ascontiguousarray(encode, dtype="float32")
+        sub = np.zeros([4, self.encoded_dim, self.sub_board_size, self.sub_board_size], dtype="float32")
+        self.lib.getSubEncode(encode.ctypes.data, sub.ctypes.data, self.sub_board_size, self.encoded_dim, 4)
+        return sub
+
+    # -- environment.py:115-129
+    def getScore(self, state):
+        return self.lib.getScore(ctypes.byref(state))
+
+    def getWinner(self, state):
+        return BLACK if self.getScore(state) > 0 else WHITE
+
+    def getLegalAction(self, state):
+        legal_action = np.zeros([self._P + 1], dtype="int32")
+        num_action = self.lib.getLegalAction(ctypes.byref(state), legal_action.ctypes.data)
+        legal_acts = legal_action[:num_action]
+        if num_action != 1:
+            legal_acts = [act for act in legal_acts if act != self._P]
+        return legal_acts
+
+    def getPlayer(self, state):
+        return self.lib.getPlayer(ctypes.byref(state))
+
+    def action_to_location(self, action):
+        return [action // self.board_size, action % self.board_size]
+
+    def location_to_action(self, location):
+        return self.board_size * location[0] + location[1]
+
+    # -- environment.py:153-173
+    def checkAction(self, state, action):
+        return self.lib.checkAction(ctypes.byref(state), int(action))
+
+    def getScoreAndTerritory(self, state):
+        territory = np.zeros([self._P], dtype="float32")
+        score = self.lib.getTerritory(ctypes.byref(state), territory.ctypes.data)
+        return score, territory
+
+    def getLegalNoEye(self, state):
+        candidate = np.zeros([self._P + 1], dtype="int32")
+        n = self.lib.getLegalNoEye(ctypes.byref(state), candidate.ctypes.data)
+        return candidate[:n]
+
+    def show(self, state):
+        self.lib.Show(ctypes.byref(state))
+
+    def getStep(self, state):
+        return self.lib.getStep(ctypes.byref(state))
+
+    def justStarted(self, state):
+        return self.lib.getStep(ctypes.byref(state)) == 1
+
+    def isTerminated(self, state):
+        return self.lib.isTerminated(ctypes.byref(state))
+
+
+class BatchedGoEnv:
+    """G concurrent games in HBM.  State tensor: int32 [SQ, G, 4] (SQ planes of 128-bit words, include/transgo_b200.h).
+
+    ``step`` keeps the reference semantics per game (go_env.cc:51-80): terminated games stay put and report
+    done, illegal actions leave the state unchanged and report accepted = 0.
+    """
+
+    def __init__(self, num_games, board_size=9, max_step=None, komi=7.5, device="cuda", tile=0):
+        import torch
+        self.torch = torch
+        if not torch.cuda.is_available():
+            raise _lib.TransgoLibraryError("BatchedGoEnv needs a CUDA device (no CPU fallback)")
+        self.lib = _lib.lib()
+        if not self.lib.tg_supported_board(board_size):
+            raise ValueError("unsupported board size %d" % board_size)
+        self.G = int(num_games)
+        self.n = board_size
+        self.P = board_size * board_size
+        self.A = self.P + 1
+        self.max_step = DEFAULT_MAX_STEP.get(board_size, 2 * self.P) if max_step is None else int(max_step)
+        self.komi = float(komi)
+        self.device = torch.device(device)
+        self.tile = tile
+        self.SQ = self.lib.tg_state_bytes(board_size) // 16
+        self.LW = self.lib.tg_legal_words(board_size)
+        self.states = torch.zeros([self.SQ, self.G, 4], dtype=torch.int32, device=self.device)
+        self.legal = torch.zeros([self.G, self.LW], dtype=torch.int32, device=self.device)
+        self.done = torch.zeros([self.G], dtype=torch.uint8, device=self.device)
+        self.accepted = torch.zeros([self.G], dtype=torch.uint8, device=self.device)
+        self._bitpos = None
+        self.reset()
+
+    def _s(self):
+        return _lib.stream_ptr()
+
+    def reset(self):
+        _lib.check(self.lib.tg_env_reset(self.n, _lib.ptr(self.states), self.G, self._s()), "tg_env_reset")
+        self.done.zero_()
+        return self.states
+
+    def step(self, actions, want_legal=True):
+        """actions: int16 [G] on the device.  Returns (legal mask int32 [G, LW] of the new positions, done uint8 [G])."""
+        assert actions.dtype == self.torch.int16 and actions.is_cuda and actions.numel() == self.G
+        _lib.check(self.lib.tg_env_step(self.n, _lib.ptr(self.states), self.G, _lib.ptr(actions),
+                                        _lib.ptr(self.legal) if want_legal else None, _lib.ptr(self.done),
+                                        _lib.ptr(self.accepted), self.max_step, self.tile, self._s()), "tg_env_step")
+        return self.legal, self.done
+
+    def legal_mask(self, no_eye=False, out=None):
+        out = self.legal if out is None else out
+        _lib.check(self.lib.tg_env_legal(self.n, _lib.ptr(self.states), self.G, _lib.ptr(out), int(no_eye), self.tile,
+                                         self._s()), "tg_env_legal")
+        return out
+
+    def encode(self, out=None):
+        """float32 [G, 10, n, n]; pass ``out`` (e.g. a slice of the net's input tensor) to write in place."""
+        if out is None:
+            out = self.torch.empty([self.G, 10, self.n, self.n], dtype=self.torch.float32, device=self.device)
+        assert out.is_contiguous() and out.dtype == self.torch.float32
+        _lib.check(self.lib.tg_env_encode(self.n, _lib.ptr(self.states), self.G, _lib.ptr(out), self.tile, self._s()),
+                   "tg_env_encode")
+        return out
+
+    def score(self, want_territory=False):
+        sc = self.torch.empty([self.G], dtype=self.torch.float32, device=self.device)
+        terr = self.torch.empty([self.G, self.P], dtype=self.torch.float32, device=self.device) if want_territory else None
+        _lib.check(self.lib.tg_env_score(self.n, _lib.ptr(self.states), self.G, self.komi, _lib.ptr(sc), _lib.ptr(terr),
+                                         self.tile, self._s()), "tg_env_score")
+        return (sc, terr) if want_territory else sc
+
+    def playout(self, plies, seed=0x7261, game_id0=0, no_eye=False, trace=None, counter=None):
+        """Every game plays up to ``plies`` moves of the SURVEY 8d C2 rule in one launch."""
+        _lib.check(self.lib.tg_env_playout(self.n, _lib.ptr(self.states), self.G, int(plies), self.max_step, int(seed),
+                                           int(game_id0), int(no_eye), _lib.ptr(trace), _lib.ptr(counter), self.tile,
+                                           self._s()), "tg_env_playout")
+
+    # ---- helpers (format conversion only)
+    def unpack_legal(self, legal=None):
+        """dense mask int32 [G, LW] -> bool [G, A]"""
+        torch = self.torch
+        legal = self.legal if legal is None else legal
+        if self._bitpos is None:
+            a = torch.arange(self.A, device=self.device)
+            self._bitpos = (a // 32, (a % 32).to(torch.int32))
+        w, b = self._bitpos
+        return ((legal[:, w] >> b) & 1).bool()
+
+    def meta(self):
+        """Decoded meta words as a dict of int tensors (step, player, last1, last2, ko_loc, ko_age, terminated)."""
+        torch = self.torch
+        m = self.states[self.SQ - 1]          # [G, 4]
+        s16 = lambda v: ((v & 0xffff) ^ 0x8000) - 0x8000
+        return dict(last1=s16(m[:, 0]), last2=s16(m[:, 0] >> 16), ko_loc=s16(m[:, 1]), ko_age=s16(m[:, 1] >> 16),
+                    step=m[:, 2] & 0xffff, player=(m[:, 2] >> 16) & 0xff, ko_color=(m[:, 2] >> 24) & 0xff,
+                    terminated=m[:, 3] & 1)
