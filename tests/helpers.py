@@ -70,3 +70,43 @@ def playout_action(seed, game_id, step, legal_points, P):
         return P
     r = int(mix32(seed, game_id, step))
     return int(legal_points[(r * nl) >> 32])
+
+
+# ----------------------------------------------------------------------------------------------- MCTS golden
+def load_mcts_golden():
+    z = np.load(os.path.join(GOLDEN, "mcts_trace_9.npz"))
+    return {k: z[k] for k in z.files}
+
+
+def mcts_golden_games(t):
+    """Yields (game id, sims, sharp, row indices) per recorded game."""
+    for g in np.unique(t["game"]):
+        rows = np.nonzero(t["game"] == g)[0]
+        yield int(g), int(t["sims"][rows[0]]), int(t["sharp"][rows[0]]), rows
+
+
+def golden_hooks(t, rows, game):
+    """noise / uniform / tie-break hooks that replay exactly what the reference run consumed."""
+    from oracle import provider
+    seed = int(t["seed"])
+    ties = [0]
+
+    def tie(n):
+        i = provider.tie_index(seed, game, ties[0], n)
+        ties[0] += 1
+        return i
+    return dict(noise_fn=lambda m, k: t["noise"][rows[m]][:k], u_fn=lambda m: float(t["u"][rows[m]]), tie_fn=tie), ties
+
+
+def check_mcts_move_against_golden(t, row, acts, N, W, var, action, pi, done, rtol=1e-5):
+    """Visit counts exact; W / var within 1e-5 relative (the north_star tolerance for fp32 Q statistics); the
+    reference arm itself is float32, so the oracle is expected to hit them exactly."""
+    counts = np.zeros(82, np.int64); counts[acts] = N
+    assert np.array_equal(counts, t["counts"][row]), ("visit counts", row)
+    w = np.zeros(82, np.float32); w[acts] = W
+    v = np.zeros(82, np.float32); v[acts] = var
+    np.testing.assert_allclose(w, t["W"][row], rtol=rtol, atol=1e-6)
+    np.testing.assert_allclose(v, t["var"][row], rtol=rtol, atol=1e-6)
+    assert int(action) == int(t["action"][row]), ("action", row)
+    assert np.array_equal(np.asarray(pi, dtype=np.float64), t["pi"][row]), ("pi", row)
+    assert bool(done) == bool(t["done"][row])

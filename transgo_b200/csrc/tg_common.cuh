@@ -14,11 +14,11 @@ int pick_tile(int tile, long long G);
 // The CTA keeps ONE contiguous bit string: game `local` of the CTA owns bits [local*10P, (local+1)*10P), plane k
 // of that game bits [k*P, (k+1)*P) inside it, in action order -- i.e. exactly the order of the output floats.
 template <int N> __host__ __device__ constexpr size_t planes_smem_bytes(int games_per_cta) {
-    return (size_t)((games_per_cta * Geo<N>::PLANE_BITS + 31) / 32 + 1) * 4;
+    return (size_t)((games_per_cta * Geo<N>::PLANE_BITS + 31) / 32 + 2) * 4;
 }
 
 template <int N> __device__ __forceinline__ void planes_smem_clear(uint32_t* sm, int games_per_cta) {
-    const int words = (games_per_cta * Geo<N>::PLANE_BITS + 31) / 32 + 1;
+    const int words = (games_per_cta * Geo<N>::PLANE_BITS + 31) / 32 + 2;
     for (int i = threadIdx.x; i < words; i += blockDim.x) sm[i] = 0;
 }
 
@@ -42,16 +42,22 @@ template <int N, int T> __device__ __forceinline__ void planes_to_smem(const BB<
     }
 }
 
-// out must be 16-byte aligned; ngames * PLANE_BITS floats are written by the whole CTA.
+// ngames * PLANE_BITS floats are written by the whole CTA.  `out` is 4-byte aligned at least; up to three leading
+// floats are peeled so that the bulk goes out as aligned 128-bit stores.
 template <int N> __device__ __forceinline__ void planes_smem_to_global(const uint32_t* sm, float* __restrict__ out, int ngames) {
     const int total = ngames * Geo<N>::PLANE_BITS;
-    const int quads = total >> 2;
-    float4* o4 = reinterpret_cast<float4*>(out);
+    int head = (int)(((16u - (unsigned)(reinterpret_cast<uintptr_t>(out) & 15u)) & 15u) >> 2);
+    head = head < total ? head : total;
+    const int quads = (total - head) >> 2;
+    float4* o4 = reinterpret_cast<float4*>(out + head);
     for (int f = threadIdx.x; f < quads; f += blockDim.x) {
-        const uint32_t nib = (sm[f >> 3] >> ((f & 7) * 4)) & 15u;
+        const int bit = head + 4 * f;
+        const uint32_t nib = __funnelshift_r(sm[bit >> 5], sm[(bit >> 5) + 1], bit & 31) & 15u;
         o4[f] = make_float4((float)(nib & 1u), (float)((nib >> 1) & 1u), (float)((nib >> 2) & 1u), (float)((nib >> 3) & 1u));
     }
-    for (int e = (quads << 2) + threadIdx.x; e < total; e += blockDim.x) out[e] = (float)((sm[e >> 5] >> (e & 31)) & 1u);
+    if ((int)threadIdx.x < head) out[threadIdx.x] = (float)((sm[0] >> threadIdx.x) & 1u);
+    const int e = head + (quads << 2) + (int)threadIdx.x;
+    if (e < total) out[e] = (float)((sm[e >> 5] >> (e & 31)) & 1u);
 }
 
 }  // namespace tg

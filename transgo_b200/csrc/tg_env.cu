@@ -263,7 +263,7 @@ int tg_env_legal(int n, const void* states, int64_t G, uint32_t* legal_out, int 
 
 int tg_env_encode(int n, const void* states, int64_t G, float* planes, int tile, void* stream) {
     if (!states || !planes || G <= 0) return set_err(-1, "tg_env_encode");
-    if ((reinterpret_cast<uintptr_t>(planes) & 15) != 0) return set_err(-1, "tg_env_encode: planes must be 16-byte aligned");
+    if ((reinterpret_cast<uintptr_t>(planes) & 3) != 0) return set_err(-1, "tg_env_encode: planes must be 4-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
     tile = snap_tile(tile, G);
     TG_DISPATCH(n, tile, launch_encode, st, (const uint4*)states, G, planes);
