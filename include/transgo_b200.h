@@ -106,6 +106,88 @@ int tg_env_playout(int n, void* states, int64_t G, int plies, int max_step, uint
 /* board.cc:1166-1271: float32[B][C][n][n] -> float32[B][cuts][C][sub][sub] */
 int tg_sub_encode(int n, const float* enc, int64_t B, int channels, int sub, int cuts, float* out, void* stream);
 
+/* ---------------------------------------------------------------- (3) batched MCTS (self_play.py: WP_MCTS :575-875)
+ *
+ * G independent searches, one per game, advanced in lock-step "waves" exactly like WP_MCTS.run (self_play.py:607-654):
+ * up to `readouts` leaves per game are selected one after another (PUCT + variance bonus + ongoing-simulation counts,
+ * :706-725, :767-774), terminal leaves are scored and backed up at once (:638-642), the remaining leaves are encoded
+ * straight into the net's input tensor, and after the net ran they are expanded and backed up (:727-764).
+ * The tree is a per-game arena in the caller-provided workspace (device memory): 16-byte "hot" edge records
+ * {prior f32, W f32, var f32, N:16|ons:7|action:9} scanned with 128-bit loads, 8-byte "cold" records {mean f32, child},
+ * and node records {state, edge base, edge count}.  Re-rooting keeps the chosen subtree (self_play.py:857-860) by
+ * compacting it into the arena's other half.
+ *
+ * The library is stateless: every call takes the same TgMctsConfig and workspace pointer.  All other pointers are
+ * device pointers owned by the caller (PyTorch tensors).  Calls on one stream are ordered; nothing synchronises.
+ */
+typedef struct TgMctsConfig {
+    int32_t  n;                 /* board size: 9 or 19 */
+    int32_t  num_games;         /* G */
+    int32_t  readouts;          /* configure.py:33 parallel_readouts (leaves per wave and game), <= 8 */
+    int32_t  num_simulation;    /* configure.py:29 */
+    int32_t  wu_loss;           /* configure.py:32 */
+    int32_t  max_step;          /* environment.py:37 */
+    int32_t  node_cap;          /* expanded nodes per game and arena half */
+    int32_t  edge_cap;          /* edges per game and arena half */
+    int32_t  max_depth;         /* longest recorded path (edges) */
+    int32_t  tie_mode;          /* 0: first maximal child in ascending action order; 1: hashed draw (see tg_mcts_select) */
+    double   c_puct1;           /* configure.py:26 */
+    double   c_puct2;           /* configure.py:27 */
+    float    komi;              /* environment.py:38 */
+    int32_t  reserved0;
+    uint64_t tie_seed;          /* hashed tie-break: index = (mix32(tie_seed, game_id0 + g, tie_counter++) * n_ties) >> 32 */
+    int64_t  game_id0;          /* global id of game 0 of this shard (multi-GPU: identical results for any sharding) */
+} TgMctsConfig;
+
+/* per-game status bits reported by tg_mcts_status */
+#define TG_MCTS_ACTIVE        1u    /* game not finished */
+#define TG_MCTS_NEED_EXPAND   2u    /* root has no children yet (new game, or re-rooted onto an unexpanded child) */
+#define TG_MCTS_NOISY         4u    /* root priors carry Dirichlet noise (float64, self_play.py:90-95) */
+#define TG_MCTS_ERR_NODES    16u    /* arena overflow: raise node_cap */
+#define TG_MCTS_ERR_EDGES    32u    /* arena overflow: raise edge_cap */
+#define TG_MCTS_ERR_DEPTH    64u    /* path longer than max_depth */
+#define TG_MCTS_ERR_COUNT   128u    /* visit count above 65535 */
+#define TG_MCTS_ERR_ANY     (16u | 32u | 64u | 128u)
+
+int64_t tg_mcts_workspace_bytes(const TgMctsConfig* cfg);
+/* every game: empty board, empty tree, ACTIVE | NEED_EXPAND (WP_MCTS.reset_root before the net call, :595-597) */
+int tg_mcts_init(const TgMctsConfig* cfg, void* ws, void* stream);
+/* re-initialise the games whose mask byte is non-zero (start the next self-play game in that slot) */
+int tg_mcts_reset_games(const TgMctsConfig* cfg, void* ws, const uint8_t* mask, void* stream);
+/* encode10 of every root state -> obs_root float32 [G][10][n][n] (computeValuePolicy([root.state]), :598) */
+int tg_mcts_root_obs(const TgMctsConfig* cfg, void* ws, float* obs_root, void* stream);
+/* expand roots flagged NEED_EXPAND with the RAW policy over legal actions and W = -value (:599-605, :862-870) */
+int tg_mcts_root_expand(const TgMctsConfig* cfg, void* ws, const float* policy_root /*[G][A]*/,
+                        const float* value_root /*[G]*/, void* stream);
+/* start of get_action_probs (:657-663): noise float64 [G][A] in root-edge order (first K entries used per game; NULL = no
+ * noise, is_selfplay False); records N0 = root visits so far */
+int tg_mcts_begin_move(const TgMctsConfig* cfg, void* ws, const double* noise, void* stream);
+/* wave, first half: selection + terminal backups + leaf step/legal/encode.  obs float32 [G*readouts][10][n][n];
+ * rows of unused slots are left untouched. */
+int tg_mcts_wave_begin(const TgMctsConfig* cfg, void* ws, float* obs, void* stream);
+/* wave, second half: policy float32 [G*readouts][A] (softmaxed, model.py:111), value float32 [G*readouts];
+ * pending (may be NULL) receives the number of active games still below N0 + num_simulation */
+int tg_mcts_wave_end(const TgMctsConfig* cfg, void* ws, const float* policy, const float* value, int32_t* pending,
+                     void* stream);
+/* root statistics in ACTION order, zero where the action has no edge.  Any pointer may be NULL.
+ *   counts i32 [G][A]  (:666)   W f32 [G][A]   var f32 [G][A]   prior f32 [G][A]   root_n i32 [G] = root total_visit_count
+ *   root_k i32 [G] = number of root edges   step i32 [G] = getStep(root.state) */
+int tg_mcts_root_stats(const TgMctsConfig* cfg, void* ws, int32_t* counts, float* W, float* var, float* prior,
+                       int32_t* root_n, int32_t* root_k, int32_t* step, void* stream);
+/* update_with_action (:857-872): play actions int16 [G] on the root states, re-root onto the chosen child keeping its
+ * subtree; done_out u8 [G] as returned by env.step.  Finished / inactive games are left alone. */
+int tg_mcts_advance(const TgMctsConfig* cfg, void* ws, const int16_t* actions, uint8_t* done_out, void* stream);
+/* status u32 [G] (TG_MCTS_* bits), sims u64 [1] += simulations (net-evaluated leaves + terminal backups) since last call;
+ * either may be NULL */
+int tg_mcts_status(const TgMctsConfig* cfg, void* ws, uint32_t* status, unsigned long long* sims, void* stream);
+/* root game states as a batch in the layout of section (2): returns the device pointer inside the workspace */
+void* tg_mcts_root_states(const TgMctsConfig* cfg, void* ws);
+/* final labels of finished games (self_play.py:931-937): winner u8 [G] (1|2), score f32 [G], territory f32 [G][P] */
+int tg_mcts_outcome(const TgMctsConfig* cfg, void* ws, uint8_t* winner, float* score, float* territory, void* stream);
+/* a device-side synthetic policy/value provider for tree-only throughput runs (bench.py): policy[row] = normalised
+ * heavy-tailed hash weights of (seed, row, wave), value in (-1, 1).  NOT the reference net. */
+int tg_synth_provider(int n, int64_t rows, uint64_t seed, uint64_t wave, float* policy, float* value, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -26,19 +26,37 @@ def mix32(seed, a, b):
     return z >> 32
 
 
+def _mix32_vec(seed, a, b):
+    with np.errstate(over="ignore"):
+        z = (np.uint64(seed & _M64) + np.uint64(a & _M64) * np.uint64(0x9E3779B97F4A7C15)
+             + np.asarray(b, dtype=np.uint64) * np.uint64(0xBF58476D1CE4E5B9))
+        z ^= z >> np.uint64(30); z *= np.uint64(0xBF58476D1CE4E5B9)
+        z ^= z >> np.uint64(27); z *= np.uint64(0x94D049BB133111EB)
+        z ^= z >> np.uint64(31)
+    return z >> np.uint64(32)
+
+
+_CACHE = {}
+
+
 def synth_eval(obs, seed=1234, sharp=3):
     """obs: float32 [10, n, n] (values 0/1).  Returns (policy float32 [A] summing to ~1, value float32 in (-1, 1))."""
     obs = np.ascontiguousarray(obs, dtype=np.float32)
     A = obs.shape[-1] * obs.shape[-2] + 1
     h = zlib.crc32(np.packbits(obs.astype(np.uint8)).tobytes())
-    w = np.empty(A, dtype=np.int64)
-    for a in range(A):
-        r = mix32(seed, h, a) & 0xFFFF            # 16 bits
-        w[a] = 1 + ((r ** sharp) >> (16 * (sharp - 1)))   # heavy-tailed integer weight in [1, 65536]
+    key = (h, A, seed, sharp)
+    hit = _CACHE.get(key)
+    if hit is not None:
+        return hit
+    r = (_mix32_vec(seed, h, np.arange(A)) & np.uint64(0xFFFF)).astype(object)     # 16 bits, python ints from here
+    w = np.array([1 + ((int(x) ** sharp) >> (16 * (sharp - 1))) for x in r], dtype=np.int64)   # heavy-tailed weights in [1, 65536]
     total = np.float32(int(w.sum()))
     policy = w.astype(np.float32) / total          # one correctly-rounded f32 division per entry
     v = (mix32(seed ^ 0x5555, h, 977) & 0xFFFF) - 32768
     value = np.float32(v) / np.float32(32768 + 64)
+    if len(_CACHE) > 200000:
+        _CACHE.clear()
+    _CACHE[key] = (policy, value)
     return policy, value
 
 

@@ -1,0 +1,220 @@
+"""GPU parity tests of the MCTS kernels, through the C ABI (tg_mcts_* in include/transgo_b200.h).
+
+Checker = oracle/mcts_oracle.py (numpy restatement pinned bit-exact to the reference WP_MCTS by tests/test_oracle_mcts.py)
+and tests/golden/mcts_trace_9.npz produced by the reference itself.  Bar (BASELINE.json north_star): visit counts
+bit-exact given identical net outputs, Dirichlet noise and tie-break order; W / var within 1e-5 relative (fp32).
+"""
+import numpy as np
+import pytest
+
+from helpers import load_mcts_golden, mcts_golden_games, check_mcts_move_against_golden
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+def cpu_provider(seed, sharp):
+    """The deterministic stand-in net (oracle/provider.py) evaluated on the host: identical bits on every arm."""
+    from oracle import provider
+
+    def evaluator(obs):
+        p, v = provider.synth_eval_batch(obs.cpu().numpy(), seed=seed, sharp=sharp)
+        return torch.from_numpy(p).cuda(), torch.from_numpy(v).cuda()
+    return evaluator
+
+
+def make_oracles(G, n, sims, seed, sharp, game_id0=0, max_step=None, tie="hash", readouts=4):
+    from oracle import provider
+    from oracle.go_oracle import OracleEnv
+    from oracle.mcts_oracle import OracleMCTS, MCTSConfig
+    out = []
+    for g in range(G):
+        gid = game_id0 + g
+        cnt = [0]
+
+        def tie_fn(k, gid=gid, cnt=cnt):
+            if tie != "hash":
+                return 0
+            i = provider.tie_index(seed, gid, cnt[0], k)
+            cnt[0] += 1
+            return i
+        out.append(OracleMCTS(OracleEnv(n, max_step=max_step), lambda o: provider.synth_eval_batch(o, seed=seed, sharp=sharp),
+                              MCTSConfig(board_size=n, num_simulation=sims, parallel_readouts=readouts), tie_fn=tie_fn,
+                              noise_fn=lambda m, k, gid=gid: provider.dirichlet(seed, gid, m, k),
+                              u_fn=lambda m, gid=gid: provider.uniform(seed, gid, m)))
+    return out
+
+
+def compare_batch(eng, oracles, seed, moves, game_id0=0, selfplay=True):
+    """Plays `moves` moves on both sides with identical injected randomness and compares every observable."""
+    from oracle import provider
+    G, A = eng.G, eng.A
+    alive = [True] * G
+    for move in range(moves):
+        noise = np.zeros([G, A])
+        for g in range(G):
+            if alive[g]:
+                k = len(oracles[g].root.acts)
+                noise[g, :k] = provider.dirichlet(seed, game_id0 + g, oracles[g].move_idx, k)
+        u = torch.tensor([provider.uniform(seed, game_id0 + g, oracles[g].move_idx) for g in range(G)], dtype=torch.float64).cuda()
+        actions, pi, obs = eng.get_action_probs(selfplay, noise=torch.from_numpy(noise).cuda() if selfplay else None, u=u)
+        counts, W, var, prior = eng.root_stats(full=True)
+        counts, W, var = counts.cpu().numpy(), W.cpu().numpy(), var.cpu().numpy()
+        root_n = eng.root_n.cpu().numpy()
+        pi, obs, actions = pi.cpu().numpy(), obs.cpu().numpy(), actions.cpu().numpy()
+        for g in range(G):
+            if not alive[g]:
+                continue
+            o = oracles[g]
+            a, opi, oobs = o.get_action_probs(selfplay)
+            acts, N, oW, ovar, _ = o.root_children()
+            assert np.array_equal(counts[g], o.visit_counts()), ("visit counts", move, g)          # bit-exact
+            assert root_n[g] == o.rootN, ("root N", move, g)
+            np.testing.assert_allclose(W[g][acts], oW, rtol=1e-5, atol=1e-6)                          # north_star tolerance
+            np.testing.assert_allclose(var[g][acts], ovar, rtol=1e-5, atol=1e-6)
+            assert np.array_equal(W[g][acts], oW) and np.array_equal(var[g][acts], ovar), "fp32 statistics are expected to be bit-equal"
+            assert np.array_equal(pi[g], opi), ("pi", move, g)
+            assert np.array_equal(obs[g], oobs), ("root obs", move, g)
+            assert int(actions[g]) == a, ("sampled action", move, g)
+        done = eng.update_with_action(torch.from_numpy(actions).cuda()).cpu().numpy()
+        for g in range(G):
+            if alive[g]:
+                d = oracles[g].update_with_action(int(actions[g]))
+                assert bool(done[g]) == d, ("done", move, g)
+                alive[g] = not d
+        if not any(alive):
+            break
+    return alive
+
+
+@pytest.mark.parametrize("which", [0, 1, 2, 3])
+def test_reference_golden_trace(oracle_built, which):
+    """The reference WP_MCTS's own recorded games: counts / W / var / pi / action / done per move."""
+    from transgo_b200.mcts import BatchedMCTS
+    t = load_mcts_golden()
+    game, sims, sharp, rows = list(mcts_golden_games(t))[which]
+    seed = int(t["seed"])
+    eng = BatchedMCTS(cpu_provider(seed, sharp), 1, num_simulation=sims, tie_mode="hash", tie_seed=seed, game_id0=game)
+    for row in rows:
+        noise = torch.from_numpy(t["noise"][row][None, :].copy()).cuda()
+        u = torch.tensor([float(t["u"][row])], dtype=torch.float64).cuda()
+        actions, pi, _ = eng.get_action_probs(True, noise=noise, u=u)
+        counts, W, var, _ = eng.root_stats(full=True)
+        acts = np.nonzero(eng.root_stats(full=True)[3][0].cpu().numpy() > -1)[0]    # all actions; zeros where no edge
+        done = eng.update_with_action(actions)
+        check_mcts_move_against_golden(t, row, acts, counts[0].cpu().numpy()[acts], W[0].cpu().numpy()[acts],
+                                       var[0].cpu().numpy()[acts], int(actions[0].item()), pi[0].cpu().numpy(),
+                                       bool(done[0].item()))
+        if bool(done[0].item()):
+            break
+
+
+@pytest.mark.parametrize("G,sims,sharp,moves", [(8, 48, 4, 12), (4, 210, 3, 3), (6, 32, 9, 30)])
+def test_batched_search_matches_oracle(oracle_built, G, sims, sharp, moves):
+    from transgo_b200.mcts import BatchedMCTS
+    seed = 100 + sims
+    eng = BatchedMCTS(cpu_provider(seed, sharp), G, num_simulation=sims, tie_mode="hash", tie_seed=seed)
+    compare_batch(eng, make_oracles(G, 9, sims, seed, sharp), seed, moves)
+
+
+def test_terminal_heavy_games_and_first_tiebreak(oracle_built):
+    """Short games (max_step 14) force terminal leaves (scored and backed up at once, self_play.py:638-642), the
+    failsafe of 2*readouts attempts, PASS-only nodes and the game-over path; tie_mode 'first' is the other rule."""
+    from transgo_b200.mcts import BatchedMCTS
+    seed, G, sims = 31, 6, 40
+    eng = BatchedMCTS(cpu_provider(seed, 6), G, num_simulation=sims, max_step=14, tie_mode="first")
+    alive = compare_batch(eng, make_oracles(G, 9, sims, seed, 6, max_step=14, tie="first"), seed, 20)
+    assert not any(alive)                                      # every game reached its end on both sides
+    st = eng.check_status()
+    assert not (st & 1).any()
+
+
+def test_game_id_offset_gives_identical_games(oracle_built):
+    """Multi-GPU rule: a shard starting at game_id0 plays exactly the games of the full batch."""
+    from transgo_b200.mcts import BatchedMCTS
+    seed, sims = 7, 24
+    full = BatchedMCTS(cpu_provider(seed, 5), 4, num_simulation=sims, tie_seed=seed)
+    shard = BatchedMCTS(cpu_provider(seed, 5), 2, num_simulation=sims, tie_seed=seed, game_id0=2)
+    compare_batch(shard, make_oracles(2, 9, sims, seed, 5, game_id0=2), seed, 4, game_id0=2)
+    compare_batch(full, make_oracles(4, 9, sims, seed, 5), seed, 4)
+
+
+def test_wp_mcts_facade_has_the_reference_surface(oracle_built):
+    """self_play.py:906-926 call sequence on the G = 1 facade, with a model object exposing main_prediction."""
+    from oracle import provider
+    from oracle.go_oracle import OracleEnv
+    from oracle.mcts_oracle import OracleMCTS, MCTSConfig
+    from transgo_b200.environment import GoEnv
+    from transgo_b200.mcts import WP_MCTS
+    seed = 3
+
+    class Model:
+        def main_prediction(self, x):
+            p, v = provider.synth_eval_batch(x.cpu().numpy(), seed=seed, sharp=5)
+            return torch.from_numpy(p).cuda(), torch.from_numpy(v).cuda(), torch.zeros(len(p), 81).cuda()
+
+    class Cfg:
+        board_size, num_simulation, c_puct1, c_puct2, wu_loss, parallel_readouts = 9, 30, 3, 0.05, 2, 4
+    env = GoEnv(Cfg())
+    agent = WP_MCTS(Cfg(), env, Model(), None, tie_mode="first")
+    assert str(agent) == "WP_MCTS" and env.getStep(agent.root.state) == 1
+    # evaluation mode (no noise, temperature 0.12) is deterministic up to the move draw -> compare visit counts
+    ora = OracleMCTS(OracleEnv(9), lambda o: provider.synth_eval_batch(o, seed=seed, sharp=5), MCTSConfig(num_simulation=30),
+                     u_fn=lambda m: 0.5)
+    a, pi, obs = agent.get_action_probs(is_selfplay=False)
+    oa, opi, oobs = ora.get_action_probs(is_selfplay=False, forced_action=a)
+    assert np.array_equal(pi, opi) and np.array_equal(obs, oobs) and pi.shape == (82,) and obs.shape == (10, 9, 9)
+    assert agent.update_with_action(a) is False and ora.update_with_action(a) is False
+    assert env.getStep(agent.root.state) == 2
+    # select_action(state) (self_play.py:689-704) searches from an arbitrary position
+    s, _ = env.reset()
+    for mv in (40, 41, 31):
+        s, _ = env.step(s, mv)
+    act = agent.select_action(s)
+    assert 0 <= act <= 81 and env.checkAction(s, act if act != 81 else -1)
+
+
+def test_19x19_search_matches_oracle(oracle_built):
+    from transgo_b200.mcts import BatchedMCTS
+    seed, G, sims = 19, 2, 24
+    eng = BatchedMCTS(cpu_provider(seed, 4), G, board_size=19, num_simulation=sims, tie_seed=seed)
+    compare_batch(eng, make_oracles(G, 19, sims, seed, 4), seed, 3)
+
+
+def test_full_size_invariants_with_device_provider():
+    """BASELINE C3 size (1024 games x 800 simulations per move) with the device-side synthetic provider: properties
+    that hold for any net -- per-game budget met, child visits sum to the root's, arena never overflows, and the run is
+    reproducible bit for bit."""
+    from transgo_b200 import _lib
+    from transgo_b200.mcts import BatchedMCTS
+    G, sims = 1024, 800
+    L = _lib.lib()
+
+    def run():
+        wave = [0]
+
+        def evaluator(obs):
+            B = obs.shape[0]
+            p = torch.empty([B, 82], dtype=torch.float32, device="cuda")
+            v = torch.empty([B], dtype=torch.float32, device="cuda")
+            _lib.check(L.tg_synth_provider(9, B, 12345, wave[0], _lib.ptr(p), _lib.ptr(v), _lib.stream_ptr()))
+            wave[0] += 1
+            return p, v
+        eng = BatchedMCTS(evaluator, G, num_simulation=sims, tie_seed=1)
+        g = torch.Generator(device="cuda"); g.manual_seed(5)
+        noise = eng.make_noise(generator=g)
+        u = torch.rand([G], dtype=torch.float64, device="cuda", generator=g)
+        actions, pi, _ = eng.get_action_probs(True, noise=noise, u=u)
+        counts = eng.counts.clone(); rootn = eng.root_n.clone()
+        eng.update_with_action(actions)
+        nsims = eng.total_sims()
+        return counts, rootn, actions, pi, nsims
+    c1, n1, a1, pi1, s1 = run()
+    c2, n2, a2, pi2, s2 = run()
+    assert torch.equal(c1, c2) and torch.equal(n1, n2) and torch.equal(a1, a2) and s1 == s2
+    assert bool((n1 >= sims).all()) and bool((n1 <= sims + 3).all())       # the last wave may overshoot by readouts-1
+    assert bool((c1.sum(1) == n1).all())                                    # fresh roots: every backup passes one child
+    assert s1 == int(n1.sum().item())
+    assert bool((pi1.sum(1) - 1).abs().max() < 1e-12)
+    assert bool((c1.gather(1, a1.long()[:, None]) >= 2).all())             # counts of 1 are zeroed before sampling (:668)

@@ -480,19 +480,23 @@ __device__ __forceinline__ int area_score(const BB<N>& black, const BB<N>& white
 
 // The ten feature planes of encode10 (board_feature.cc:213-223) as bitboards, from the view of the player to move.
 template <int N, int T>
-__device__ __forceinline__ void feature_planes(const Pos<N>& s, BB<N>* pl /*[10]*/) {
+__device__ __forceinline__ void feature_planes_g(const Pos<N>& s, BB<N>* pl /*[10]*/, Groups<N>& g) {
     const int me = s.player, op = 3 - s.player;
-    Groups<N> g;
     analyse_groups<N, T, true>(s.stones[0], s.stones[1], s.player, g);
     const BB<N> own = stones_of(s, me), opp = stones_of(s, op);
     const BB<N> l1me = l1_of(g, me), l1op = l1_of(g, op), l2me = l2_of(g, me), l2op = l2_of(g, op);
     pl[0] = l1me; pl[1] = l2me; pl[2] = andn(andn(own, l1me), l2me);       // getLibertyMap3 :17-41
     pl[3] = l1op; pl[4] = l2op; pl[5] = andn(andn(opp, l1op), l2op);
     pl[6] = (s.last1 >= 0 && s.last1 < Geo<N>::P) ? bb_point<N>(s.last1) : bb_zero<N>();  // getHistoryMap1 :92-100
-    pl[7] = suicide_points(own, opp, l1me, l1op);                                   // getSimpleKoAndSuicide :69-89
+    pl[7] = suicide_points(own, opp, l1me, l1op);                                           // getSimpleKoAndSuicide :69-89
     if (s.ko_age == 0 && s.ko_loc >= 0 && s.ko_loc < Geo<N>::P) pl[7] = pl[7] | bb_point<N>(s.ko_loc);   // colour ignored (board.cc:205-213)
     pl[8] = true_eyes(own, opp);                                                            // getTrueEyeMap :142-161
     pl[9] = g.lives;                                                                        // getBlockLives :164-182
+}
+template <int N, int T>
+__device__ __forceinline__ void feature_planes(const Pos<N>& s, BB<N>* pl /*[10]*/) {
+    Groups<N> g;
+    feature_planes_g<N, T>(s, pl, g);
 }
 
 // deterministic per-(seed, game, ply) 32-bit draw shared with the CPU checkers (tests mirror it in numpy)

@@ -42,22 +42,26 @@ template <int N, int T> __device__ __forceinline__ void planes_to_smem(const BB<
     }
 }
 
-// ngames * PLANE_BITS floats are written by the whole CTA.  `out` is 4-byte aligned at least; up to three leading
-// floats are peeled so that the bulk goes out as aligned 128-bit stores.
-template <int N> __device__ __forceinline__ void planes_smem_to_global(const uint32_t* sm, float* __restrict__ out, int ngames) {
+// ngames * PLANE_BITS floats are written by `nthreads` cooperating threads (a CTA or one warp), thread `tid` of them.
+// `out` is 4-byte aligned at least; up to three leading floats are peeled so that the bulk goes out as aligned
+// 128-bit stores.
+template <int N> __device__ __forceinline__ void planes_smem_to_global_part(const uint32_t* sm, float* __restrict__ out, int ngames, int tid, int nthreads) {
     const int total = ngames * Geo<N>::PLANE_BITS;
     int head = (int)(((16u - (unsigned)(reinterpret_cast<uintptr_t>(out) & 15u)) & 15u) >> 2);
     head = head < total ? head : total;
     const int quads = (total - head) >> 2;
     float4* o4 = reinterpret_cast<float4*>(out + head);
-    for (int f = threadIdx.x; f < quads; f += blockDim.x) {
+    for (int f = tid; f < quads; f += nthreads) {
         const int bit = head + 4 * f;
         const uint32_t nib = __funnelshift_r(sm[bit >> 5], sm[(bit >> 5) + 1], bit & 31) & 15u;
         o4[f] = make_float4((float)(nib & 1u), (float)((nib >> 1) & 1u), (float)((nib >> 2) & 1u), (float)((nib >> 3) & 1u));
     }
-    if ((int)threadIdx.x < head) out[threadIdx.x] = (float)((sm[0] >> threadIdx.x) & 1u);
-    const int e = head + (quads << 2) + (int)threadIdx.x;
+    if (tid < head) out[tid] = (float)((sm[0] >> tid) & 1u);
+    const int e = head + (quads << 2) + tid;
     if (e < total) out[e] = (float)((sm[e >> 5] >> (e & 31)) & 1u);
+}
+template <int N> __device__ __forceinline__ void planes_smem_to_global(const uint32_t* sm, float* __restrict__ out, int ngames) {
+    planes_smem_to_global_part<N>(sm, out, ngames, (int)threadIdx.x, (int)blockDim.x);
 }
 
 }  // namespace tg

@@ -1,0 +1,752 @@
+// tg_mcts.cu -- batched MCTS kernels (one warp per game) + the tg_mcts_* C ABI of include/transgo_b200.h.
+// Replaces the pure-Python tree search self_play.py: Node_V :51-96 and WP_MCTS :575-875.
+//
+// Arithmetic contract (SURVEY.md 8a-3 dtype ledger, numpy 2.x semantics of the reference): every float operation is an
+// explicit round-to-nearest intrinsic in the reference's order and width; the file is also built with -fmad=false.
+#include <cstdio>
+#include "../../include/transgo_b200.h"
+#include "tg_board.cuh"
+#include "tg_common.cuh"
+
+namespace tg {
+
+enum { H_BUF = 0, H_NNODES, H_NEDGES, H_ROOTN, H_ROOTONS, H_ROOTW, H_ROOTMEAN, H_ROOTVAR, H_TIE, H_N0, H_MOVE, H_FLAGS,
+       H_NPATHS, H_SIMS, H_SPARE0, H_SPARE1, H_WORDS };
+constexpr unsigned kErrAction = 256u;
+constexpr int kMaxReadouts = 8;
+
+// hot.w : N[31:16] | ons[15:9] | action[8:0]
+__device__ __forceinline__ int pk_n(uint32_t p) { return (int)(p >> 16); }
+__device__ __forceinline__ int pk_ons(uint32_t p) { return (int)((p >> 9) & 127u); }
+__device__ __forceinline__ int pk_act(uint32_t p) { return (int)(p & 511u); }
+
+struct View {
+    // config
+    int G, R, num_sim, wu, max_step, NC, EC, MAXD, tie_mode;
+    double c1, c2;
+    float komi;
+    unsigned long long tie_seed;
+    long long game_id0;
+    // workspace
+    int* hdr;               // [G][H_WORDS]
+    uint4* root_state;      // [SQ][G]
+    double* root_prior64;   // [G][A]
+    uint4* hot;             // [2][G][EC]
+    uint2* cold;            // [2][G][EC]
+    uint4* nodes;           // [2][G][NC][SQ+1]
+    int* paths;             // [G][R][MAXD]
+    int* path_len;          // [G][R]
+    int* leaf_parent;       // [G][R]
+    int* leaf_action;       // [G][R]
+    uint4* leaf_state;      // [SQ][G*R]
+    uint32_t* leaf_legal;   // [G*R][LW]
+    size_t total_bytes;
+};
+
+static inline size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
+
+template <int N>
+static View make_view(const TgMctsConfig* c, void* ws) {
+    using GG = Geo<N>;
+    View v{};
+    v.G = c->num_games; v.R = c->readouts; v.num_sim = c->num_simulation; v.wu = c->wu_loss; v.max_step = c->max_step;
+    v.NC = c->node_cap; v.EC = c->edge_cap; v.MAXD = c->max_depth; v.tie_mode = c->tie_mode;
+    v.c1 = c->c_puct1; v.c2 = c->c_puct2; v.komi = c->komi; v.tie_seed = c->tie_seed; v.game_id0 = c->game_id0;
+    char* p = (char*)ws; size_t off = 0;
+    auto take = [&](size_t bytes) { char* q = p ? p + off : nullptr; off += align_up(bytes); return q; };
+    const size_t G = v.G, R = v.R;
+    v.hdr = (int*)take(G * H_WORDS * 4);
+    v.root_state = (uint4*)take(G * GG::SQ * 16);
+    v.root_prior64 = (double*)take(G * GG::A * 8);
+    v.hot = (uint4*)take(2 * G * (size_t)v.EC * 16);
+    v.cold = (uint2*)take(2 * G * (size_t)v.EC * 8);
+    v.nodes = (uint4*)take(2 * G * (size_t)v.NC * (GG::SQ + 1) * 16);
+    v.paths = (int*)take(G * R * (size_t)v.MAXD * 4);
+    v.path_len = (int*)take(G * R * 4);
+    v.leaf_parent = (int*)take(G * R * 4);
+    v.leaf_action = (int*)take(G * R * 4);
+    v.leaf_state = (uint4*)take(G * R * GG::SQ * 16);
+    v.leaf_legal = (uint32_t*)take(G * R * GG::DQ * 16);
+    v.total_bytes = off;
+    return v;
+}
+
+template <int N> __device__ __forceinline__ uint4* hot_of(const View& v, int buf, int g) { return v.hot + ((size_t)buf * v.G + g) * v.EC; }
+template <int N> __device__ __forceinline__ uint2* cold_of(const View& v, int buf, int g) { return v.cold + ((size_t)buf * v.G + g) * v.EC; }
+template <int N> __device__ __forceinline__ uint4* nodes_of(const View& v, int buf, int g) { return v.nodes + ((size_t)buf * v.G + g) * v.NC * (Geo<N>::SQ + 1); }
+
+__device__ __forceinline__ double warp_max(double x) {
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+        double y = __shfl_xor_sync(0xffffffffu, x, s);
+        x = y > x ? y : x;
+    }
+    return x;
+}
+
+// value backup along a recorded path (self_play.py:758-764 + Node_V.value_mean_var :84-88); lane-parallel: edge i of a
+// path of `len` edges receives v * (-1)^(len-1-i), the root itself v * (-1)^len.
+template <int N>
+__device__ __forceinline__ void backup(const View& v, int* h, uint4* hot, uint2* cold, const int* path, int len, float value, unsigned& err) {
+    const int lane = threadIdx.x & 31;
+    for (int i = lane; i <= len; i += 32) {
+        const float sv = ((len - 1 - i) & 1) ? -value : value;       // i == len -> (-1)^(-1) handled below
+        if (i == len) {
+            const float rv = (len & 1) ? -value : value;
+            const float W = __fadd_rn(__int_as_float(h[H_ROOTW]), rv);
+            const int n = h[H_ROOTN] + 1;
+            const float t = __int_as_float(h[H_ROOTMEAN]);
+            const float mean = __fdiv_rn(W, (float)(n + 1));
+            const float var = __fadd_rn(__int_as_float(h[H_ROOTVAR]), __fmul_rn(__fsub_rn(rv, t), __fsub_rn(rv, mean)));
+            h[H_ROOTW] = __float_as_int(W); h[H_ROOTN] = n; h[H_ROOTMEAN] = __float_as_int(mean); h[H_ROOTVAR] = __float_as_int(var);
+        } else {
+            const int e = path[i];
+            uint4 q = hot[e];
+            uint2 c = cold[e];
+            const float W = __fadd_rn(__uint_as_float(q.y), sv);
+            const int n = pk_n(q.w) + 1;
+            if (n > 65535) err |= TG_MCTS_ERR_COUNT;
+            const float t = __uint_as_float(c.x);
+            const float mean = __fdiv_rn(W, (float)(n + 1));
+            const float var = __fadd_rn(__uint_as_float(q.z), __fmul_rn(__fsub_rn(sv, t), __fsub_rn(sv, mean)));
+            q.y = __float_as_uint(W); q.z = __float_as_uint(var); q.w += (1u << 16);
+            c.x = __float_as_uint(mean);
+            hot[e] = q; cold[e] = c;
+        }
+    }
+    __syncwarp();
+}
+
+// ons += d * wu_loss on every node of the path, root included (self_play.py:767-774)
+__device__ __forceinline__ void add_ons(int* h, uint4* hot, const int* path, int len, int d) {
+    const int lane = threadIdx.x & 31;
+    for (int i = lane; i <= len; i += 32) {
+        if (i == len) h[H_ROOTONS] += d;
+        else {
+            uint32_t* w = &reinterpret_cast<uint32_t*>(hot + path[i])[3];
+            *w = (uint32_t)((int)*w + d * 512);
+        }
+    }
+    __syncwarp();
+}
+
+// ---------------------------------------------------------------------------------------------- selection
+template <int N>
+__global__ void __launch_bounds__(kThreads) k_select(View v) {
+    using GG = Geo<N>;
+    constexpr int MAXR = (GG::A + 31) / 32;
+    const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (g >= v.G) return;
+    int* h = v.hdr + (size_t)g * H_WORDS;
+    const unsigned flags = (unsigned)h[H_FLAGS];
+    const bool run = (flags & TG_MCTS_ACTIVE) && !(flags & (TG_MCTS_NEED_EXPAND | TG_MCTS_ERR_ANY | kErrAction)) &&
+                     h[H_ROOTN] < h[H_N0] + v.num_sim;
+    if (!run) { if (lane == 0) h[H_NPATHS] = 0; return; }
+    const int buf = h[H_BUF];
+    uint4* hot = hot_of<N>(v, buf, g);
+    uint2* cold = cold_of<N>(v, buf, g);
+    const uint4* nodes = nodes_of<N>(v, buf, g);
+    const double* p64 = v.root_prior64 + (size_t)g * GG::A;
+    const bool noisy = (flags & TG_MCTS_NOISY) != 0;
+    const float c1f = (float)v.c1, c2f = (float)v.c2;
+    int npaths = 0, tie = h[H_TIE], sims = 0;
+    unsigned err = 0;
+    for (int attempt = 0; attempt < 2 * v.R && npaths < v.R && !err; ++attempt) {      // self_play.py:616-619
+        int* path = v.paths + ((size_t)g * v.R + npaths) * v.MAXD;
+        int node = 0, depth = 0;
+        int Np = h[H_ROOTN], onsp = h[H_ROOTONS];
+        uint32_t pk_sel = 0;
+        while (true) {                                                                // :623-627
+            const uint4 info = nodes[(size_t)node * (GG::SQ + 1) + GG::SQ];
+            const int eb = (int)info.x, K = (int)info.y;
+            const double sq = __dsqrt_rn((double)(Np + onsp));
+            double sc[MAXR]; uint32_t pk[MAXR];
+            double best = -1.0e300;
+#pragma unroll
+            for (int r = 0; r < MAXR; ++r) {
+                const int k = lane + 32 * r;
+                sc[r] = -1.0e300; pk[r] = 0;
+                if (k < K) {
+                    const uint4 q = hot[eb + k];
+                    const float prior = __uint_as_float(q.x), W = __uint_as_float(q.y), var = __uint_as_float(q.z);
+                    const int nc = pk_n(q.w), oc = pk_ons(q.w);
+                    // prior_score = c1 * prior * sqrt(Np + ons_p) / (Nc + ons_c + 1)          (:718-719)
+                    double ps = (noisy && node == 0) ? __dmul_rn(v.c1, p64[k]) : (double)__fmul_rn(c1f, prior);
+                    ps = __ddiv_rn(__dmul_rn(ps, sq), (double)(nc + oc + 1));
+                    // var_score = c2 * sqrt(1 + clip(var, 0, 3)); float64 for a never-visited child      (:721-722)
+                    double vs;
+                    if (nc == 0) vs = v.c2;
+                    else {
+                        const float cv = var < 0.0f ? 0.0f : (var > 3.0f ? 3.0f : var);
+                        vs = (double)__fmul_rn(c2f, __fsqrt_rn(__fadd_rn(1.0f, cv)));
+                    }
+                    const double qv = (double)(-__fdiv_rn(W, (float)(nc + 1)));                 // -child.value() (:724, :67-68)
+                    sc[r] = __dadd_rn(__dadd_rn(ps, vs), qv);
+                    pk[r] = q.w;
+                }
+                best = sc[r] > best ? sc[r] : best;
+            }
+            best = warp_max(best);
+            // exact ties, ascending action order (:708-713)
+            unsigned bal[MAXR]; int total = 0;
+#pragma unroll
+            for (int r = 0; r < MAXR; ++r) { bal[r] = __ballot_sync(0xffffffffu, sc[r] == best); total += __popc(bal[r]); }
+            int j = 0;
+            if (total > 1) {
+                if (v.tie_mode == 1) j = (int)(((unsigned long long)mix32(v.tie_seed, (unsigned long long)(v.game_id0 + g), (unsigned long long)tie) * (unsigned)total) >> 32);
+                tie += 1;
+            }
+            int ksel = -1;
+#pragma unroll
+            for (int r = 0; r < MAXR; ++r) {
+                const int c = __popc(bal[r]);
+                if (ksel < 0 && j < c) {
+                    const int src = nth_bit(bal[r], j);
+                    ksel = src + 32 * r;
+                    pk_sel = __shfl_sync(0xffffffffu, pk[r], src);
+                } else if (ksel < 0) j -= c;
+            }
+            const int e = eb + ksel;
+            if (depth >= v.MAXD) { err |= TG_MCTS_ERR_DEPTH; break; }
+            if (lane == 0) path[depth] = e;
+            depth += 1;
+            const int child = (int)cold[e].y;
+            if (child < 0) break;
+            Np = pk_n(pk_sel); onsp = pk_ons(pk_sel); node = child;
+        }
+        if (err) break;
+        __syncwarp();
+        // the leaf: step from its parent's state (:629).  `done` follows from the parent's meta alone.
+        const int action = pk_act(pk_sel);
+        Pos<N> s; pos_load<N>(s, nodes + (size_t)node * (GG::SQ + 1), 0, 1, 0);
+        const int step2 = s.step + 1;
+        const bool is_pass = action == GG::P;
+        const bool done = (is_pass && s.last1 == kPass && step2 > 1) || step2 > v.max_step;
+        if (done) {                                                                   // :638-642
+            Groups<N> gr;
+            if (!is_pass) analyse_groups<N, 32, false>(s.stones[0], s.stones[1], s.player, gr);
+            else { gr.l1[0] = gr.l1[1] = gr.l2[0] = gr.l2[1] = gr.lives = bb_zero<N>(); }
+            bool acc;
+            apply_move<N, 32>(s, gr, action, v.max_step, acc);
+            BB<N> bt, wt;
+            const int raw = area_score<N, 32>(s.stones[0], s.stones[1], bt, wt);
+            const int winner = ((float)raw - v.komi) > 0.0f ? kBlack : kWhite;          // environment.py:118-119
+            const float value = (s.player == winner) ? 1.0f : -1.0f;
+            backup<N>(v, h, hot, cold, path, depth, value, err);
+            sims += 1;
+        } else {
+            if (lane == 0) {
+                const size_t slot = (size_t)g * v.R + npaths;
+                v.leaf_parent[slot] = node; v.leaf_action[slot] = action; v.path_len[slot] = depth;
+            }
+            add_ons(h, hot, path, depth, v.wu);                                        // :644
+            npaths += 1;
+        }
+    }
+    if (lane == 0) {
+        h[H_TIE] = tie; h[H_NPATHS] = npaths; h[H_SIMS] += sims;
+        if (err) h[H_FLAGS] = (int)(flags | err);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- leaves
+// One warp per leaf slot: env.step from the parent (:629), getLegalAction (:634, :737) and encode (:798) fused; the planes
+// go straight into the net's input tensor.
+template <int N>
+__global__ void __launch_bounds__(kThreads) k_leaves(View v, float* __restrict__ obs) {
+    using GG = Geo<N>;
+    extern __shared__ uint32_t sm_bits[];
+    const int slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    if (slot >= v.G * v.R) return;
+    const int g = slot / v.R, jj = slot - g * v.R;
+    const int* h = v.hdr + (size_t)g * H_WORDS;
+    if (jj >= h[H_NPATHS]) return;
+    const uint4* nodes = nodes_of<N>(v, h[H_BUF], g);
+    Pos<N> s; pos_load<N>(s, nodes + (size_t)v.leaf_parent[slot] * (GG::SQ + 1), 0, 1, 0);
+    Groups<N> gr;
+    analyse_groups<N, 32, false>(s.stones[0], s.stones[1], s.player, gr);
+    bool acc;
+    apply_move<N, 32>(s, gr, v.leaf_action[slot], v.max_step, acc);
+    BB<N> pl[10];
+    Groups<N> g2;
+    feature_planes_g<N, 32>(s, pl, g2);
+    const BB<N> lg = legal_points(s, g2);
+    constexpr int WPW = (GG::PLANE_BITS + 31) / 32 + 2;       // smem words per warp
+    uint32_t* sm = sm_bits + wib * WPW;
+    for (int i = lane; i < WPW; i += 32) sm[i] = 0;
+    __syncwarp();
+    planes_to_smem<N, 32>(pl, sm, 0);
+    __syncwarp();
+    planes_smem_to_global_part<N>(sm, obs + (size_t)slot * GG::PLANE_BITS, 1, lane, 32);
+    if (lane == 0) {
+        pos_store<N>(s, v.leaf_state, slot, (long long)v.G * v.R, 1);
+        uint32_t d[GG::DQ * 4];
+#pragma unroll
+        for (int i = 0; i < GG::DQ * 4; ++i) d[i] = 0;
+        bb_to_dense<N>(lg, d);
+        if (!any(lg)) d[GG::P >> 5] |= 1u << (GG::P & 31);
+        uint4* o = reinterpret_cast<uint4*>(v.leaf_legal) + (size_t)slot * GG::DQ;
+#pragma unroll
+        for (int k = 0; k < GG::DQ; ++k) o[k] = make_uint4(d[4 * k], d[4 * k + 1], d[4 * k + 2], d[4 * k + 3]);
+    }
+}
+
+// write one node's edges from a dense legal mask: prior_k = pol[a_k] * (renorm ? 1/scale : raw), W = w0
+// returns K; sp/sa are per-warp shared scratch of A entries.
+template <int N>
+__device__ __forceinline__ int compact_legal(const uint32_t* __restrict__ legal, const float* __restrict__ pol, float* sp, int* sa) {
+    using GG = Geo<N>;
+    constexpr int MAXR = (GG::A + 31) / 32;
+    const int lane = threadIdx.x & 31;
+    int K = 0;
+#pragma unroll
+    for (int r = 0; r < MAXR; ++r) {
+        const int a = lane + 32 * r;
+        const uint32_t word = legal[r];                           // word r holds actions 32r .. 32r+31
+        const bool on = a < GG::A && ((word >> lane) & 1u);
+        const int pos = K + __popc(word & ((1u << lane) - 1u));
+        if (on) { sp[pos] = pol[a]; sa[pos] = a; }
+        K += __popc(word);
+    }
+    __syncwarp();
+    return K;
+}
+
+// ---------------------------------------------------------------------------------------------- expansion + backup
+template <int N>
+__global__ void __launch_bounds__(kThreads) k_expand(View v, const float* __restrict__ policy, const float* __restrict__ value, int* __restrict__ pending) {
+    using GG = Geo<N>;
+    extern __shared__ uint32_t sm_raw[];
+    const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    if (g >= v.G) return;
+    float* sp = reinterpret_cast<float*>(sm_raw) + wib * 2 * GG::A;
+    int* sa = reinterpret_cast<int*>(sp + GG::A);
+    int* h = v.hdr + (size_t)g * H_WORDS;
+    unsigned flags = (unsigned)h[H_FLAGS];
+    const int npaths = h[H_NPATHS];
+    const int buf = h[H_BUF];
+    uint4* hot = hot_of<N>(v, buf, g);
+    uint2* cold = cold_of<N>(v, buf, g);
+    uint4* nodes = nodes_of<N>(v, buf, g);
+    unsigned err = 0;
+    int sims = 0;
+    int nn = h[H_NNODES], ne = h[H_NEDGES];
+    for (int j = 0; j < npaths; ++j) {                                                // self_play.py:651-654
+        const size_t slot = (size_t)g * v.R + j;
+        const int* path = v.paths + slot * v.MAXD;
+        const int len = v.path_len[slot];
+        add_ons(h, hot, path, len, -v.wu);                                            // :653
+        const int e = path[len - 1];
+        if ((int)cold[e].y >= 0 || err) continue;                                      // :733-734 duplicate leaf: no backup
+        const float val = value[slot];
+        const int K = compact_legal<N>(v.leaf_legal + slot * GG::DQ * 4, policy + slot * GG::A, sp, sa);
+        const int node = nn, eb = ne;
+        if (node + 1 > v.NC) err |= TG_MCTS_ERR_NODES;
+        if (eb + K > v.EC) err |= TG_MCTS_ERR_EDGES;
+        if (err) continue;
+        float scale = 0.0f;                                                           // :739 python sum(): sequential float32
+        if (lane == 0) for (int k = 0; k < K; ++k) scale = __fadd_rn(scale, sp[k]);
+        scale = __shfl_sync(0xffffffffu, scale, 0);
+        const bool ok = scale > 0.0f;                                                 // :740
+        for (int k = lane; k < K; k += 32) {
+            const float prior = ok ? __fdiv_rn(sp[k], scale) : 0.0f;                   // :743-744
+            const float w0 = ok ? -val : -0.0f;                                        // :752 / :76
+            hot[eb + k] = make_uint4(__float_as_uint(prior), __float_as_uint(w0), 0u, (uint32_t)sa[k]);
+            cold[eb + k] = make_uint2(0u, 0xffffffffu);
+        }
+        uint4* rec = nodes + (size_t)node * (GG::SQ + 1);
+        if (lane < GG::SQ) rec[lane] = v.leaf_state[(size_t)lane * v.G * v.R + slot];
+        if (lane == 0) {
+            rec[GG::SQ] = make_uint4((uint32_t)eb, (uint32_t)K, 0u, 0u);
+            cold[e].y = (uint32_t)node;
+        }
+        nn = node + 1; ne = eb + K;
+        __syncwarp();
+        backup<N>(v, h, hot, cold, path, len, val, err);                               // :755
+        sims += 1;
+        __syncwarp();
+    }
+    if (lane == 0) {
+        h[H_NPATHS] = 0; h[H_SIMS] += sims; h[H_NNODES] = nn; h[H_NEDGES] = ne;
+        if (err) { flags |= err; h[H_FLAGS] = (int)flags; }
+        if (pending && (flags & TG_MCTS_ACTIVE) && !(flags & (TG_MCTS_ERR_ANY | kErrAction)) && h[H_ROOTN] < h[H_N0] + v.num_sim)
+            atomicAdd(pending, 1);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- roots
+template <int N>
+__global__ void k_init(View v, const uint8_t* __restrict__ mask) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= v.G) return;
+    if (mask && !mask[g]) return;
+    int* h = v.hdr + (size_t)g * H_WORDS;
+    const int sims = mask ? h[H_SIMS] : 0;
+    for (int i = 0; i < H_WORDS; ++i) h[i] = 0;
+    h[H_SIMS] = sims;
+    h[H_FLAGS] = (int)(TG_MCTS_ACTIVE | TG_MCTS_NEED_EXPAND);
+    Pos<N> s; pos_reset(s);
+    pos_store<N>(s, v.root_state, g, v.G, 1);
+}
+
+template <int N>
+__global__ void __launch_bounds__(kThreads) k_root_expand(View v, const float* __restrict__ policy_root, const float* __restrict__ value_root) {
+    using GG = Geo<N>;
+    extern __shared__ uint32_t sm_raw[];
+    const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    if (g >= v.G) return;
+    int* h = v.hdr + (size_t)g * H_WORDS;
+    unsigned flags = (unsigned)h[H_FLAGS];
+    if (!(flags & TG_MCTS_NEED_EXPAND) || !(flags & TG_MCTS_ACTIVE)) return;
+    float* sp = reinterpret_cast<float*>(sm_raw) + wib * 2 * GG::A;
+    int* sa = reinterpret_cast<int*>(sp + GG::A);
+    __shared__ uint32_t dense[kThreads / 32][GG::DQ * 4];
+    const int buf = h[H_BUF];
+    uint4* hot = hot_of<N>(v, buf, g);
+    uint2* cold = cold_of<N>(v, buf, g);
+    uint4* nodes = nodes_of<N>(v, buf, g);
+    Pos<N> s; pos_load<N>(s, v.root_state, g, v.G, 1);
+    Groups<N> gr;
+    analyse_groups<N, 32, false>(s.stones[0], s.stones[1], s.player, gr);
+    const BB<N> lg = legal_points(s, gr);
+    if (lane == 0) {
+        uint32_t d[GG::DQ * 4];
+#pragma unroll
+        for (int i = 0; i < GG::DQ * 4; ++i) d[i] = 0;
+        bb_to_dense<N>(lg, d);
+        if (!any(lg)) d[GG::P >> 5] |= 1u << (GG::P & 31);
+#pragma unroll
+        for (int i = 0; i < GG::DQ * 4; ++i) dense[wib][i] = d[i];
+    }
+    __syncwarp();
+    const int K = compact_legal<N>(dense[wib], policy_root + (size_t)g * GG::A, sp, sa);
+    unsigned err = 0;
+    if (K > v.EC) err |= TG_MCTS_ERR_EDGES;
+    if (v.NC < 1) err |= TG_MCTS_ERR_NODES;
+    if (!err) {
+        const float w0 = -value_root[g];                                                // :76, value from :599
+        for (int k = lane; k < K; k += 32) {
+            hot[k] = make_uint4(__float_as_uint(sp[k]), __float_as_uint(w0), 0u, (uint32_t)sa[k]);   // RAW prior (:602)
+            cold[k] = make_uint2(0u, 0xffffffffu);
+        }
+        uint4* rec = nodes;
+        if (lane < GG::SQ) rec[lane] = v.root_state[(size_t)lane * v.G + g];
+        if (lane == 0) rec[GG::SQ] = make_uint4(0u, (uint32_t)K, 0u, 0u);
+    }
+    if (lane == 0) {
+        h[H_NNODES] = 1; h[H_NEDGES] = K;
+        flags &= ~(TG_MCTS_NEED_EXPAND | TG_MCTS_NOISY);
+        h[H_FLAGS] = (int)(flags | err);
+    }
+}
+
+template <int N>
+__global__ void k_begin_move(View v, const double* __restrict__ noise) {
+    using GG = Geo<N>;
+    const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (g >= v.G) return;
+    int* h = v.hdr + (size_t)g * H_WORDS;
+    unsigned flags = (unsigned)h[H_FLAGS];
+    if (!(flags & TG_MCTS_ACTIVE) || (flags & TG_MCTS_NEED_EXPAND)) return;
+    const int K = h[H_NEDGES] > 0 ? (int)nodes_of<N>(v, h[H_BUF], g)[GG::SQ].y : 0;
+    if (noise) {                                                                     // Node_V.dirichlet_prior :90-95
+        const uint4* hot = hot_of<N>(v, h[H_BUF], g);
+        for (int k = lane; k < K; k += 32) {
+            const float p = __fmul_rn(__uint_as_float(hot[k].x), 0.75f);
+            v.root_prior64[(size_t)g * GG::A + k] = __dadd_rn((double)p, __dmul_rn(noise[(size_t)g * GG::A + k], 0.25));
+        }
+        flags |= TG_MCTS_NOISY;
+    } else flags &= ~TG_MCTS_NOISY;
+    if (lane == 0) { h[H_N0] = h[H_ROOTN]; h[H_FLAGS] = (int)flags; }
+}
+
+template <int N>
+__global__ void k_root_stats(View v, int* __restrict__ counts, float* __restrict__ W, float* __restrict__ var, float* __restrict__ prior,
+                             int* __restrict__ root_n, int* __restrict__ root_k, int* __restrict__ step) {
+    using GG = Geo<N>;
+    const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (g >= v.G) return;
+    const int* h = v.hdr + (size_t)g * H_WORDS;
+    const size_t row = (size_t)g * GG::A;
+    for (int a = lane; a < GG::A; a += 32) {
+        if (counts) counts[row + a] = 0;
+        if (W) W[row + a] = 0.0f;
+        if (var) var[row + a] = 0.0f;
+        if (prior) prior[row + a] = 0.0f;
+    }
+    __syncwarp();
+    const bool has = !((unsigned)h[H_FLAGS] & TG_MCTS_NEED_EXPAND) && h[H_NNODES] > 0;
+    const int K = has ? (int)nodes_of<N>(v, h[H_BUF], g)[GG::SQ].y : 0;
+    const uint4* hot = hot_of<N>(v, h[H_BUF], g);
+    for (int k = lane; k < K; k += 32) {
+        const uint4 q = hot[k];
+        const int a = pk_act(q.w);
+        if (counts) counts[row + a] = pk_n(q.w);
+        if (W) W[row + a] = __uint_as_float(q.y);
+        if (var) var[row + a] = __uint_as_float(q.z);
+        if (prior) prior[row + a] = __uint_as_float(q.x);
+    }
+    if (lane == 0) {
+        if (root_n) root_n[g] = h[H_ROOTN];
+        if (root_k) root_k[g] = K;
+        if (step) step[g] = (int)(v.root_state[(size_t)(GG::SQ - 1) * v.G + g].z & 0xffffu);
+    }
+}
+
+// update_with_action (:857-872): env.step on the root state, then keep the chosen child's subtree by copying it
+// breadth-first into the other half of the arena.
+template <int N>
+__global__ void __launch_bounds__(kThreads) k_advance(View v, const int16_t* __restrict__ actions, uint8_t* __restrict__ done_out) {
+    using GG = Geo<N>;
+    const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (g >= v.G) return;
+    int* h = v.hdr + (size_t)g * H_WORDS;
+    unsigned flags = (unsigned)h[H_FLAGS];
+    if (!(flags & TG_MCTS_ACTIVE) || (flags & (TG_MCTS_NEED_EXPAND | TG_MCTS_ERR_ANY | kErrAction))) {
+        if (lane == 0 && done_out) done_out[g] = (flags & TG_MCTS_ACTIVE) ? 0 : 1;
+        return;
+    }
+    const int action = (int)actions[g];
+    const int buf = h[H_BUF];
+    const uint4* shot = hot_of<N>(v, buf, g);
+    const uint2* scold = cold_of<N>(v, buf, g);
+    const uint4* snodes = nodes_of<N>(v, buf, g);
+    const int K0 = (int)snodes[GG::SQ].y;
+    // the root edge of `action`
+    int ksel = -1;
+    for (int base = 0; base < K0; base += 32) {
+        const int k = base + lane;
+        const bool hit = k < K0 && pk_act(shot[k].w) == action;
+        const unsigned b = __ballot_sync(0xffffffffu, hit);
+        if (b && ksel < 0) ksel = base + __ffs((int)b) - 1;
+    }
+    if (ksel < 0) { if (lane == 0) { h[H_FLAGS] = (int)(flags | kErrAction); if (done_out) done_out[g] = 0; } return; }
+    // env.step(root.state, action)  (:859)
+    Pos<N> s; pos_load<N>(s, v.root_state, g, v.G, 1);
+    Groups<N> gr;
+    analyse_groups<N, 32, false>(s.stones[0], s.stones[1], s.player, gr);
+    bool acc;
+    const bool done = apply_move<N, 32>(s, gr, action, v.max_step, acc);
+    if (lane == 0) pos_store<N>(s, v.root_state, g, v.G, 1);
+    const uint4 qe = shot[ksel];
+    const uint2 ce = scold[ksel];
+    const int child = (int)ce.y;
+    int nd = 0, ne = 0;
+    if (child >= 0) {
+        const int dbuf = 1 - buf;
+        uint4* dhot = hot_of<N>(v, dbuf, g);
+        uint2* dcold = cold_of<N>(v, dbuf, g);
+        uint4* dnodes = nodes_of<N>(v, dbuf, g);
+        if (lane == 0) dnodes[GG::SQ].z = (uint32_t)child;
+        __syncwarp();
+        nd = 1;
+        for (int i = 0; i < nd; ++i) {
+            uint4* drec = dnodes + (size_t)i * (GG::SQ + 1);
+            const int src = (int)drec[GG::SQ].z;
+            const uint4* srec = snodes + (size_t)src * (GG::SQ + 1);
+            const uint4 sinfo = srec[GG::SQ];
+            const int seb = (int)sinfo.x, K = (int)sinfo.y;
+            if (lane < GG::SQ) drec[lane] = srec[lane];
+            for (int base = 0; base < K; base += 32) {
+                const int k = base + lane;
+                uint4 q = make_uint4(0, 0, 0, 0); uint2 c = make_uint2(0, 0xffffffffu);
+                if (k < K) { q = shot[seb + k]; c = scold[seb + k]; }
+                const bool has = k < K && (int)c.y >= 0;
+                const unsigned b = __ballot_sync(0xffffffffu, has);
+                if (has) {
+                    const int my = nd + __popc(b & ((1u << lane) - 1u));
+                    dnodes[(size_t)my * (GG::SQ + 1) + GG::SQ].z = c.y;
+                    c.y = (uint32_t)my;
+                }
+                if (k < K) { dhot[ne + k] = q; dcold[ne + k] = c; }
+                nd += __popc(b);
+            }
+            __syncwarp();
+            if (lane == 0) drec[GG::SQ] = make_uint4((uint32_t)ne, (uint32_t)K, (uint32_t)src, 0u);
+            ne += K;
+            __syncwarp();
+        }
+    }
+    if (lane == 0) {
+        h[H_BUF] = child >= 0 ? 1 - buf : buf;
+        h[H_NNODES] = nd; h[H_NEDGES] = ne;
+        h[H_ROOTN] = pk_n(qe.w); h[H_ROOTONS] = pk_ons(qe.w);
+        h[H_ROOTW] = (int)qe.y; h[H_ROOTMEAN] = (int)ce.x; h[H_ROOTVAR] = (int)qe.z;
+        h[H_MOVE] += 1;
+        flags &= ~TG_MCTS_NOISY;
+        if (child < 0) flags |= TG_MCTS_NEED_EXPAND;                                   // :861-870
+        if (done) flags &= ~TG_MCTS_ACTIVE;
+        h[H_FLAGS] = (int)flags;
+        if (done_out) done_out[g] = done ? 1 : 0;
+    }
+}
+
+__global__ void k_status(View v, uint32_t* __restrict__ status, unsigned long long* __restrict__ sims) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long mine = 0;
+    if (g < v.G) {
+        int* h = v.hdr + (size_t)g * H_WORDS;
+        if (status) status[g] = (uint32_t)h[H_FLAGS];
+        if (sims) { mine = (unsigned long long)(unsigned)h[H_SIMS]; h[H_SIMS] = 0; }
+    }
+    if (sims) {
+#pragma unroll
+        for (int s = 16; s >= 1; s >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, s);
+        if ((threadIdx.x & 31) == 0 && mine) atomicAdd(sims, mine);
+    }
+}
+
+__global__ void k_winner(const float* __restrict__ score, uint8_t* __restrict__ winner, int G) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g < G) winner[g] = score[g] > 0.0f ? kBlack : kWhite;                          // environment.py:118-119
+}
+
+// synthetic provider (bench only): heavy-tailed integer weights -> one f32 division per entry
+__global__ void k_synth(int A, long long rows, unsigned long long seed, unsigned long long wave, float* __restrict__ policy, float* __restrict__ value) {
+    const long long row = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    unsigned long long sum = 0;
+    for (int a = lane; a < A; a += 32) {
+        const unsigned long long r = mix32(seed + wave * 0x632BE59BD9B4E019ull, (unsigned long long)row, (unsigned long long)a) & 0xFFFFu;
+        sum += 1ull + ((r * r * r) >> 32);
+    }
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, s);
+    const float total = (float)sum;
+    for (int a = lane; a < A; a += 32) {
+        const unsigned long long r = mix32(seed + wave * 0x632BE59BD9B4E019ull, (unsigned long long)row, (unsigned long long)a) & 0xFFFFu;
+        policy[row * A + a] = __fdiv_rn((float)(1ull + ((r * r * r) >> 32)), total);
+    }
+    if (lane == 0) {
+        const int vv = (int)(mix32(seed ^ 0x5555ull, (unsigned long long)row, wave) & 0xFFFFu) - 32768;
+        value[row] = __fdiv_rn((float)vv, 32832.0f);
+    }
+}
+
+// ------------------------------------------------------------------------------------------ host side
+static int check_cfg(const TgMctsConfig* c) {
+    if (!c) return set_err(-1, "tg_mcts: null config");
+    if (c->n != 9 && c->n != 19) return set_err(-1, "tg_mcts: board size must be 9 or 19");
+    if (c->num_games <= 0 || c->readouts < 1 || c->readouts > kMaxReadouts) return set_err(-1, "tg_mcts: bad num_games / readouts");
+    if (c->wu_loss < 0 || c->wu_loss * c->readouts > 127) return set_err(-1, "tg_mcts: wu_loss * readouts must be <= 127");
+    if (c->node_cap < 1 || c->edge_cap < c->n * c->n + 1 || c->max_depth < 2) return set_err(-1, "tg_mcts: capacities too small");
+    return 0;
+}
+static inline unsigned warp_blocks(long long warps) { return (unsigned)((warps * 32 + kThreads - 1) / kThreads); }
+
+#define TG_MCTS_N(c, ...)                        \
+    if ((c)->n == 9) { constexpr int N = 9; __VA_ARGS__; } else { constexpr int N = 19; __VA_ARGS__; }
+
+}  // namespace tg
+
+using namespace tg;
+
+extern "C" {
+
+int64_t tg_mcts_workspace_bytes(const TgMctsConfig* cfg) {
+    if (check_cfg(cfg)) return -1;
+    TG_MCTS_N(cfg, return (int64_t)make_view<N>(cfg, nullptr).total_bytes);
+}
+
+int tg_mcts_init(const TgMctsConfig* cfg, void* ws, void* stream) {
+    if (check_cfg(cfg) || !ws) return set_err(-1, "tg_mcts_init");
+    TG_MCTS_N(cfg, { View v = make_view<N>(cfg, ws); k_init<N><<<(v.G + 127) / 128, 128, 0, (cudaStream_t)stream>>>(v, nullptr); });
+    return set_err((int)cudaGetLastError(), "tg_mcts_init");
+}
+
+int tg_mcts_reset_games(const TgMctsConfig* cfg, void* ws, const uint8_t* mask, void* stream) {
+    if (check_cfg(cfg) || !ws || !mask) return set_err(-1, "tg_mcts_reset_games");
+    TG_MCTS_N(cfg, { View v = make_view<N>(cfg, ws); k_init<N><<<(v.G + 127) / 128, 128, 0, (cudaStream_t)stream>>>(v, mask); });
+    return set_err((int)cudaGetLastError(), "tg_mcts_reset_games");
+}
+
+void* tg_mcts_root_states(const TgMctsConfig* cfg, void* ws) {
+    if (check_cfg(cfg) || !ws) return nullptr;
+    TG_MCTS_N(cfg, return (void*)make_view<N>(cfg, ws).root_state);
+}
+
+int tg_mcts_root_obs(const TgMctsConfig* cfg, void* ws, float* obs_root, void* stream) {
+    if (check_cfg(cfg) || !ws || !obs_root) return set_err(-1, "tg_mcts_root_obs");
+    return tg_env_encode(cfg->n, tg_mcts_root_states(cfg, ws), cfg->num_games, obs_root, 32, stream);
+}
+
+int tg_mcts_root_expand(const TgMctsConfig* cfg, void* ws, const float* policy_root, const float* value_root, void* stream) {
+    if (check_cfg(cfg) || !ws || !policy_root || !value_root) return set_err(-1, "tg_mcts_root_expand");
+    TG_MCTS_N(cfg, {
+        View v = make_view<N>(cfg, ws);
+        const size_t smem = (size_t)(kThreads / 32) * 2 * Geo<N>::A * 4;
+        k_root_expand<N><<<warp_blocks(v.G), kThreads, smem, (cudaStream_t)stream>>>(v, policy_root, value_root);
+    });
+    return set_err((int)cudaGetLastError(), "tg_mcts_root_expand");
+}
+
+int tg_mcts_begin_move(const TgMctsConfig* cfg, void* ws, const double* noise, void* stream) {
+    if (check_cfg(cfg) || !ws) return set_err(-1, "tg_mcts_begin_move");
+    TG_MCTS_N(cfg, { View v = make_view<N>(cfg, ws); k_begin_move<N><<<warp_blocks(v.G), kThreads, 0, (cudaStream_t)stream>>>(v, noise); });
+    return set_err((int)cudaGetLastError(), "tg_mcts_begin_move");
+}
+
+int tg_mcts_wave_begin(const TgMctsConfig* cfg, void* ws, float* obs, void* stream) {
+    if (check_cfg(cfg) || !ws || !obs) return set_err(-1, "tg_mcts_wave_begin");
+    if ((reinterpret_cast<uintptr_t>(obs) & 3) != 0) return set_err(-1, "tg_mcts_wave_begin: obs must be 4-byte aligned");
+    TG_MCTS_N(cfg, {
+        View v = make_view<N>(cfg, ws);
+        k_select<N><<<warp_blocks(v.G), kThreads, 0, (cudaStream_t)stream>>>(v);
+        const size_t smem = (size_t)(kThreads / 32) * ((Geo<N>::PLANE_BITS + 31) / 32 + 2) * 4;
+        k_leaves<N><<<warp_blocks((long long)v.G * v.R), kThreads, smem, (cudaStream_t)stream>>>(v, obs);
+    });
+    return set_err((int)cudaGetLastError(), "tg_mcts_wave_begin");
+}
+
+int tg_mcts_wave_end(const TgMctsConfig* cfg, void* ws, const float* policy, const float* value, int32_t* pending, void* stream) {
+    if (check_cfg(cfg) || !ws || !policy || !value) return set_err(-1, "tg_mcts_wave_end");
+    TG_MCTS_N(cfg, {
+        View v = make_view<N>(cfg, ws);
+        const size_t smem = (size_t)(kThreads / 32) * 2 * Geo<N>::A * 4;
+        k_expand<N><<<warp_blocks(v.G), kThreads, smem, (cudaStream_t)stream>>>(v, policy, value, pending);
+    });
+    return set_err((int)cudaGetLastError(), "tg_mcts_wave_end");
+}
+
+int tg_mcts_root_stats(const TgMctsConfig* cfg, void* ws, int32_t* counts, float* W, float* var, float* prior, int32_t* root_n,
+                       int32_t* root_k, int32_t* step, void* stream) {
+    if (check_cfg(cfg) || !ws) return set_err(-1, "tg_mcts_root_stats");
+    TG_MCTS_N(cfg, { View v = make_view<N>(cfg, ws); k_root_stats<N><<<warp_blocks(v.G), kThreads, 0, (cudaStream_t)stream>>>(v, counts, W, var, prior, root_n, root_k, step); });
+    return set_err((int)cudaGetLastError(), "tg_mcts_root_stats");
+}
+
+int tg_mcts_advance(const TgMctsConfig* cfg, void* ws, const int16_t* actions, uint8_t* done_out, void* stream) {
+    if (check_cfg(cfg) || !ws || !actions) return set_err(-1, "tg_mcts_advance");
+    TG_MCTS_N(cfg, { View v = make_view<N>(cfg, ws); k_advance<N><<<warp_blocks(v.G), kThreads, 0, (cudaStream_t)stream>>>(v, actions, done_out); });
+    return set_err((int)cudaGetLastError(), "tg_mcts_advance");
+}
+
+int tg_mcts_status(const TgMctsConfig* cfg, void* ws, uint32_t* status, unsigned long long* sims, void* stream) {
+    if (check_cfg(cfg) || !ws) return set_err(-1, "tg_mcts_status");
+    TG_MCTS_N(cfg, { View v = make_view<N>(cfg, ws); k_status<<<(v.G + 127) / 128, 128, 0, (cudaStream_t)stream>>>(v, status, sims); });
+    return set_err((int)cudaGetLastError(), "tg_mcts_status");
+}
+
+int tg_mcts_outcome(const TgMctsConfig* cfg, void* ws, uint8_t* winner, float* score, float* territory, void* stream) {
+    if (check_cfg(cfg) || !ws || !score) return set_err(-1, "tg_mcts_outcome (score is required)");
+    int rc = tg_env_score(cfg->n, tg_mcts_root_states(cfg, ws), cfg->num_games, cfg->komi, score, territory, 32, stream);
+    if (rc) return rc;
+    if (winner) k_winner<<<(cfg->num_games + 127) / 128, 128, 0, (cudaStream_t)stream>>>(score, winner, cfg->num_games);
+    return set_err((int)cudaGetLastError(), "tg_mcts_outcome");
+}
+
+int tg_synth_provider(int n, int64_t rows, uint64_t seed, uint64_t wave, float* policy, float* value, void* stream) {
+    if (!policy || !value || rows <= 0 || (n != 9 && n != 19)) return set_err(-1, "tg_synth_provider");
+    k_synth<<<warp_blocks(rows), kThreads, 0, (cudaStream_t)stream>>>(n * n + 1, rows, seed, wave, policy, value);
+    return set_err((int)cudaGetLastError(), "tg_synth_provider");
+}
+
+}  // extern "C"

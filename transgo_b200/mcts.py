@@ -1,0 +1,328 @@
+"""Host-side mirror of the search entry point self_play.py calls (WP_MCTS, self_play.py:575-875).
+
+``BatchedMCTS``  G concurrent searches on the GPU (one warp per game inside libtransgo_b200.so); same method names as
+                 the reference with a leading game dimension: reset_root(), get_action_probs() -> (actions[G],
+                 pi[G, A], obs[G, 10, n, n]), update_with_action(actions[G]) -> done[G].
+``WP_MCTS``      the G = 1 facade with the reference's scalar signature (config, env, model, sub_model=None).
+
+The policy/value net stays a PyTorch module (model.py: main_prediction); everything else -- selection, virtual loss,
+leaf step / legal mask / feature planes, expansion, backup, re-rooting -- runs in hand-written CUDA.
+"""
+import ctypes
+import math
+
+import numpy as np
+
+from . import _lib
+from .environment import DEFAULT_MAX_STEP, GoState
+
+ACTIVE, NEED_EXPAND, NOISY = 1, 2, 4
+ERR_BITS = {16: "node arena overflow (raise node_cap)", 32: "edge arena overflow (raise edge_cap)",
+            64: "search path deeper than max_depth", 128: "visit count above 65535",
+            256: "update_with_action: action is not a child of the root"}
+
+
+class TgMctsConfig(ctypes.Structure):
+    """include/transgo_b200.h: struct TgMctsConfig"""
+    _fields_ = [("n", ctypes.c_int32), ("num_games", ctypes.c_int32), ("readouts", ctypes.c_int32),
+                ("num_simulation", ctypes.c_int32), ("wu_loss", ctypes.c_int32), ("max_step", ctypes.c_int32),
+                ("node_cap", ctypes.c_int32), ("edge_cap", ctypes.c_int32), ("max_depth", ctypes.c_int32),
+                ("tie_mode", ctypes.c_int32), ("c_puct1", ctypes.c_double), ("c_puct2", ctypes.c_double),
+                ("komi", ctypes.c_float), ("reserved0", ctypes.c_int32), ("tie_seed", ctypes.c_uint64),
+                ("game_id0", ctypes.c_int64)]
+
+
+def epsilon_by_frame(game_step):
+    """configure.py:75-79 -- move-sampling temperature 1.0 -> 0.65"""
+    return 0.65 + (1.0 - 0.65) * math.exp(-1.0 * game_step / 10)
+
+
+def _declare(L):
+    if getattr(L, "_tg_mcts_declared", False):
+        return
+    P = ctypes.POINTER(TgMctsConfig)
+    vp, i32 = ctypes.c_void_p, ctypes.c_int
+    L.tg_mcts_workspace_bytes.argtypes = [P]
+    L.tg_mcts_workspace_bytes.restype = ctypes.c_int64
+    L.tg_mcts_init.argtypes = [P, vp, vp]
+    L.tg_mcts_reset_games.argtypes = [P, vp, vp, vp]
+    L.tg_mcts_root_obs.argtypes = [P, vp, vp, vp]
+    L.tg_mcts_root_expand.argtypes = [P, vp, vp, vp, vp]
+    L.tg_mcts_begin_move.argtypes = [P, vp, vp, vp]
+    L.tg_mcts_wave_begin.argtypes = [P, vp, vp, vp]
+    L.tg_mcts_wave_end.argtypes = [P, vp, vp, vp, vp, vp]
+    L.tg_mcts_root_stats.argtypes = [P, vp] + [vp] * 7 + [vp]
+    L.tg_mcts_advance.argtypes = [P, vp, vp, vp, vp]
+    L.tg_mcts_status.argtypes = [P, vp, vp, vp, vp]
+    L.tg_mcts_root_states.argtypes = [P, vp]
+    L.tg_mcts_root_states.restype = ctypes.c_void_p
+    L.tg_mcts_outcome.argtypes = [P, vp, vp, vp, vp, vp]
+    L.tg_synth_provider.argtypes = [i32, ctypes.c_int64, ctypes.c_uint64, ctypes.c_uint64, vp, vp, vp]
+    L._tg_mcts_declared = True
+
+
+class BatchedMCTS:
+    """G searches in lock-step.  ``evaluator(obs) -> (policy [B, A] float32, value [B] or [B, 1] float32)`` is the net
+    (obs is a CUDA float32 tensor [B, 10, n, n]; outputs must be CUDA tensors)."""
+
+    def __init__(self, evaluator, num_games, board_size=9, num_simulation=210, c_puct1=3, c_puct2=0.05, wu_loss=2,
+                 parallel_readouts=4, max_step=None, komi=7.5, tie_mode="hash", tie_seed=0, game_id0=0,
+                 node_cap=None, edge_cap=None, max_depth=64, device="cuda", check_every=4):
+        import torch
+        self.torch = torch
+        if not torch.cuda.is_available():
+            raise _lib.TransgoLibraryError("BatchedMCTS needs a CUDA device (no CPU fallback)")
+        self.lib = _lib.lib()
+        _declare(self.lib)
+        self.evaluator = evaluator
+        self.G, self.n = int(num_games), int(board_size)
+        self.P = self.n * self.n
+        self.A = self.P + 1
+        self.R = int(parallel_readouts)
+        self.num_simulation = int(num_simulation)
+        self.device = torch.device(device)
+        self.check_every = check_every
+        max_step = DEFAULT_MAX_STEP.get(self.n, 2 * self.P) if max_step is None else int(max_step)
+        # every net-evaluated simulation adds one node; the kept subtree can carry several moves' worth of visits
+        node_cap = node_cap or (6 * self.num_simulation + 64)
+        edge_cap = edge_cap or max(self.A, int(node_cap * self.A * 0.85))
+        self.cfg = TgMctsConfig(self.n, self.G, self.R, self.num_simulation, int(wu_loss), max_step, node_cap, edge_cap,
+                                max_depth, 1 if tie_mode == "hash" else 0, float(c_puct1), float(c_puct2), float(komi), 0,
+                                int(tie_seed), int(game_id0))
+        self._cfg = ctypes.byref(self.cfg)
+        nbytes = self.lib.tg_mcts_workspace_bytes(self._cfg)
+        if nbytes <= 0:
+            raise _lib.TransgoLibraryError("bad MCTS config: " + self.lib.tg_last_error().decode())
+        self.workspace_bytes = int(nbytes)
+        self.ws = torch.empty([(nbytes + 15) // 16, 4], dtype=torch.int32, device=self.device)
+        G, R, A, n = self.G, self.R, self.A, self.n
+        f32 = torch.float32
+        self.obs = torch.zeros([G * R, 10, n, n], dtype=f32, device=self.device)        # the net's input, written in place
+        self.obs_root = torch.zeros([G, 10, n, n], dtype=f32, device=self.device)
+        self.pending = torch.zeros([1], dtype=torch.int32, device=self.device)
+        self.counts = torch.zeros([G, A], dtype=torch.int32, device=self.device)
+        self.root_n = torch.zeros([G], dtype=torch.int32, device=self.device)
+        self.root_k = torch.zeros([G], dtype=torch.int32, device=self.device)
+        self.step = torch.zeros([G], dtype=torch.int32, device=self.device)
+        self.done = torch.zeros([G], dtype=torch.uint8, device=self.device)
+        self.status = torch.zeros([G], dtype=torch.int32, device=self.device)
+        self.sims = torch.zeros([1], dtype=torch.int64, device=self.device)
+        self.waves = 0
+        self.reset_root()
+
+    # ---------------------------------------------------------------- plumbing
+    def _s(self):
+        return _lib.stream_ptr()
+
+    def _w(self):
+        return _lib.ptr(self.ws)
+
+    def _eval(self, obs):
+        out = self.evaluator(obs)
+        policy, value = out[0], out[1]
+        policy = policy.to(self.torch.float32).contiguous()
+        value = value.to(self.torch.float32).reshape(-1).contiguous()
+        assert policy.is_cuda and policy.shape == (obs.shape[0], self.A), policy.shape
+        return policy, value
+
+    def _expand_roots(self):
+        """computeValuePolicy([root.state]) + root.expand(raw priors, value) for roots flagged NEED_EXPAND."""
+        _lib.check(self.lib.tg_mcts_root_obs(self._cfg, self._w(), _lib.ptr(self.obs_root), self._s()), "tg_mcts_root_obs")
+        policy, value = self._eval(self.obs_root)
+        _lib.check(self.lib.tg_mcts_root_expand(self._cfg, self._w(), _lib.ptr(policy), _lib.ptr(value), self._s()),
+                   "tg_mcts_root_expand")
+
+    def check_status(self):
+        _lib.check(self.lib.tg_mcts_status(self._cfg, self._w(), _lib.ptr(self.status), _lib.ptr(self.sims), self._s()),
+                   "tg_mcts_status")
+        st = self.status.cpu().numpy()
+        bad = st & (16 | 32 | 64 | 128 | 256)
+        if bad.any():
+            g = int(np.nonzero(bad)[0][0])
+            msgs = [m for b, m in ERR_BITS.items() if bad[g] & b]
+            raise _lib.TransgoLibraryError("MCTS game %d: %s" % (g, "; ".join(msgs)))
+        return st
+
+    def total_sims(self):
+        self.check_status()
+        return int(self.sims.item())
+
+    # ---------------------------------------------------------------- the reference surface
+    def reset_root(self):                                   # self_play.py:595-605
+        _lib.check(self.lib.tg_mcts_init(self._cfg, self._w(), self._s()), "tg_mcts_init")
+        self._expand_roots()
+
+    def reset_games(self, mask):
+        """Start a fresh game in the slots where mask (uint8 [G]) is non-zero."""
+        mask = mask.to(self.torch.uint8).contiguous()
+        _lib.check(self.lib.tg_mcts_reset_games(self._cfg, self._w(), _lib.ptr(mask), self._s()), "tg_mcts_reset_games")
+        self._expand_roots()
+
+    def run_wave(self):                                     # self_play.py:607-654
+        _lib.check(self.lib.tg_mcts_wave_begin(self._cfg, self._w(), _lib.ptr(self.obs), self._s()), "tg_mcts_wave_begin")
+        policy, value = self._eval(self.obs)
+        self.pending.zero_()
+        _lib.check(self.lib.tg_mcts_wave_end(self._cfg, self._w(), _lib.ptr(policy), _lib.ptr(value), _lib.ptr(self.pending),
+                                             self._s()), "tg_mcts_wave_end")
+        self.waves += 1
+
+    def make_noise(self, alpha=0.03, generator=None):
+        """Dirichlet(alpha) over each root's K children, float64 [G, A] in edge order (Node_V.dirichlet_prior :90-95)."""
+        torch = self.torch
+        self.root_stats()
+        conc = torch.full([self.G, self.A], alpha, dtype=torch.float64, device=self.device)
+        gam = torch._standard_gamma(conc) if generator is None else torch._standard_gamma(conc, generator=generator)
+        k = torch.arange(self.A, device=self.device)[None, :] < self.root_k[:, None]
+        gam = torch.where(k, gam, torch.zeros_like(gam))
+        return gam / gam.sum(1, keepdim=True).clamp_min(1e-300)
+
+    def root_stats(self, full=False):
+        torch = self.torch
+        W = var = prior = None
+        if full:
+            W = torch.empty([self.G, self.A], dtype=torch.float32, device=self.device)
+            var = torch.empty_like(W)
+            prior = torch.empty_like(W)
+        _lib.check(self.lib.tg_mcts_root_stats(self._cfg, self._w(), _lib.ptr(self.counts), _lib.ptr(W), _lib.ptr(var),
+                                               _lib.ptr(prior), _lib.ptr(self.root_n), _lib.ptr(self.root_k),
+                                               _lib.ptr(self.step), self._s()), "tg_mcts_root_stats")
+        return self.counts, W, var, prior
+
+    def search(self, noise=None):
+        """The simulation loop of get_action_probs (:660-664) for all games."""
+        _lib.check(self.lib.tg_mcts_begin_move(self._cfg, self._w(), _lib.ptr(noise), self._s()), "tg_mcts_begin_move")
+        min_waves = -(-self.num_simulation // self.R)
+        for _ in range(min_waves):
+            self.run_wave()
+        while int(self.pending.item()) > 0:
+            for _ in range(self.check_every):
+                self.run_wave()
+
+    def get_action_probs(self, is_selfplay=True, noise=None, u=None, forced_actions=None):
+        """Returns (actions int16 [G], pi float64 [G, A], root observations float32 [G, 10, n, n]).
+        noise: float64 [G, A] Dirichlet draws in root-edge order (generated on the device when None and is_selfplay);
+        u: float64 [G] uniforms for the move draw (torch.rand when None)."""
+        torch = self.torch
+        if is_selfplay and noise is None:
+            noise = self.make_noise()
+        if noise is not None:
+            noise = noise.to(torch.float64).contiguous()
+        self.search(noise if is_selfplay else None)
+        counts, _, _, _ = self.root_stats()
+        c = counts.to(torch.float64)
+        c = torch.where(counts == 1, torch.zeros_like(c), c)                    # :668
+        pi = c / c.sum(1, keepdim=True)                                         # :670-671
+        if forced_actions is not None:
+            actions = forced_actions.to(torch.int16)
+        else:
+            if is_selfplay:                                                     # :676-677
+                temp = 0.65 + 0.35 * torch.exp(-self.step.to(torch.float64) / 10.0)
+            else:
+                temp = torch.full([self.G], 0.12, dtype=torch.float64, device=self.device)
+            tem = torch.pow(c, (1.0 / temp)[:, None])                            # :679
+            cdf = torch.cumsum(tem / tem.sum(1, keepdim=True), 1)
+            cdf = cdf / cdf[:, -1:]
+            if u is None:
+                u = torch.rand([self.G], dtype=torch.float64, device=self.device)
+            actions = torch.searchsorted(cdf, u.to(torch.float64)[:, None].contiguous(), right=True).reshape(-1)
+            actions = actions.clamp_max(self.A - 1).to(torch.int16)             # np.random.choice(p=...) :683
+        _lib.check(self.lib.tg_mcts_root_obs(self._cfg, self._w(), _lib.ptr(self.obs_root), self._s()), "tg_mcts_root_obs")
+        return actions, pi, self.obs_root                                       # :685-687
+
+    def update_with_action(self, actions):                  # self_play.py:857-872
+        actions = actions.to(self.torch.int16).contiguous()
+        _lib.check(self.lib.tg_mcts_advance(self._cfg, self._w(), _lib.ptr(actions), _lib.ptr(self.done), self._s()),
+                   "tg_mcts_advance")
+        self._expand_roots()
+        self.check_status()
+        return self.done
+
+    def outcome(self, want_territory=True):
+        """winner uint8 [G], score float32 [G], territory float32 [G, P] of the current root states (self_play.py:931-937)."""
+        torch = self.torch
+        winner = torch.empty([self.G], dtype=torch.uint8, device=self.device)
+        score = torch.empty([self.G], dtype=torch.float32, device=self.device)
+        terr = torch.empty([self.G, self.P], dtype=torch.float32, device=self.device) if want_territory else None
+        _lib.check(self.lib.tg_mcts_outcome(self._cfg, self._w(), _lib.ptr(winner), _lib.ptr(score), _lib.ptr(terr),
+                                            self._s()), "tg_mcts_outcome")
+        return winner, score, terr
+
+    def root_state_blob(self, g=0):
+        """Host copy of game g's root state in the single-state blob format of environment.GoEnv."""
+        sq = self.lib.tg_state_bytes(self.n) // 16
+        base = self.lib.tg_mcts_root_states(self._cfg, self._w())
+        off = (base - self.ws.data_ptr()) // 4
+        st = self.ws.reshape(-1)[off:off + sq * self.G * 4].reshape(sq, self.G, 4)[:, g, :].contiguous().cpu().numpy()
+        blob = GoState()
+        ctypes.memmove(ctypes.byref(blob), st.ctypes.data, sq * 16)
+        return blob
+
+    def set_root_state_blob(self, blob, g=0):
+        torch = self.torch
+        sq = self.lib.tg_state_bytes(self.n) // 16
+        arr = np.frombuffer(bytes(blob.raw[:sq * 16]), dtype=np.int32).reshape(sq, 4)
+        base = self.lib.tg_mcts_root_states(self._cfg, self._w())
+        off = (base - self.ws.data_ptr()) // 4
+        view = self.ws.reshape(-1)[off:off + sq * self.G * 4].reshape(sq, self.G, 4)
+        view[:, g, :] = torch.from_numpy(arr.copy()).to(self.device)
+
+
+class _Root:
+    def __init__(self, owner):
+        self._o = owner
+
+    @property
+    def state(self):
+        return self._o._b.root_state_blob(0)
+
+    @property
+    def total_visit_count(self):
+        self._o._b.root_stats()
+        return int(self._o._b.root_n[0].item())
+
+
+class WP_MCTS(object):
+    """Drop-in for self_play.py's WP_MCTS with the same constructor and entry points (self_play.py:906-926, :990-1016):
+    reset_root(), get_action_probs(is_selfplay, now_train_step) -> (action, pi[A], obs[10, n, n]),
+    update_with_action(a) -> done, select_action(state) -> action, .root.state, .model.  One game, run on the GPU."""
+
+    def __init__(self, config, env, model, sub_model=None, **engine_kw):
+        import torch
+        self.config, self.env, self.model, self.sub_model = config, env, model, sub_model
+        if sub_model is not None:
+            raise NotImplementedError("the reference's transfer branch is dead code (self_play.py:809); not supported")
+        self.board_size = config.board_size
+        self._kw = dict(board_size=config.board_size, num_simulation=config.num_simulation, c_puct1=config.c_puct1,
+                        c_puct2=config.c_puct2, wu_loss=config.wu_loss, parallel_readouts=config.parallel_readouts,
+                        max_step=getattr(env, "max_step", None), komi=getattr(env, "komi", 7.5))
+        self._kw.update(engine_kw)
+
+        def evaluator(obs):
+            with torch.no_grad():
+                p, v, _ = self.model.main_prediction(obs)
+            return p, v
+        self._b = BatchedMCTS(evaluator, 1, **self._kw)      # constructor runs reset_root, like the reference (:593)
+        self.root = _Root(self)
+
+    def reset_root(self):
+        self._b.reset_root()
+
+    def get_action_probs(self, is_selfplay=True, now_train_step=0):
+        a, pi, obs = self._b.get_action_probs(is_selfplay)
+        return int(a[0].item()), pi[0].cpu().numpy(), obs[0].cpu().numpy().copy()
+
+    def update_with_action(self, fall_action):
+        torch = self._b.torch
+        done = self._b.update_with_action(torch.tensor([int(fall_action)], dtype=torch.int16, device=self._b.device))
+        return bool(done[0].item())
+
+    def select_action(self, gamestate):                     # self_play.py:689-704
+        b = self._b
+        _lib.check(b.lib.tg_mcts_init(b._cfg, b._w(), b._s()), "tg_mcts_init")
+        b.set_root_state_blob(gamestate, 0)
+        b._expand_roots()
+        action, _, _ = self.get_action_probs(is_selfplay=False)
+        return action
+
+    def __str__(self):
+        return "WP_MCTS"
