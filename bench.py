@@ -1,0 +1,502 @@
+#!/usr/bin/env python
+"""bench.py -- the driver's measurement contract for the batched self-play hot path.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+Headline workload (BASELINE.json configs[1]): 9x9 env-only batched random playouts, 4096 concurrent
+games per GPU from the empty board to termination.  One *step* = one such batch: reset + playout kernel (every ply:
+group analysis -> legal mask -> hashed move draw -> capture/ko/step) + Tromp-Taylor scoring.
+  value      board steps (plies) per second, whole job, game states resident in HBM, CUDA-event timed
+  e2e        same metric through the C ABI with HOST buffers: pinned initial states H2D, kernels, final states + scores +
+             the per-ply action trace D2H, all inside the timed region
+  roofline   k_playout against the measured HBM peak with SURVEY 8d's 115 algorithmic bytes per ply
+  cpu_baseline  the UNMODIFIED reference engine (oracle/_ref/go_env9.so, compiled from /root/reference) driven through
+             ctypes exactly like GoEnv/environment.py (getLegalAction + Step per ply) on every host core, same move rule
+  mcts       second half of the metric ("MCTS sims/sec"): BASELINE configs[2] (1024 games x 800 simulations per move),
+             tree kernels alone with a device-side synthetic provider, and end to end with the random-init TransGo net
+Multi-GPU: games shard by id (rank r owns games [r*G, (r+1)*G)); no collective on the data path; scaling is weak.
+"""
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+BYTES_PER_PLY = 115          # read S(48) + action(2); write S(48) + legal mask(16) + done(1)
+SEED = 0x7261
+GAMES = 4096
+MCTS_GAMES, MCTS_SIMS = 1024, 800
+
+
+# ------------------------------------------------------------------------------------------------ CPU reference arm
+def _cpu_worker(args):
+    """One host core: reference engine (or, if it is not built, the oracle port) playing whole games with the C2 move rule."""
+    wid, seconds, game_base = args
+    from oracle.go_oracle import OracleEnv, RefEnv, have_ref
+    from helpers import playout_action
+    kind = "reference" if have_ref(9) else "port"
+    devnull = os.open(os.devnull, os.O_WRONLY)
+    os.dup2(devnull, 1)
+    env = RefEnv(9) if kind == "reference" else OracleEnv(9)
+    plies, games = 0, 0
+    t0 = time.perf_counter()
+    while time.perf_counter() - t0 < seconds:
+        s, _ = env.reset()
+        done = False
+        g = game_base + games
+        while not done:
+            acts = env.getLegalAction(s)                       # environment.py:121-129 (ctypes + python list filter)
+            pts = [a for a in acts if a != 81]
+            s, done = env.step(s, playout_action(SEED, g, env.getStep(s), pts, 81))
+            plies += 1
+        env.getScore(s)
+        games += 1
+    return plies, games, time.perf_counter() - t0, kind
+
+
+def cpu_playout_baseline(seconds_per_core=1.5, cores=None):
+    import multiprocessing as mp
+    cores = cores or os.cpu_count() or 1
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        res = pool.map(_cpu_worker, [(w, seconds_per_core, w * 100000) for w in range(cores)])
+    plies = sum(r[0] for r in res)
+    wall = max(r[2] for r in res)
+    return dict(value=plies / wall, unit="board steps/s", cores=cores, kind=res[0][3],
+                sample="%d whole 9x9 games (%d plies) of the C2 move rule, %d processes x %.1f s, via ctypes like environment.py"
+                       % (sum(r[1] for r in res), plies, cores, seconds_per_core)), (plies, sum(r[1] for r in res), wall)
+
+
+def _cpu_mcts_worker(args):
+    wid, sims = args
+    import torch
+    torch.set_num_threads(1)
+    import numpy as np
+    from oracle.go_oracle import OracleEnv
+    from oracle.mcts_oracle import OracleMCTS, MCTSConfig
+    from oracle import provider
+    from transgo_b200.net import TransGoNetwork
+    torch.manual_seed(0)
+    net = TransGoNetwork(board_size=9).eval()
+
+    def ev(obs):
+        with torch.no_grad():
+            p, v, _ = net.main_prediction(torch.from_numpy(np.stack(obs)))
+        return p.numpy(), v.numpy()
+    cnt = [0]
+
+    def tie(n):
+        i = provider.tie_index(1, wid, cnt[0], n); cnt[0] += 1
+        return i
+    t0 = time.perf_counter()
+    m = OracleMCTS(OracleEnv(9), ev, MCTSConfig(num_simulation=sims), tie_fn=tie,
+                   noise_fn=lambda mv, k: provider.dirichlet(1, wid, mv, k), u_fn=lambda mv: provider.uniform(1, wid, mv))
+    m.get_action_probs()
+    return m.sims, time.perf_counter() - t0
+
+
+def cpu_mcts_baseline(cores=None, sims=64):
+    """self_play.py WP_MCTS restated (oracle/mcts_oracle.py, pinned bit-exact to the reference) + the TransGo net on one
+    CPU thread per process, one game per process as the reference's actors do (transgo.py:92-96)."""
+    import multiprocessing as mp
+    cores = cores or os.cpu_count() or 1
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        res = pool.map(_cpu_mcts_worker, [(w, sims) for w in range(cores)])
+    total = sum(r[0] for r in res)
+    wall = max(r[1] for r in res)
+    return dict(value=total / wall, unit="MCTS sims/s", cores=cores, kind="port",
+                sample="%d processes x one move of %d simulations (4 leaves per net call, net on 1 CPU thread each)" % (cores, sims))
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """NVML samples DURING the timed regions (B200_PROFILING.md 'clocks line')."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self._stop, self.ok = [], set(), threading.Event(), False
+        self.active = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:  # pragma: no cover
+            self.err = str(e)
+        self.t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        nv = self.nv
+        names = {nv.nvmlClocksEventReasonHwSlowdown: "hw_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksEventReasonSwThermalSlowdown: "sw_thermal_slowdown", nv.nvmlClocksEventReasonSwPowerCap: "sw_power_cap"} \
+            if hasattr(nv, "nvmlClocksEventReasonHwSlowdown") else \
+            {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown", nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+             nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown", nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap"}
+        while not self._stop.is_set():
+            if self.active.is_set():
+                try:
+                    self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                    try:
+                        r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                    except Exception:
+                        r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                    for bit, name in names.items():
+                        if r & bit:
+                            self.reasons.add(name)
+                except Exception:
+                    pass
+            time.sleep(0.005)
+
+    def start(self):
+        if self.ok:
+            self.t.start()
+
+    def stop(self):
+        self._stop.set()
+
+    def summary(self):
+        if not self.ok or not self.samples:
+            return dict(sm_mhz=None, sm_max_mhz=getattr(self, "max", None), reasons=[], samples=0)
+        return dict(sm_mhz=statistics.median(self.samples), sm_max_mhz=self.max, reasons=sorted(self.reasons), samples=len(self.samples))
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    cpu = None
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    cpu_mcts = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu, _ = cpu_playout_baseline()                        # before CUDA is initialised (fork-safe)
+        if not args.no_mcts:
+            cpu_mcts = cpu_mcts_baseline()
+    import torch
+    import torch.distributed as dist
+    from transgo_b200 import _lib
+    from transgo_b200.environment import BatchedGoEnv
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L = _lib.lib()
+    K, W, G = args.steps, max(args.warmup, 3), args.games
+    env = BatchedGoEnv(G, board_size=9, tile=args.tile, device=dev)
+    plies_max = env.max_step + 1
+    counter = torch.zeros([1], dtype=torch.int64, device=dev)
+    flush = torch.empty([64 << 20], dtype=torch.int32, device=dev)      # 256 MB > 126 MB L2
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches = [0]
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def device_step(step_idx):
+        env.reset()
+        env.playout(plies_max, seed=SEED + step_idx, game_id0=rank * G, counter=counter)
+        env.score()
+        launches[0] += 3
+
+    # ---- device-resident throughput
+    for i in range(W):
+        device_step(1000 + i)
+    counter.zero_()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    kevs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    barrier()
+    launches[0] = 0
+    sampler.active.set()
+    for i in range(K):
+        flush.zero_()                                          # L2 flush between timed iterations (outside the events)
+        evs[i][0].record()
+        env.reset()
+        kevs[i][0].record()
+        env.playout(plies_max, seed=SEED + i, game_id0=rank * G, counter=counter)
+        kevs[i][1].record()
+        env.score()
+        evs[i][1].record()
+        launches[0] += 3
+    barrier()
+    sampler.active.clear()
+    ms_total = sum(a.elapsed_time(b) for a, b in evs)
+    ms_kernel = sum(a.elapsed_time(b) for a, b in kevs)
+    plies = int(counter.item())
+    t = torch.tensor([ms_total, ms_kernel], dtype=torch.float64, device=dev)
+    p = torch.tensor([plies], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(p, op=dist.ReduceOp.SUM)
+    ms_total, ms_kernel, plies_all = float(t[0]), float(t[1]), float(p[0])
+    value = plies_all / (ms_total * 1e-3)
+
+    # ---- end to end through the C ABI with host buffers
+    SQ = env.SQ
+    h_states = torch.zeros([SQ, G, 4], dtype=torch.int32).pin_memory()
+    fresh = BatchedGoEnv(G, board_size=9, device=dev)
+    h_states.copy_(fresh.states)                               # empty boards, prepared on the host side once
+    h_out_states = torch.zeros([SQ, G, 4], dtype=torch.int32).pin_memory()
+    h_scores = torch.zeros([G], dtype=torch.float32).pin_memory()
+    h_trace = torch.zeros([plies_max, G], dtype=torch.int16).pin_memory()
+    d_trace = torch.zeros([plies_max, G], dtype=torch.int16, device=dev)
+    h2d = h_states.numel() * 4
+    d2h = h_out_states.numel() * 4 + h_scores.numel() * 4 + h_trace.numel() * 2
+
+    def e2e_step(i):
+        env.states.copy_(h_states, non_blocking=True)
+        env.playout(plies_max, seed=SEED + i, game_id0=rank * G, trace=d_trace, counter=counter)
+        sc = env.score()
+        h_out_states.copy_(env.states, non_blocking=True)
+        h_scores.copy_(sc, non_blocking=True)
+        h_trace.copy_(d_trace, non_blocking=True)
+    for i in range(W):
+        e2e_step(2000 + i)
+    counter.zero_()
+    ee = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    barrier()
+    sampler.active.set()
+    for i in range(K):
+        flush.zero_()
+        ee[i][0].record()
+        e2e_step(i)
+        ee[i][1].record()
+    barrier()
+    sampler.active.clear()
+    ms_e2e = sum(a.elapsed_time(b) for a, b in ee)
+    plies_e2e = int(counter.item())
+    t = torch.tensor([ms_e2e], dtype=torch.float64, device=dev)
+    p = torch.tensor([plies_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(p, op=dist.ReduceOp.SUM)
+    e2e_value = float(p[0]) / (float(t[0]) * 1e-3)
+    assert bool((h_scores * 2 % 2 == 1).all())                 # host really received final area scores
+
+    # ---- per-launch kernels of the stepwise API + saturation sweep (explanatory, not the headline)
+    extras = {}
+    if rank == 0 and not args.quick and not args.no_sweep:
+        extras = stepwise_and_sweep(torch, dev, BatchedGoEnv)
+
+    # ---- MCTS half of the metric
+    mcts = None
+    if not args.no_mcts:
+        sampler.active.set()
+        mcts = mcts_bench(torch, dist, dev, rank, world, args)
+        sampler.active.clear()
+    sampler.stop()
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    launch_ms = ms_kernel / K
+    plies_per_launch = plies_all / world / K
+    achieved = plies_per_launch * BYTES_PER_PLY / (launch_ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_playout_traffic.json"))).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    if rank == 0:
+        line = {
+            "metric": "board steps/sec (9x9 env-only batched random playouts) [+ MCTS sims/sec under 'mcts']",
+            "value": value, "unit": "board steps/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u32 bitboards (board), f32/f64 (tree statistics)", "data": "synthetic",
+            "config": {"workload": "BASELINE configs[1]: 9x9 env-only random playouts, %d concurrent games per GPU, empty board "
+                                   "to termination (max_step 120), hashed k-th-legal-point move rule, + area scoring" % G,
+                       "games_per_gpu": G, "tile_lanes_per_game": env.tile or "auto(32)", "board": 9,
+                       "l2": "256 MB flush buffer written between timed iterations", "sharding": "games by id, no collective"},
+            "e2e": {"value": e2e_value, "unit": "board steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": float(t[0]) / K},
+            "gpu_launches": launches[0],
+            "clocks": sampler.summary(),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "kernel": "tg::k_playout<9,%s>" % (env.tile or 32), "launch_ms": launch_ms,
+                         "bytes_per_ply": BYTES_PER_PLY, "plies_per_launch": plies_per_launch,
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
+                         "note": "integer bit-manipulation kernel: state stays in registers for ~120 plies, so it is issue-slot "
+                                 "bound, not HBM bound; see profiles/ for issue-slot utilisation"},
+            "cpu_baseline": cpu,
+        }
+        line.update(extras)
+        if mcts is not None:
+            if cpu_mcts is not None:
+                mcts["cpu_baseline"] = cpu_mcts
+            line["mcts"] = mcts
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def stepwise_and_sweep(torch, dev, BatchedGoEnv):
+    """Per-launch numbers of the stepwise API at G = 4096 and the playout saturation sweep."""
+    out = {}
+
+    def best_ms(fn, reps=5):
+        best = 1e30
+        for _ in range(reps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            a.record(); fn(); b.record()
+            torch.cuda.synchronize()
+            best = min(best, a.elapsed_time(b))
+        return best
+    env = BatchedGoEnv(GAMES, device=dev)
+    env.playout(40, seed=2)
+    act = torch.full([GAMES], 81, dtype=torch.int16, device=dev)
+    ms = best_ms(lambda: env.step(act))
+    out["step_kernel"] = {"games": GAMES, "ms": ms, "steps_per_s": GAMES / ms * 1e3, "gbps_algorithmic": GAMES * 115 / ms / 1e6}
+    ms = best_ms(lambda: env.encode())
+    out["encode_kernel"] = {"games": GAMES, "ms": ms, "positions_per_s": GAMES / ms * 1e3, "gbps_algorithmic": GAMES * 3288 / ms / 1e6}
+    sweep = []
+    for G, tile in ((4096, 32), (65536, 1), (1 << 20, 1)):
+        e = BatchedGoEnv(G, device=dev, tile=tile)
+        cnt = torch.zeros([1], dtype=torch.int64, device=dev)
+
+        def play():
+            e.reset(); cnt.zero_(); e.playout(e.max_step + 1, seed=1, counter=cnt)
+        ms = best_ms(play, 3)
+        sweep.append({"games": G, "tile": tile, "ms": ms, "steps_per_s": int(cnt.item()) / ms * 1e3})
+        del e
+    out["saturation_sweep"] = sweep
+    return out
+
+
+def mcts_bench(torch, dist, dev, rank, world, args):
+    """BASELINE configs[2]: 1024 games x 800 simulations per move.  (i) tree kernels alone: policy/value come from the
+    device-side synthetic provider; (ii) end to end with the random-init TransGo net (PyTorch, bf16 autocast + fp32)."""
+    from transgo_b200 import _lib
+    from transgo_b200.mcts import BatchedMCTS
+    from transgo_b200.net import TransGoNetwork, make_evaluator
+    L = _lib.lib()
+    G, sims = (MCTS_GAMES, MCTS_SIMS) if not args.quick else (256, 64)
+    moves = 3 if not args.tree_only else 1
+    out = {"config": {"workload": "BASELINE configs[2]: 9x9 batched MCTS self-play, %d games x %d simulations/move, 4 leaves per "
+                                  "wave and game (configure.py:33), c_puct 3/0.05, wu_loss 2, Dirichlet(0.03) root noise" % (G, sims),
+                      "games_per_gpu": G, "num_simulation": sims}}
+
+    def timed_moves(eng, moves):
+        eng.total_sims()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        a.record()
+        w0 = eng.waves
+        for _ in range(moves):
+            actions, pi, obs = eng.get_action_probs(True)
+            eng.update_with_action(actions)
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b)
+        n = eng.total_sims()
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        s = torch.tensor([n], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dist.all_reduce(s, op=dist.ReduceOp.SUM)
+        return float(s[0]) / (float(t[0]) * 1e-3), float(t[0]), float(s[0]), eng.waves - w0
+
+    wave = [0]
+    pol = torch.empty([G * 4, 82], dtype=torch.float32, device=dev)
+    val = torch.empty([G * 4], dtype=torch.float32, device=dev)
+    pol_r = torch.empty([G, 82], dtype=torch.float32, device=dev)
+    val_r = torch.empty([G], dtype=torch.float32, device=dev)
+
+    def synth(obs):
+        B = obs.shape[0]
+        p, v = (pol, val) if B == G * 4 else (pol_r, val_r)
+        _lib.check(L.tg_synth_provider(9, B, 99, wave[0], _lib.ptr(p), _lib.ptr(v), _lib.stream_ptr()))
+        wave[0] += 1
+        return p, v
+    eng = BatchedMCTS(synth, G, num_simulation=sims, tie_seed=1, game_id0=rank * G, device=dev)
+    timed_moves(eng, 1)                                        # warm-up move
+    rate, ms, n, waves = timed_moves(eng, moves)
+    out["tree_only"] = {"value": rate, "unit": "MCTS sims/s", "ms": ms, "sims": n, "moves": moves, "waves": waves,
+                        "provider": "tg_synth_provider (device-side synthetic policy/value, NOT the net)",
+                        "gbps_algorithmic": rate * 10.2e3 / 1e9, "bytes_per_sim": 10200}
+    del eng
+    if args.tree_only:
+        return out
+    torch.manual_seed(0)
+    net = TransGoNetwork(board_size=9).to(dev).eval()
+    for name, dtype in (("e2e_net_bf16", torch.bfloat16), ("e2e_net_fp32", None)):
+        if args.quick and dtype is None:
+            continue
+        eng = BatchedMCTS(make_evaluator(net, dtype=dtype, channels_last=dtype is not None), G, num_simulation=sims, tie_seed=1,
+                          game_id0=rank * G, device=dev)
+        rate, ms, n, waves = timed_moves(eng, 1)
+        out[name] = {"value": rate, "unit": "MCTS sims/s", "ms": ms, "sims": n, "moves": 1, "waves": waves,
+                     "net": "TransGoNetwork 2.97 M params random init (seed 0), eval mode, 0.457 GFLOP/position",
+                     "net_tflops": rate * 0.457e9 / 1e12}
+        del eng
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    K, W = args.steps, max(args.warmup, 1)
+    cores = os.cpu_count() or 1
+    per = 0.25                                                 # seconds per step and core: bounded sample
+    for _ in range(min(W, 2)):
+        cpu_playout_baseline(per, cores)
+    plies, wall, kind, games = 0.0, 0.0, "reference", 0
+    for _ in range(K):
+        r, (n, ng, w) = cpu_playout_baseline(per, cores)
+        kind = r["kind"]
+        plies += n
+        wall += w
+        games += ng
+    value = plies / wall
+    line = {"impl": "reference", "metric": "board steps/sec (9x9 env-only batched random playouts) [+ MCTS sims/sec under 'mcts']",
+            "value": value, "unit": "board steps/s", "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": wall / K * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int (reference C++ engine)", "data": "synthetic",
+            "config": {"workload": "BASELINE configs[1]: 9x9 env-only random playouts, same hashed move rule, whole games; each step is "
+                                   "a bounded sample of %.2f s on every host core" % per, "board": 9},
+            "cpu_baseline": {"value": value, "unit": "board steps/s", "cores": cores, "kind": kind,
+                             "sample": "%d steps x %d processes x %.2f s: %d games, %d plies" % (K, cores, per, games, int(plies))},
+            "e2e": {"value": value, "unit": "board steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--games", type=int, default=GAMES)
+    ap.add_argument("--tile", type=int, default=0)
+    ap.add_argument("--no-mcts", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="small MCTS phase, no sweep (profiling runs)")
+    ap.add_argument("--tree-only", action="store_true", help="MCTS phase: skip the end-to-end net runs (profiling runs)")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the stepwise kernels / saturation sweep")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -16,6 +16,7 @@ REFERENCE_SYMBOLS = ["Init", "Reset", "Step", "Step_", "checkAction", "isTermina
 def declared_symbols():
     src = open(HEADER).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    src = re.sub(r"^\s*#.*$", "", src, flags=re.M)          # preprocessor lines
     names = re.findall(r"\b([A-Za-z_][A-Za-z0-9_]*)\s*\([^;{]*\)\s*;", src)
     return sorted(set(names))
 
