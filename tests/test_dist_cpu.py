@@ -104,3 +104,32 @@ def test_net_is_state_dict_compatible_with_the_reference():
     with torch.no_grad():
         for a, b in zip(ref.main_prediction(x), mine.main_prediction(x)):
             assert torch.equal(a, b)
+
+
+def test_replay_ring_and_pacing_cpu(tmp_path):
+    """replay_buffer.py:16-94 semantics (ring index / full flag / sampling rule / pickle layout) and the
+    shared_storage.py + configure.py schedules."""
+    from transgo_b200.replay import ReplayRing, Pacing
+    r = ReplayRing(10, device="cpu")
+    mk = lambda b, v: (torch.full([b, 10, 9, 9], float(v)), torch.full([b, 82], float(v)), torch.full([b], float(v)), torch.full([b, 81], float(v)))
+    r.append(*mk(4, 1)); assert r.info() == {"capacity": 10, "index": 4, "full": False} and len(r) == 4
+    r.append(*mk(8, 2)); assert r.info() == {"capacity": 10, "index": 2, "full": True} and len(r) == 10
+    assert r.z.tolist() == [2, 2, 1, 1, 2, 2, 2, 2, 2, 2]                 # wrapped rows overwrote the oldest
+    o, p, z, w = r.sample(6)
+    assert o.shape == (6, 10, 9, 9) and p.shape == (6, 82) and z.shape == (6,) and w.shape == (6, 81)
+    small = ReplayRing(10, device="cpu"); small.append(*mk(3, 5))
+    assert small.sample(7)[2].tolist() == [5.0] * 7                        # fewer rows than the batch: sample with replacement
+    path = str(tmp_path / "replay_buffer0.pkl")
+    saved = r.save(path)
+    assert set(saved) == {"buffer_capacity", "index", "full", "data", "save_len"} and saved["data"].dtype == object
+    assert saved["data"][0][0].shape == (10, 9, 9) and saved["data"][0][1].shape == (82,) and saved["data"][0][3].shape == (81,)
+    r2 = ReplayRing(10, device="cpu"); r2.load(path)
+    assert torch.equal(r2.z.sort().values, r.z.sort().values)
+    pc = Pacing()
+    pc.add_play_steps(11); assert pc.train_play_ratio == 7500 / 100000     # no change before the first finished game
+    pc.add_play_games(1); pc.add_play_steps(1)
+    assert pc.now_play_steps == 12 and pc.train_play_ratio == 7500 / 100000
+    pc.add_play_steps(5)                                                   # step 17: (17 + 1) % 6 == 0 -> +1e-5
+    assert abs(pc.train_play_ratio - (7500 + 1) / 100000) < 1e-12
+    assert pc.selfplay_should_wait() and not pc.trainer_should_wait()
+    pc.add_play_games(1498); assert pc.learn_rate == 6.5e-5 / 2            # game 1499: (1499 + 1) % 1500 == 0

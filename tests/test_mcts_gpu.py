@@ -218,3 +218,24 @@ def test_full_size_invariants_with_device_provider():
     assert s1 == int(n1.sum().item())
     assert bool((pi1.sum(1) - 1).abs().max() < 1e-12)
     assert bool((c1.gather(1, a1.long()[:, None]) >= 2).all())             # counts of 1 are zeroed before sampling (:668)
+
+
+def test_selfplay_worker_labels_and_augmentation(oracle_built):
+    """self_play.py:917-965 for a batch: positions are labelled with the final winner / ownership from the mover's view and
+    expanded x8; the recorded root observations replay on the oracle."""
+    from oracle.go_oracle import OracleEnv
+    from transgo_b200.selfplay import SelfPlayWorker
+    w = SelfPlayWorker(cpu_provider(5, 6), 4, num_simulation=16, max_step=10, tie_seed=5)
+    out = w.play_games(augment=False)
+    n = out["positions"]
+    assert out["obs"].shape == (n, 10, 9, 9) and out["pi"].shape == (n, 82) and out["z"].shape == (n,) and out["own"].shape == (n, 81)
+    assert 4 <= n <= 40 and set(out["z"].cpu().tolist()) <= {1.0, -1.0}
+    assert bool(((out["pi"].sum(1) - 1).abs() < 1e-5).all())
+    winner = out["winner"].cpu().numpy(); score = out["score"].cpu().numpy()
+    assert ((score > 0) == (winner == 1)).all()
+    # first recorded position of each game is the empty board with black to move: z = +1 iff black won
+    first = out["obs"].reshape(n, -1).abs().sum(1) == 0
+    zs = out["z"][first].cpu().numpy()
+    assert first.sum().item() == 4 and sorted(zs.tolist()) == sorted(np.where(winner == 1, 1.0, -1.0).tolist())
+    aug = w.play_games(augment=True)
+    assert aug["obs"].shape[0] == 8 * aug["positions"] and aug["pi"].shape == (8 * aug["positions"], 82)

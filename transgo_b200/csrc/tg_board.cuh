@@ -161,27 +161,32 @@ template <int N> __device__ __forceinline__ int bb_lowest(const BB<N>& a) {   //
     for (int i = Geo<N>::W - 1; i >= 0; --i) if (a.w[i]) p = wb_to_pt<N>(i, ffs0(a.w[i]));
     return p;
 }
-// k-th (0-based, ascending action order) point of a set; k < count(a)
-template <int N> __device__ __forceinline__ int bb_nth(const BB<N>& a, int k) {
-    int p = -1; bool found = false;
+// word index + bit index of the k-th (0-based, ascending action order) point of a set; wi = -1 when k is out of range.
+template <int N> __device__ __forceinline__ void bb_locate(const BB<N>& a, int k, int& wi, int& bit) {
+    using word_t = typename Geo<N>::word_t;
+    wi = -1;
+    word_t sel = 0;
+    int kk = 0;
     TG_FOR_W {
-        int c = popc(a.w[i]);
-        if (!found && k < c) { p = wb_to_pt<N>(i, nth_bit(a.w[i], k)); found = true; }
+        const int c = popc(a.w[i]);
+        const bool here = wi < 0 && k >= 0 && k < c;
+        sel = here ? a.w[i] : sel;
+        kk = here ? k : kk;
+        wi = here ? i : wi;
         k -= c;
     }
-    return p;
+    bit = nth_bit(sel, kk);
 }
-// single-bit set holding the k-th point of a (empty set when k >= count)
+// k-th point of a set; k < count(a)
+template <int N> __device__ __forceinline__ int bb_nth(const BB<N>& a, int k) {
+    int wi, bit; bb_locate<N>(a, k, wi, bit);
+    return wb_to_pt<N>(wi, bit);
+}
+// single-bit set holding the k-th point of a (empty set when k is out of range)
 template <int N> __device__ __forceinline__ BB<N> bb_nth_bit(const BB<N>& a, int k) {
     using word_t = typename Geo<N>::word_t;
-    BB<N> r; bool found = false;
-    TG_FOR_W {
-        int c = popc(a.w[i]);
-        bool here = !found && k >= 0 && k < c;
-        r.w[i] = here ? (word_t(1) << nth_bit(a.w[i], here ? k : 0)) : word_t(0);
-        found |= here;
-        k -= c;
-    }
+    int wi, bit; bb_locate<N>(a, k, wi, bit);
+    BB<N> r; TG_FOR_W r.w[i] = (i == wi) ? (word_t(1) << bit) : word_t(0);
     return r;
 }
 
@@ -325,14 +330,34 @@ template <int N, int T> __device__ __forceinline__ BB<N> tile_or(const BB<N>& a)
 
 // flood `seed` through `mask` (4-connectivity) until no lane of the tile changes any more.
 template <int N, int T> __device__ __forceinline__ BB<N> flood(BB<N> g, const BB<N>& mask) {
-    bool ch;
-    do {
+    bool ch = any(g);
+    while (Tile<T>::any(ch)) {
         BB<N> n1 = (g | nbrs(g)) & mask;
         BB<N> n2 = (n1 | nbrs(n1)) & mask;
         ch = differs(n2, g);
         g = n2;
-    } while (Tile<T>::any(ch));
+    }
     return g;
+}
+
+// Flood the group of `seed` inside `col` and count its liberties, but stop caring once `lim` liberties are known:
+// callers only distinguish 1 / 2 / >=3 liberties (board_feature.cc:17-41, board.cc:130-158), and big groups reach the
+// limit in the first step.  On return `complete` tells whether g is the whole group (then libs is exact); otherwise
+// libs >= lim.  The loop is tile-uniform: it runs until no lane still needs another step.
+template <int N, int T>
+__device__ __forceinline__ void flood_group(BB<N>& g, const BB<N>& col, const BB<N>& empty, int lim, int& libs, bool& complete) {
+    bool ch = any(g);
+    libs = 0;
+    complete = true;
+    while (true) {
+        const BB<N> nb = nbrs(g);
+        const BB<N> n1 = (g | nb) & col;
+        libs = count(nb & empty);
+        ch = differs(n1, g);
+        g = n1;
+        complete = !ch;
+        if (!Tile<T>::any(ch && libs < lim)) break;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -361,7 +386,8 @@ template <int N> __device__ __forceinline__ BB<N> true_eyes(const BB<N>& own, co
     return andn(eye, fake);
 }
 
-template <int N, int T, bool WANT_LIVES>
+// WANT_L2: also classify "exactly two liberties" (feature planes); without it only l1 is produced (rules).
+template <int N, int T, bool WANT_LIVES, bool WANT_L2 = WANT_LIVES>
 __device__ __forceinline__ void analyse_groups(const BB<N>& black, const BB<N>& white, int me /*1|2*/, Groups<N>& out) {
     using G = Geo<N>;
     const BB<N> empty = bb_not(black | white);
@@ -369,25 +395,29 @@ __device__ __forceinline__ void analyse_groups(const BB<N>& black, const BB<N>& 
     const BB<N> lb = andn(andn(black, shift_e(black)), shift_s(black));
     const BB<N> lw = andn(andn(white, shift_e(white)), shift_s(white));
     const int nb = count(lb), total = nb + count(lw);
-    BB<N> eyes_me;
-    if (WANT_LIVES) eyes_me = (me == kBlack) ? true_eyes(black, white) : true_eyes(white, black);
+    BB<N> eyes_me = bb_zero<N>();
+    bool has_eyes = false;
+    if (WANT_LIVES) {
+        eyes_me = (me == kBlack) ? true_eyes(black, white) : true_eyes(white, black);
+        has_eyes = any(eyes_me);
+    }
     BB<N> p1b = bb_zero<N>(), p1w = p1b, p2b = p1b, p2w = p1b, plv = p1b;
-    for (int base = 0; Tile<T>::any(base < total); base += T) {
+    for (int base = 0; base < total; base += T) {
         const int j = base + Tile<T>::lane();
-        const bool is_w = j >= nb;
-        BB<N> seed = bb_nth_bit<N>(is_w ? lw : lb, (j < total) ? (is_w ? j - nb : j) : -1);
-        const BB<N> col = bb_select(is_w, white, black);
-        BB<N> g = flood<N, T>(seed, col);
-        BB<N> libs = nbrs(g) & empty;
-        const int c = count(libs);
         const bool valid = j < total;
+        const bool is_w = j >= nb;
+        BB<N> g = bb_nth_bit<N>(is_w ? lw : lb, valid ? (is_w ? j - nb : j) : -1);
+        const BB<N> col = bb_select(is_w, white, black);
+        const bool mine = WANT_LIVES && has_eyes && valid && ((me == kWhite) == is_w);
+        int c; bool complete;
+        flood_group<N, T>(g, col, empty, mine ? 1 << 20 : (WANT_L2 ? 3 : 2), c, complete);
+        const bool is1 = valid && complete && c == 1, is2 = WANT_L2 && valid && complete && c == 2;
         TG_FOR_W {
-            typename G::word_t m1 = (valid && c == 1) ? g.w[i] : 0, m2 = (valid && c == 2) ? g.w[i] : 0;
+            const typename G::word_t m1 = is1 ? g.w[i] : 0, m2 = is2 ? g.w[i] : 0;
             p1b.w[i] |= is_w ? 0 : m1; p1w.w[i] |= is_w ? m1 : 0;
-            p2b.w[i] |= is_w ? 0 : m2; p2w.w[i] |= is_w ? m2 : 0;
+            if (WANT_L2) { p2b.w[i] |= is_w ? 0 : m2; p2w.w[i] |= is_w ? m2 : 0; }
         }
-        if (WANT_LIVES) {
-            const bool mine = valid && ((me == kWhite) == is_w) && c >= 2;
+        if (WANT_LIVES && has_eyes) {                               // tile-uniform
             // candidate eyes of this block, then the diagonal test of board.cc:775-815
             BB<N> E = nbrs(g) & eyes_me;
             BB<N> bad = bb_not(col | E);                            // on-board points that are neither own stones nor candidate eyes
@@ -397,21 +427,21 @@ __device__ __forceinline__ void analyse_groups(const BB<N>& black, const BB<N>& 
             BB<N> twod = (d1 & d2) | ((d1 | d2) & d3) | ((d1 | d2 | d3) & d4);
             BB<N> good;
             TG_FOR_W good.w[i] = E.w[i] & ((G::emask(i) & ~anyd.w[i]) | (~G::emask(i) & ~twod.w[i]));
-            const bool alive = mine && count(good) >= 2;
+            const bool alive = mine && c >= 2 && count(good) >= 2;
             TG_FOR_W plv.w[i] |= alive ? g.w[i] : 0;
         }
     }
     out.l1[0] = tile_or<N, T>(p1b); out.l1[1] = tile_or<N, T>(p1w);
-    out.l2[0] = tile_or<N, T>(p2b); out.l2[1] = tile_or<N, T>(p2w);
-    if (WANT_LIVES) out.lives = tile_or<N, T>(plv); else out.lives = bb_zero<N>();
+    if (WANT_L2) { out.l2[0] = tile_or<N, T>(p2b); out.l2[1] = tile_or<N, T>(p2w); }
+    else { out.l2[0] = bb_zero<N>(); out.l2[1] = bb_zero<N>(); }
+    if (WANT_LIVES && has_eyes) out.lives = tile_or<N, T>(plv); else out.lives = bb_zero<N>();
 }
 
 // Points that are suicide for `me` (board.cc:130-158 over every empty point, ko ignored): no empty neighbour,
 // no own neighbour group with >1 liberty, no enemy neighbour group with exactly 1 liberty.
 template <int N> __device__ __forceinline__ BB<N> suicide_points(const BB<N>& own, const BB<N>& opp, const BB<N>& l1own, const BB<N>& l1opp) {
     BB<N> empty = bb_not(own | opp);
-    BB<N> safe = nbrs(empty) | nbrs(andn(own, l1own)) | nbrs(l1opp);
-    return andn(empty, safe);
+    return andn(empty, nbrs(empty | andn(own, l1own) | l1opp));
 }
 
 // Legal board points for the player to move (board.cc:467-489 / TryPlay :437-464).
@@ -427,8 +457,9 @@ template <int N> __device__ __forceinline__ BB<N> legal_points(const Pos<N>& s, 
 // One move.  `action` in [0,P) places a stone, P or -1 passes, -2 resigns (go_env.cc:51-80, board.cc:546-661).
 // Returns done; *accepted = false when the reference would print "invalid action" and keep the state.
 // g must be the analysis of the position BEFORE the move (only l1 is used).
+// trusted = the caller took `action` from legal_points() of this very position (playouts, MCTS): skip the re-check.
 template <int N, int T>
-__device__ __forceinline__ bool apply_move(Pos<N>& s, const Groups<N>& g, int action, int max_step, bool& accepted) {
+__device__ __forceinline__ bool apply_move(Pos<N>& s, const Groups<N>& g, int action, int max_step, bool& accepted, bool trusted = false) {
     using GG = Geo<N>;
     accepted = false;
     if (s.terminated) return true;                                   // go_env.cc:52-55
@@ -441,21 +472,24 @@ __device__ __forceinline__ bool apply_move(Pos<N>& s, const Groups<N>& g, int ac
     } else {
         if (action < 0 || action >= GG::P) return false;
         const BB<N> pb = bb_point<N>(action);
-        const BB<N> lg = legal_points(s, g);
-        if (!any(lg & pb)) return false;                             // occupied / ko / suicide (board.cc:448-462)
+        if (!trusted && !any(legal_points(s, g) & pb)) return false; // occupied / ko / suicide (board.cc:448-462)
         const BB<N> own = stones_of(s, me), opp = stones_of(s, op);
         const BB<N> l1opp = l1_of(g, op);
         const BB<N> empty = bb_not(own | opp);
         const BB<N> around = nbrs(pb);
-        // simple-ko bookkeeping, decided before captures (board.cc:163-194, 561-570)
-        const BB<N> singles = andn(opp, nbrs(opp));
-        const BB<N> cand = around & singles & l1opp;
-        const bool ko = !any(around & empty) && !any(around & own) && count(cand) == 1;
-        if (ko) { s.ko_loc = bb_lowest(cand); s.ko_color = 3 - s.player; s.ko_age = 0; }
-        else s.ko_age += 1;
+        // simple-ko bookkeeping, decided before captures (board.cc:163-194, 561-570): no empty and no own neighbour, and
+        // exactly one enemy neighbour block that is a single stone in atari
+        const BB<N> hit = around & l1opp;                            // enemy neighbours in atari: they die
+        bool ko = false;
+        if (any(hit) && !any(around & (empty | own))) {              // rare, tile-uniform
+            const BB<N> cand = andn(hit, nbrs(opp));                 // ... that are single stones
+            ko = count(cand) == 1;
+            if (ko) { s.ko_loc = bb_lowest(cand); s.ko_color = 3 - s.player; s.ko_age = 0; }
+        }
+        if (!ko) s.ko_age += 1;
         // captures: every enemy neighbour group whose single liberty was this point (board.cc:606-630).
         // Distinct groups inside l1[op] never touch, so flooding inside l1[op] lifts exactly the seeded groups.
-        BB<N> dead = flood<N, T>(around & l1opp, l1opp);
+        BB<N> dead = flood<N, T>(hit, l1opp);
         set_stones(s, op, andn(opp, dead));
         set_stones(s, me, own | pb);
         s.player = 3 - s.player; s.last2 = s.last1; s.last1 = action; s.step += 1;

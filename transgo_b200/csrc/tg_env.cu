@@ -136,7 +136,7 @@ k_playout(uint4* __restrict__ states, long long G, int plies, int max_step, unsi
                 action = bb_nth<N>(lg, (int)(((unsigned long long)r * (unsigned)nl) >> 32));
             }
             bool acc;
-            apply_move<N, T>(s, gr, action, max_step, acc);
+            apply_move<N, T>(s, gr, action, max_step, acc, true);
             played += 1;
         }
         if (trace && Tile<T>::lane() == 0) trace[(long long)t * G + g] = (int16_t)action;

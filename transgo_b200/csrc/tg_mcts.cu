@@ -228,7 +228,7 @@ __global__ void __launch_bounds__(kThreads) k_select(View v) {
             if (!is_pass) analyse_groups<N, 32, false>(s.stones[0], s.stones[1], s.player, gr);
             else { gr.l1[0] = gr.l1[1] = gr.l2[0] = gr.l2[1] = gr.lives = bb_zero<N>(); }
             bool acc;
-            apply_move<N, 32>(s, gr, action, v.max_step, acc);
+            apply_move<N, 32>(s, gr, action, v.max_step, acc, true);
             BB<N> bt, wt;
             const int raw = area_score<N, 32>(s.stones[0], s.stones[1], bt, wt);
             const int winner = ((float)raw - v.komi) > 0.0f ? kBlack : kWhite;          // environment.py:118-119
@@ -268,7 +268,7 @@ __global__ void __launch_bounds__(kThreads) k_leaves(View v, float* __restrict__
     Groups<N> gr;
     analyse_groups<N, 32, false>(s.stones[0], s.stones[1], s.player, gr);
     bool acc;
-    apply_move<N, 32>(s, gr, v.leaf_action[slot], v.max_step, acc);
+    apply_move<N, 32>(s, gr, v.leaf_action[slot], v.max_step, acc, true);
     BB<N> pl[10];
     Groups<N> g2;
     feature_planes_g<N, 32>(s, pl, g2);
@@ -533,7 +533,7 @@ __global__ void __launch_bounds__(kThreads) k_advance(View v, const int16_t* __r
     Groups<N> gr;
     analyse_groups<N, 32, false>(s.stones[0], s.stones[1], s.player, gr);
     bool acc;
-    const bool done = apply_move<N, 32>(s, gr, action, v.max_step, acc);
+    const bool done = apply_move<N, 32>(s, gr, action, v.max_step, acc, true);
     if (lane == 0) pos_store<N>(s, v.root_state, g, v.G, 1);
     const uint4 qe = shot[ksel];
     const uint2 ce = scold[ksel];

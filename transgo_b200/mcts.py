@@ -144,8 +144,11 @@ class BatchedMCTS:
         return st
 
     def total_sims(self):
+        """Simulations (net-evaluated leaves + terminal backups) since the previous call."""
         self.check_status()
-        return int(self.sims.item())
+        n = int(self.sims.item())
+        self.sims.zero_()
+        return n
 
     # ---------------------------------------------------------------- the reference surface
     def reset_root(self):                                   # self_play.py:595-605
