@@ -295,6 +295,9 @@ def run_ours(args):
         sampler.active.set()
         mcts = mcts_bench(torch, dist, dev, rank, world, args)
         sampler.active.clear()
+    c4 = None
+    if rank == 0 and not args.quick and not args.no_sweep and not args.no_mcts:
+        c4 = c4_bench(torch, dev, BatchedGoEnv)
     sampler.stop()
 
     peaks = {}
@@ -338,6 +341,8 @@ def run_ours(args):
             if cpu_mcts is not None:
                 mcts["cpu_baseline"] = cpu_mcts
             line["mcts"] = mcts
+        if c4 is not None:
+            line["c4_19x19"] = c4
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -377,9 +382,51 @@ def stepwise_and_sweep(torch, dev, BatchedGoEnv):
     return out
 
 
+def c4_bench(torch, dev, BatchedGoEnv):
+    """BASELINE configs[3] (board-size generalisation): 19x19, 512 games; env playouts and one tree-only search move of 400
+    simulations.  Explanatory numbers, not the headline."""
+    from transgo_b200 import _lib
+    from transgo_b200.mcts import BatchedMCTS
+    L = _lib.lib()
+    G, sims = 512, 400
+    env = BatchedGoEnv(G, board_size=19, device=dev)
+    cnt = torch.zeros([1], dtype=torch.int64, device=dev)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    env.playout(50, seed=3)
+    env.reset(); torch.cuda.synchronize()
+    a.record(); env.playout(env.max_step + 1, seed=1, counter=cnt); b.record(); torch.cuda.synchronize()
+    out = {"config": "19x19, %d games, max_step %d; MCTS %d simulations/move" % (G, env.max_step, sims),
+           "playout_steps_per_s": int(cnt.item()) / a.elapsed_time(b) * 1e3, "playout_ms": a.elapsed_time(b)}
+    del env
+    wave = [0]
+    pol = {G * 4: torch.empty([G * 4, 362], dtype=torch.float32, device=dev), G: torch.empty([G, 362], dtype=torch.float32, device=dev)}
+    val = {G * 4: torch.empty([G * 4], dtype=torch.float32, device=dev), G: torch.empty([G], dtype=torch.float32, device=dev)}
+
+    def synth(obs):
+        B = obs.shape[0]
+        _lib.check(L.tg_synth_provider(19, B, 7, wave[0], _lib.ptr(pol[B]), _lib.ptr(val[B]), _lib.stream_ptr()))
+        wave[0] += 1
+        return pol[B], val[B]
+    eng = BatchedMCTS(synth, G, board_size=19, num_simulation=sims, tie_seed=1, device=dev)
+    actions, _, _ = eng.get_action_probs(True)
+    eng.update_with_action(actions)
+    eng.total_sims()
+    torch.cuda.synchronize()
+    a.record()
+    actions, _, _ = eng.get_action_probs(True)
+    eng.update_with_action(actions)
+    b.record(); torch.cuda.synchronize()
+    n = eng.total_sims()
+    out["mcts_tree_only_sims_per_s"] = n / a.elapsed_time(b) * 1e3
+    out["mcts_ms_per_move"] = a.elapsed_time(b)
+    out["workspace_gb"] = eng.workspace_bytes / 1e9
+    return out
+
+
 def mcts_bench(torch, dist, dev, rank, world, args):
     """BASELINE configs[2]: 1024 games x 800 simulations per move.  (i) tree kernels alone: policy/value come from the
-    device-side synthetic provider; (ii) end to end with the random-init TransGo net (PyTorch, bf16 autocast + fp32)."""
+    device-side synthetic provider; (ii) end to end with the random-init TransGo net (PyTorch: bf16 weights + channels_last,
+    and fp32), forward replayed as a CUDA graph on the engine's static input tensors."""
     from transgo_b200 import _lib
     from transgo_b200.mcts import BatchedMCTS
     from transgo_b200.net import TransGoNetwork, make_evaluator
@@ -438,8 +485,8 @@ def mcts_bench(torch, dist, dev, rank, world, args):
     for name, dtype in (("e2e_net_bf16", torch.bfloat16), ("e2e_net_fp32", None)):
         if args.quick and dtype is None:
             continue
-        eng = BatchedMCTS(make_evaluator(net, dtype=dtype, channels_last=dtype is not None), G, num_simulation=sims, tie_seed=1,
-                          game_id0=rank * G, device=dev)
+        eng = BatchedMCTS(make_evaluator(net, dtype=dtype, channels_last=dtype is not None, cuda_graph=True), G,
+                          num_simulation=sims, tie_seed=1, game_id0=rank * G, device=dev)
         rate, ms, n, waves = timed_moves(eng, 1)
         out[name] = {"value": rate, "unit": "MCTS sims/s", "ms": ms, "sims": n, "moves": 1, "waves": waves,
                      "net": "TransGoNetwork 2.97 M params random init (seed 0), eval mode, 0.457 GFLOP/position",

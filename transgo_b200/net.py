@@ -108,17 +108,49 @@ class TransGoNetwork(nn.Module):
         self.load_state_dict(weights)
 
 
-def make_evaluator(model, dtype=None, channels_last=False):
-    """obs [B,10,n,n] float32 -> (policy float32 [B,A], value float32 [B]) under no_grad; optional autocast dtype."""
+def make_evaluator(model, dtype=None, channels_last=False, cuda_graph=False):
+    """obs [B,10,n,n] float32 -> (policy float32 [B,A], value float32 [B]) under no_grad.
+
+    dtype None / float32: the model as it is (parity runs).  dtype bfloat16 / float16: an inference COPY of the model with
+    weights converted once (and channels_last when asked) -- 1.4x faster than autocast at the wave batch on B200 because
+    no per-call casts remain.  cuda_graph: capture the forward once per input shape and replay it (the search always
+    calls with the same two static input tensors: the leaf batch and the root batch)."""
+    import copy
     model.eval()
+    low = dtype is not None and dtype != torch.float32
+    run_model = model
+    if low:
+        run_model = copy.deepcopy(model).to(dtype)
+        if channels_last:
+            run_model = run_model.to(memory_format=torch.channels_last)
+        run_model.eval()
+    graphs = {}
+
+    def forward(obs):
+        x = obs.to(dtype) if low else obs
+        if channels_last:
+            x = x.contiguous(memory_format=torch.channels_last)
+        p, v, _ = run_model.main_prediction(x)
+        return p.float(), v.float().reshape(-1)
 
     def evaluator(obs):
         with torch.no_grad():
-            x = obs.contiguous(memory_format=torch.channels_last) if channels_last else obs
-            if dtype is not None and dtype != torch.float32:
-                with torch.autocast("cuda", dtype=dtype):
-                    p, v, _ = model.main_prediction(x)
-            else:
-                p, v, _ = model.main_prediction(x)
-        return p.float(), v.float().reshape(-1)
+            if not cuda_graph:
+                return forward(obs)
+            key = (obs.data_ptr(), tuple(obs.shape))
+            if key not in graphs:
+                s = torch.cuda.Stream()
+                s.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(s):
+                    for _ in range(3):
+                        forward(obs)
+                torch.cuda.current_stream().wait_stream(s)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    out = forward(obs)
+                graphs[key] = (g, out)
+            g, out = graphs[key]
+            g.replay()
+            return out
+    evaluator.refresh = lambda: run_model.load_state_dict({k: v.to(dtype) if v.is_floating_point() else v for k, v in model.state_dict().items()}) if low else None
     return evaluator
