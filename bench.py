@@ -376,7 +376,17 @@ def stepwise_and_sweep(torch, dev, BatchedGoEnv):
         def play():
             e.reset(); cnt.zero_(); e.playout(e.max_step + 1, seed=1, counter=cnt)
         ms = best_ms(play, 3)
-        sweep.append({"games": G, "tile": tile, "ms": ms, "steps_per_s": int(cnt.item()) / ms * 1e3})
+        row = {"games": G, "tile": tile, "ms": ms, "steps_per_s": int(cnt.item()) / ms * 1e3}
+        if G >= 65536:                                         # the HBM-heavy kernels at saturation (mid-game positions)
+            e.reset(); e.playout(60, seed=4)
+            acts = torch.full([G], 81, dtype=torch.int16, device=dev)
+            ms_s = best_ms(lambda: e.step(acts), 3)
+            buf = torch.empty([G, 10, 9, 9], dtype=torch.float32, device=dev)
+            ms_e = best_ms(lambda: e.encode(out=buf), 3)
+            row.update(step_kernel_per_s=G / ms_s * 1e3, step_kernel_gbps=G * 115 / ms_s / 1e6,
+                       encode_per_s=G / ms_e * 1e3, encode_gbps=G * 3288 / ms_e / 1e6)
+            del buf
+        sweep.append(row)
         del e
     out["saturation_sweep"] = sweep
     return out
@@ -482,14 +492,17 @@ def mcts_bench(torch, dist, dev, rank, world, args):
         return out
     torch.manual_seed(0)
     net = TransGoNetwork(board_size=9).to(dev).eval()
-    for name, dtype in (("e2e_net_bf16", torch.bfloat16), ("e2e_net_fp32", None)):
+    from transgo_b200.fused_net import make_fused_evaluator
+    for name, dtype in (("e2e_net_bf16_fused", "fused"), ("e2e_net_bf16", torch.bfloat16), ("e2e_net_fp32", None)):
         if args.quick and dtype is None:
             continue
-        eng = BatchedMCTS(make_evaluator(net, dtype=dtype, channels_last=dtype is not None, cuda_graph=True), G,
-                          num_simulation=sims, tie_seed=1, game_id0=rank * G, device=dev)
+        ev = make_fused_evaluator(net, cuda_graph=True) if dtype == "fused" else \
+            make_evaluator(net, dtype=dtype, channels_last=dtype is not None, cuda_graph=True)
+        eng = BatchedMCTS(ev, G, num_simulation=sims, tie_seed=1, game_id0=rank * G, device=dev)
         rate, ms, n, waves = timed_moves(eng, 1)
         out[name] = {"value": rate, "unit": "MCTS sims/s", "ms": ms, "sims": n, "moves": 1, "waves": waves,
-                     "net": "TransGoNetwork 2.97 M params random init (seed 0), eval mode, 0.457 GFLOP/position",
+                     "net": "TransGoNetwork 2.97 M params random init (seed 0), eval mode, 0.457 GFLOP/position" +
+                            ("; BN folded, NHWC bf16, junctions fused by tg_net_add_bn_relu" if dtype == "fused" else ""),
                      "net_tflops": rate * 0.457e9 / 1e12}
         del eng
     return out

@@ -188,6 +188,14 @@ int tg_mcts_outcome(const TgMctsConfig* cfg, void* ws, uint8_t* winner, float* s
  * heavy-tailed hash weights of (seed, row, wave), value in (-1, 1).  NOT the reference net. */
 int tg_synth_provider(int n, int64_t rows, uint64_t seed, uint64_t wave, float* policy, float* value, void* stream);
 
+/* ---------------------------------------------------------------- (4) inference epilogue of the policy/value net
+ * One pass over NHWC bf16 activations [rows][channels] (channels % 8 == 0):
+ *     sum = x + alpha * y   (y may be NULL: sum = x)        -> sum_out (may be NULL)
+ *     act = relu(sum * scale[c] + shift[c])                 -> act_out (may be NULL)
+ * i.e. a residual junction of model.py:208-262 / :286-314 with the next eval-mode BatchNorm folded to scale/shift (f32). */
+int tg_net_add_bn_relu(const void* x, const void* y, float alpha, const float* scale, const float* shift,
+                       void* sum_out, void* act_out, int64_t rows, int channels, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -49,3 +49,11 @@ with torch.no_grad():
     with profile(activities=[ProfilerActivity.CUDA]) as prof:
         nb.main_prediction(xb); torch.cuda.synchronize()
     print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=14, max_name_column_width=70))
+    from transgo_b200.fused_net import FusedTransGoInference, make_fused_evaluator
+    fn = FusedTransGoInference(net)
+    report("fused inference (eager)", t_ms(lambda: fn(x)))
+    ev = make_fused_evaluator(net, cuda_graph=True)
+    report("fused inference + CUDA graph", t_ms(lambda: ev(x)))
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        fn(x); torch.cuda.synchronize()
+    print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=16, max_name_column_width=80))

@@ -1,0 +1,85 @@
+"""GPU numerics tests of the inference path of the policy/value net: the hand-written junction kernel against a plain
+PyTorch fp32 restatement of the same op (bit-equal: same rounding points), and the fused bf16 forward against the fp32
+module (tolerance stated below; bf16 storage has 8 mantissa bits)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+
+def _perturbed_model(seed=0, features=128):
+    from transgo_b200.net import TransGoNetwork
+    torch.manual_seed(seed)
+    m = TransGoNetwork(board_size=9, num_features=features).cuda().eval()
+    with torch.no_grad():
+        for mod in m.modules():
+            if isinstance(mod, torch.nn.BatchNorm2d):
+                mod.running_mean.normal_(0, 0.2); mod.running_var.uniform_(0.5, 1.5)
+                mod.weight.uniform_(0.7, 1.3); mod.bias.normal_(0, 0.1)
+        for k, p in m.named_parameters():
+            if k.endswith("gamma"):
+                p.fill_(0.4)
+    return m
+
+
+@pytest.mark.parametrize("rows,C,with_y,want_sum,want_act", [(81 * 7, 128, True, True, True), (81 * 3, 128, False, False, True),
+                                                              (1000, 64, True, True, False), (5, 8, True, False, True)])
+def test_junction_kernel_matches_fp32_reference(rows, C, with_y, want_sum, want_act):
+    from transgo_b200 import _lib
+    L = _lib.lib()
+    g = torch.Generator(device="cuda"); g.manual_seed(rows + C)
+    x = torch.randn([rows, C], device="cuda", generator=g).to(torch.bfloat16)
+    y = torch.randn([rows, C], device="cuda", generator=g).to(torch.bfloat16) if with_y else None
+    scale = torch.rand([C], device="cuda", generator=g) + 0.5
+    shift = torch.randn([C], device="cuda", generator=g)
+    alpha = 0.37
+    s_out = torch.empty_like(x) if want_sum else None
+    a_out = torch.empty_like(x) if want_act else None
+    _lib.check(L.tg_net_add_bn_relu(_lib.ptr(x), _lib.ptr(y), alpha, _lib.ptr(scale), _lib.ptr(shift), _lib.ptr(s_out),
+                                    _lib.ptr(a_out), rows, C, _lib.stream_ptr()))
+    ref_sum = x.float() + (torch.tensor(alpha, device="cuda") * y.float() if with_y else 0.0)
+    ref_sum = ref_sum.to(torch.bfloat16)
+    ref_act = torch.relu(ref_sum.float() * scale + shift).to(torch.bfloat16)
+    if want_sum:
+        assert torch.equal(s_out, ref_sum)
+    if want_act:
+        assert torch.equal(a_out, ref_act)
+
+
+def test_fused_forward_matches_fp32_module():
+    """Tolerance: policy max |dp| <= 4e-3 (probabilities), value / ownership max |dv| <= 4e-2 -- bf16 activations through
+    26 convolution layers; argmax of the policy must agree wherever the fp32 margin exceeds the tolerance."""
+    from transgo_b200.fused_net import FusedTransGoInference
+    m = _perturbed_model()
+    fused = FusedTransGoInference(m)
+    g = torch.Generator(device="cuda"); g.manual_seed(3)
+    obs = (torch.rand([257, 10, 9, 9], device="cuda", generator=g) > 0.75).float()
+    with torch.no_grad():
+        p0, v0, o0 = m.main_prediction(obs)
+    p1, v1, o1 = fused(obs)
+    assert p1.shape == p0.shape and v1.shape == (257,) and o1.shape == o0.shape
+    assert float((p1.sum(1) - 1).abs().max()) < 1e-4
+    assert float((p1 - p0).abs().max()) <= 4e-3, float((p1 - p0).abs().max())
+    assert float((v1 - v0.reshape(-1)).abs().max()) <= 4e-2 and float((o1 - o0).abs().max()) <= 4e-2
+    top2 = p0.topk(2, dim=1).values
+    clear = (top2[:, 0] - top2[:, 1]) > 8e-3
+    assert bool((p1.argmax(1)[clear] == p0.argmax(1)[clear]).all())
+
+
+def test_search_runs_on_the_fused_evaluator_and_graph_replay_is_stable():
+    from transgo_b200.fused_net import make_fused_evaluator
+    from transgo_b200.mcts import BatchedMCTS
+    m = _perturbed_model(1)
+    ev = make_fused_evaluator(m, cuda_graph=True)
+    eng = BatchedMCTS(ev, 64, num_simulation=32, tie_seed=2)
+    g = torch.Generator(device="cuda"); g.manual_seed(1)
+    noise = eng.make_noise(generator=g)
+    a1, pi1, _ = eng.get_action_probs(True, noise=noise, u=torch.full([64], 0.5, dtype=torch.float64, device="cuda"))
+    c1 = eng.counts.clone()
+    ev2 = make_fused_evaluator(m, cuda_graph=False)
+    eng2 = BatchedMCTS(ev2, 64, num_simulation=32, tie_seed=2)
+    a2, pi2, _ = eng2.get_action_probs(True, noise=noise, u=torch.full([64], 0.5, dtype=torch.float64, device="cuda"))
+    assert torch.equal(c1, eng2.counts) and torch.equal(a1, a2)          # graph replay == eager, bit for bit
+    assert bool((eng.root_n >= 32).all())
+    eng.update_with_action(a1)

@@ -1,0 +1,186 @@
+"""Inference-only forward of the TransGo net (model.py:41-114) for the search's wave batches.
+
+Same weights, same maths, re-scheduled for a B200: the tensor-core work stays in PyTorch library calls (cuDNN 3x3 convolutions
+with bias+ReLU epilogue, cuBLAS GEMMs for the 1x1 convolutions / attention / heads), eval-mode BatchNorm is folded
+ - into the PRECEDING convolution where one exists (stem, the second BN of every residual block, both head convs), and
+ - into a per-channel scale/shift otherwise, applied by ONE hand-written kernel per residual junction
+   (tg_net_add_bn_relu: residual add / gamma*attention + x, next BatchNorm, ReLU in a single NHWC bf16 pass).
+Activations are NHWC bf16 end to end, so the attention blocks read them as [B, P, C] views without layout copies.
+
+``FusedTransGoInference(model)`` snapshots a ``TransGoNetwork``; ``refresh()`` re-folds after ``set_weights``.
+Numerics: bf16 storage with fp32 accumulation (library kernels) -- compared against the fp32 module in tests/test_net_gpu.py.
+"""
+import torch
+import torch.nn.functional as F
+
+from . import _lib
+from .net import _PreActResidual, _SpatialAttention
+
+
+def _fold(bn):
+    """eval-mode BatchNorm2d -> (scale, shift) float32 with y = x * scale + shift"""
+    scale = bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + bn.eps)
+    shift = bn.bias.detach().float() - bn.running_mean.detach().float() * scale
+    return scale, shift
+
+
+def _conv_bn(conv, bn, dtype, pad_in=None):
+    """conv followed by BatchNorm -> (weight [O,I,3,3] channels_last in `dtype`, bias) with the BN folded in"""
+    w, b = conv.weight.detach().float(), conv.bias.detach().float()
+    if bn is not None:
+        s, t = _fold(bn)
+        w = w * s[:, None, None, None]
+        b = b * s + t
+    if pad_in is not None and w.shape[1] < pad_in:
+        w = F.pad(w, (0, 0, 0, 0, 0, pad_in - w.shape[1]))
+    return w.to(dtype).contiguous(memory_format=torch.channels_last), b.to(dtype).contiguous()
+
+
+class FusedTransGoInference:
+    def __init__(self, model, dtype=torch.bfloat16):
+        self.model, self.dtype = model, dtype
+        self.lib = _lib.lib()
+        self.refresh()
+
+    # ------------------------------------------------------------------ weight folding
+    def refresh(self):
+        m, dt = self.model.main_network, self.dtype
+        self.n = m.board_width
+        self.P = self.n * self.n
+        dev = next(m.parameters()).device
+        self.stem = _conv_bn(m.conv1.conv[0], m.conv1.conv[1], dt, pad_in=16)
+        self.blocks = []
+        i = 2
+        while hasattr(m, "res_conv%d" % i):
+            blk = getattr(m, "res_conv%d" % i)
+            if isinstance(blk, _PreActResidual):
+                s1, t1 = _fold(blk.batchnormlize_1)
+                self.blocks.append(("R", dict(s1=s1.contiguous(), t1=t1.contiguous(),
+                                              c1=_conv_bn(blk.conv_1, blk.batchnormlize_2, dt), c2=_conv_bn(blk.conv_2, None, dt))))
+            else:
+                self.blocks.append(("A", self._attn(blk)))
+            i += 1
+        self.end = tuple(t.contiguous() for t in _fold(m.bn_res_end))
+        C, P = m.fc_val_own.in_features // (self.P), self.P
+
+        def nhwc_fc(fc, ch):                   # the reference flattens NCHW (c*P + p); our activations flatten as p*ch + c
+            w = fc.weight.detach().float().view(fc.out_features, ch, P).permute(0, 2, 1).reshape(fc.out_features, P * ch)
+            return w.to(dt).contiguous(), fc.bias.detach().to(dt).contiguous()
+        self.val_conv = _conv_bn(m.conv_val_own.conv[0], m.conv_val_own.conv[1], dt)
+        self.val_conv = (F.pad(self.val_conv[0], (0, 0, 0, 0, 0, 0, 0, 6)).contiguous(memory_format=torch.channels_last),
+                         F.pad(self.val_conv[1], (0, 6)))                      # 2 -> 8 output channels (tensor-core friendly)
+        self.fc_val_own = nhwc_fc(m.fc_val_own, 2)
+        self.fc_val = (m.fc_val.weight.detach().to(dt).contiguous(), m.fc_val.bias.detach().to(dt))
+        self.fc_own = (m.fc_own.weight.detach().to(dt).contiguous(), m.fc_own.bias.detach().to(dt))
+        self.act_attn = self._attn(m.attention_act)
+        self.act_conv = _conv_bn(m.conv_act.conv[0], m.conv_act.conv[1], dt)
+        self.act_conv = (F.pad(self.act_conv[0], (0, 0, 0, 0, 0, 0, 0, 4)).contiguous(memory_format=torch.channels_last),
+                         F.pad(self.act_conv[1], (0, 4)))                      # 4 -> 8 output channels
+        self.fc_act = nhwc_fc(m.fc_act, 4)
+        self.device = dev
+        self._bufs = {}
+
+    def _attn(self, blk):
+        dt = self.dtype
+        wq, wk, wv = (c.weight.detach().float().flatten(1) for c in (blk.query_conv, blk.key_conv, blk.value_conv))
+        bq, bk, bv = (c.bias.detach().float() for c in (blk.query_conv, blk.key_conv, blk.value_conv))
+        s, t = _fold(blk.bn)
+        return dict(w=torch.cat([wq, wk, wv], 0).to(dt).contiguous(), b=torch.cat([bq, bk, bv], 0).to(dt).contiguous(),
+                    dq=wq.shape[0], gamma=float(blk.gamma.detach().float().item()), s=s.contiguous(), t=t.contiguous())
+
+    # ------------------------------------------------------------------ pieces
+    def _junction(self, x, y, alpha, scale, shift, want_sum, want_act):
+        """x (+ alpha*y) -> (sum, relu(sum*scale+shift)); x, y: channels_last [B,C,n,n] bf16 (NHWC memory)"""
+        B, C = x.shape[0], x.shape[1]
+        rows = B * self.P
+        s_out = torch.empty_like(x) if want_sum else None
+        a_out = torch.empty_like(x) if want_act else None
+        _lib.check(self.lib.tg_net_add_bn_relu(_lib.ptr(x), _lib.ptr(y), float(alpha), _lib.ptr(scale), _lib.ptr(shift),
+                                               _lib.ptr(s_out), _lib.ptr(a_out), rows, C, _lib.stream_ptr()),
+                   "tg_net_add_bn_relu")
+        return s_out, a_out
+
+    def _attention(self, x, p):
+        """model.py:299-314 on an NHWC tensor: returns relu(bn(gamma * (V . softmax(Q^T K)) + x))"""
+        B, C = x.shape[0], x.shape[1]
+        x2 = x.permute(0, 2, 3, 1).reshape(B, self.P, C)                       # free view of channels_last memory
+        qkv = F.linear(x2, p["w"], p["b"])
+        dq = p["dq"]
+        q, k, v = qkv[..., :dq], qkv[..., dq:2 * dq], qkv[..., 2 * dq:]
+        att = torch.softmax(torch.bmm(q, k.transpose(1, 2)), dim=-1)           # [B, P, P], rows = query position
+        o = torch.bmm(att.transpose(1, 2), v)                                  # out[:, j] = sum_i att[i, j] * v[i]
+        o = o.reshape(B, self.n, self.n, C).permute(0, 3, 1, 2)                # NHWC memory, NCHW view
+        _, act = self._junction(x, o, p["gamma"], p["s"], p["t"], False, True)
+        return act
+
+    # ------------------------------------------------------------------ forward
+    @torch.no_grad()
+    def __call__(self, obs):
+        """obs float32 [B, 10, n, n] -> (policy float32 [B, A], value float32 [B], ownership float32 [B, P])"""
+        B = obs.shape[0]
+        key = (B, obs.device)
+        if key not in self._bufs:
+            self._bufs[key] = torch.zeros([B, 16, self.n, self.n], dtype=self.dtype, device=obs.device).contiguous(memory_format=torch.channels_last)
+        x16 = self._bufs[key]
+        x16[:, :obs.shape[1]] = obs
+        conv_relu = torch.cudnn_convolution_relu
+        one, pad = [1, 1], [1, 1]
+        x = conv_relu(x16, self.stem[0], self.stem[1], one, pad, one, 1)       # stem: conv + folded BN + ReLU
+        pending = None                                                         # activation already prepared for the next R block
+        nb = len(self.blocks)
+        for i, (kind, p) in enumerate(self.blocks):
+            if kind == "R":
+                a1 = pending if pending is not None else self._junction(x, None, 1.0, p["s1"], p["t1"], False, True)[1]
+                pending = None
+                h = conv_relu(a1, p["c1"][0], p["c1"][1], one, pad, one, 1)    # conv_1 + folded batchnormlize_2 + ReLU
+                y = F.conv2d(h, p["c2"][0], p["c2"][1], padding=1)
+                nxt = self.blocks[i + 1] if i + 1 < nb else None
+                if nxt is not None and nxt[0] == "R":                          # x + y and the next block's BN1 + ReLU in one pass
+                    x, pending = self._junction(x, y, 1.0, nxt[1]["s1"], nxt[1]["t1"], True, True)
+                elif nxt is None:                                              # last block: x + y, bn_res_end, ReLU
+                    x = self._junction(x, y, 1.0, self.end[0], self.end[1], False, True)[1]
+                else:
+                    x = self._junction(x, y, 1.0, None, None, True, False)[0]
+            else:
+                x = self._attention(x, p)
+        # value / ownership head (model.py:93-99)
+        hv = conv_relu(x, self.val_conv[0], self.val_conv[1], one, pad, one, 1)[:, :2]
+        hv = hv.permute(0, 2, 3, 1).reshape(B, self.P * 2)
+        hv = F.relu(F.linear(hv, *self.fc_val_own))
+        value = torch.tanh(F.linear(hv, *self.fc_val).float()).reshape(-1)
+        own = torch.tanh(F.linear(hv, *self.fc_own).float())
+        # policy head (model.py:103-111)
+        xa = self._attention(x, self.act_attn)
+        ha = conv_relu(xa, self.act_conv[0], self.act_conv[1], one, pad, one, 1)[:, :4]
+        ha = ha.permute(0, 2, 3, 1).reshape(B, self.P * 4)
+        policy = torch.softmax(F.linear(ha, *self.fc_act).float(), -1)
+        return policy, value, own
+
+
+def make_fused_evaluator(model, dtype=torch.bfloat16, cuda_graph=True):
+    """evaluator(obs) -> (policy, value) for BatchedMCTS, forward captured once per static input tensor as a CUDA graph."""
+    net = FusedTransGoInference(model, dtype)
+    graphs = {}
+
+    def evaluator(obs):
+        if not cuda_graph:
+            p, v, _ = net(obs)
+            return p, v
+        key = (obs.data_ptr(), tuple(obs.shape))
+        if key not in graphs:
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                for _ in range(3):
+                    net(obs)
+            torch.cuda.current_stream().wait_stream(s)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                out = net(obs)
+            graphs[key] = (g, out)
+        g, out = graphs[key]
+        g.replay()
+        return out[0], out[1]
+    evaluator.net = net
+    evaluator.refresh = lambda: (net.refresh(), graphs.clear())
+    return evaluator
