@@ -322,14 +322,15 @@ def run_ours(args):
             "dtype": "u32 bitboards (board), f32/f64 (tree statistics)", "data": "synthetic",
             "config": {"workload": "BASELINE configs[1]: 9x9 env-only random playouts, %d concurrent games per GPU, empty board "
                                    "to termination (max_step 120), hashed k-th-legal-point move rule, + area scoring" % G,
-                       "games_per_gpu": G, "tile_lanes_per_game": env.tile or "auto(32)", "board": 9,
+                       "games_per_gpu": G, "playout_layout": env.playout_layout() + (" (library choice)" if not env.tile else ""), "board": 9,
                        "l2": "256 MB flush buffer written between timed iterations", "sharding": "games by id, no collective"},
             "e2e": {"value": e2e_value, "unit": "board steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": float(t[0]) / K},
             "gpu_launches": launches[0],
             "clocks": sampler.summary(),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "tg::k_playout<9,%s>" % (env.tile or 32), "launch_ms": launch_ms,
+                         "traffic": traffic, "kernel": "tg::k_playout_rows<9>" if env.playout_layout() == "rows" else "tg::k_playout<9,%s>" % env.playout_layout(),
+                         "launch_ms": launch_ms,
                          "bytes_per_ply": BYTES_PER_PLY, "plies_per_launch": plies_per_launch,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
                          "note": "integer bit-manipulation kernel: state stays in registers for ~120 plies, so it is issue-slot "

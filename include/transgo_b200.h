@@ -71,7 +71,9 @@ int         tg_legal_words(int n);              /* u32 words of a dense legal ma
 
 /* All pointers are device pointers; `stream` is a cudaStream_t (NULL = default stream).
  * `tile` = lanes cooperating on one game: 32 (lowest latency, small batches) ... 1 (highest throughput,
- * very large batches); 0 lets the library choose from G. */
+ * very large batches); 0 lets the library choose from G.  tg_env_playout also takes TG_TILE_ROWS: one board ROW per lane,
+ * 31 / (n + 1) games side by side in a warp (csrc/tg_rows.cuh) -- the fastest layout at the BASELINE batch sizes. */
+#define TG_TILE_ROWS (-1)
 
 /* board.cc:13-26 + go_env.cc:34-41 */
 int tg_env_reset(int n, void* states, int64_t G, void* stream);
@@ -102,6 +104,9 @@ int tg_env_score(int n, const void* states, int64_t G, float komi, float* score,
  *   plies_done    u64[1]           += number of moves actually played (may be NULL) */
 int tg_env_playout(int n, void* states, int64_t G, int plies, int max_step, uint64_t seed, int64_t game_id0,
                    int no_eye, int16_t* trace_actions, unsigned long long* plies_done, int tile, void* stream);
+
+/* the layout tg_env_playout uses for (n, G, tile): TG_TILE_ROWS or the number of lanes per game (tile = 0: measured choice) */
+int tg_env_playout_tile(int n, int64_t G, int tile);
 
 /* board.cc:1166-1271: float32[B][C][n][n] -> float32[B][cuts][C][sub][sub] */
 int tg_sub_encode(int n, const float* enc, int64_t B, int channels, int sub, int cuts, float* out, void* stream);

@@ -85,7 +85,9 @@ def _replay_trace_with_oracle(n, trace, game_ids, seed, max_step, no_eye=False):
 
 
 @pytest.mark.parametrize("n,G,tile,no_eye", [(9, 4096, 32, False), (9, 4096, 8, False), (9, 4096, 1, False),
-                                             (9, 1024, 32, True), (19, 256, 32, False), (19, 256, 1, False)])
+                                             (9, 1024, 32, True), (19, 256, 32, False), (19, 256, 1, False),
+                                             (9, 4096, 16, False), (9, 4096, -1, False), (9, 1000, -1, True), (9, 1, -1, False),
+                                             (19, 256, -1, False), (19, 37, -1, True)])
 def test_playout_matches_oracle(oracle_built, n, G, tile, no_eye):
     """G concurrent random playouts in one launch; a sample of games is replayed on the CPU."""
     from transgo_b200.environment import BatchedGoEnv
@@ -100,7 +102,7 @@ def test_playout_matches_oracle(oracle_built, n, G, tile, no_eye):
     assert int(counter.item()) == int((tr != -3).sum())
     meta = {k: v.cpu().numpy() for k, v in env.meta().items()}
     assert meta["terminated"].all()
-    sample = np.unique(np.concatenate([np.arange(0, 24), np.random.default_rng(1).integers(0, G, 40 if n == 9 else 6)]))
+    sample = np.unique(np.concatenate([np.arange(0, min(G, 24)), np.random.default_rng(1).integers(0, G, 40 if n == 9 else 6)]))
     o, finals = _replay_trace_with_oracle(n, tr[:, sample], sample, seed, env.max_step, no_eye)
     sc, terr = env.score(want_territory=True)
     planes = env.encode()
@@ -178,12 +180,13 @@ def test_step_kernel_per_ply_against_oracle(oracle_built, n, G, tile):
 
 
 def test_tiles_agree_bit_for_bit_at_full_size():
-    """Size-independent property at the BASELINE C2 size and beyond: the three tile widths are different programs
-    (32, 8, 1 lanes per game) and must produce identical final states, scores and planes."""
+    """Size-independent property at the BASELINE C2 size and beyond: the tile widths (32, 8, 1 lanes per game) and the
+    row-per-lane layout (-1, a different formulation of the rules) are different programs and must produce identical final
+    states, scores and planes."""
     from transgo_b200.environment import BatchedGoEnv
     G = 65536
     ref = None
-    for tile in (32, 8, 1):
+    for tile in (32, 8, 1, -1):
         env = BatchedGoEnv(G, board_size=9, tile=tile)
         env.playout(122, seed=99)
         out = (env.states.clone(), env.score(), env.encode(), env.legal_mask().clone())
@@ -208,8 +211,9 @@ def test_playout_is_resumable_and_deterministic():
     a = BatchedGoEnv(2048, tile=32); a.playout(122, seed=5)
     b = BatchedGoEnv(2048, tile=32); b.playout(50, seed=5); b.playout(72, seed=5)
     c = BatchedGoEnv(1024, tile=32); c.playout(122, seed=5, game_id0=1024)
+    d = BatchedGoEnv(2048, tile=-1); d.playout(31, seed=5); d.playout(91, seed=5)
     torch.cuda.synchronize()
-    assert torch.equal(a.states, b.states)
+    assert torch.equal(a.states, b.states) and torch.equal(a.states, d.states)
     assert torch.equal(a.states[:, 1024:], c.states)      # sharding by game id gives the same games (multi-GPU rule)
 
 

@@ -30,6 +30,7 @@ def _declare(L):
     L.tg_env_score.argtypes = [ctypes.c_int, c_vp, c_i64, ctypes.c_float, c_vp, c_vp, ctypes.c_int, c_vp]
     L.tg_env_playout.argtypes = [ctypes.c_int, c_vp, c_i64, ctypes.c_int, ctypes.c_int, ctypes.c_uint64, c_i64,
                                  ctypes.c_int, c_vp, c_vp, ctypes.c_int, c_vp]
+    L.tg_env_playout_tile.argtypes = [ctypes.c_int, c_i64, ctypes.c_int]
     L.tg_sub_encode.argtypes = [ctypes.c_int, c_vp, c_i64, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_vp, c_vp]
     L.tg_net_add_bn_relu.argtypes = [c_vp, c_vp, ctypes.c_float, c_vp, c_vp, c_vp, c_vp, c_i64, ctypes.c_int, c_vp]
     # the reference's 15 symbols (go_env.h:23-71), typed exactly as GoEnv/environment.py:43-90 types them

@@ -437,6 +437,129 @@ __device__ __forceinline__ void analyse_groups(const BB<N>& black, const BB<N>& 
     if (WANT_LIVES && has_eyes) out.lives = tile_or<N, T>(plv); else out.lives = bb_zero<N>();
 }
 
+// Seeded analysis: atari classes of ONLY the groups that hold a stone of `seeds`.  The rules need liberty counts in two
+// places -- StoneLibertyAnalysis of a point with no empty neighbour (board.cc:90-158) and the capture test around the
+// stone just played (board.cc:606-630) -- so a playout ply floods the handful of groups next to those points instead of
+// every group on the board.  l1b / l1w are OR-ed into (callers pass zero or an earlier partial result).
+template <int N, int T>
+__device__ __forceinline__ void analyse_seeded(const BB<N>& black, const BB<N>& white, const BB<N>& seeds, BB<N>& l1b, BB<N>& l1w) {
+    using G = Geo<N>;
+    const BB<N> empty = bb_not(black | white);
+    BB<N> sb = seeds & black, sw = seeds & white;
+    BB<N> p1b = bb_zero<N>(), p1w = p1b;
+    if (T == 1) {
+        // one thread: take the lowest remaining seed, flood its group, strike the flooded stones from the seed sets
+        while (any(sb | sw)) {
+            const bool is_w = !any(sb);
+            const BB<N> src = is_w ? sw : sb;
+            BB<N> g; bool taken = false;
+            TG_FOR_W { g.w[i] = taken ? 0 : (src.w[i] & (0 - src.w[i])); taken = taken || src.w[i] != 0; }
+            const BB<N> col = bb_select(is_w, white, black);
+            int c; bool complete;
+            flood_group<N, 1>(g, col, empty, 2, c, complete);
+            const bool is1 = complete && c == 1;
+            TG_FOR_W {
+                const typename G::word_t m1 = is1 ? g.w[i] : 0;
+                p1b.w[i] |= is_w ? 0 : m1; p1w.w[i] |= is_w ? m1 : 0;
+                sb.w[i] &= ~g.w[i]; sw.w[i] &= ~g.w[i];
+            }
+        }
+        l1b = l1b | p1b; l1w = l1w | p1w;
+        return;
+    }
+    // seeds whose west / north neighbour is a same-colour seed belong to that seed's group: drop them
+    sb = andn(andn(sb, shift_e(sb)), shift_s(sb));
+    sw = andn(andn(sw, shift_e(sw)), shift_s(sw));
+    const int nb = count(sb), total = nb + count(sw);
+    for (int base = 0; base < total; base += T) {               // tile-uniform trip count
+        const int j = base + Tile<T>::lane();
+        const bool valid = j < total;
+        const bool is_w = j >= nb;
+        BB<N> g = bb_nth_bit<N>(is_w ? sw : sb, valid ? (is_w ? j - nb : j) : -1);
+        const BB<N> col = bb_select(is_w, white, black);
+        int c; bool complete;
+        flood_group<N, T>(g, col, empty, 2, c, complete);
+        const bool is1 = valid && complete && c == 1;
+        TG_FOR_W {
+            const typename G::word_t m1 = is1 ? g.w[i] : 0;
+            p1b.w[i] |= is_w ? 0 : m1; p1w.w[i] |= is_w ? m1 : 0;
+        }
+    }
+    if (total > 0) { l1b = l1b | tile_or<N, T>(p1b); l1w = l1w | tile_or<N, T>(p1w); }
+}
+
+// Empty points with no empty neighbour: the only points whose legality depends on group liberties.
+template <int N> __device__ __forceinline__ BB<N> enclosed_points(const BB<N>& black, const BB<N>& white) {
+    const BB<N> empty = bb_not(black | white);
+    return andn(empty, nbrs(empty));
+}
+
+// Legal board points of the player to move.  Group liberties matter only next to enclosed points, so nothing is flooded
+// when there is none.  Otherwise a single thread (T == 1) floods just the groups next to them (its cost is the SUM over
+// groups), while a wider tile floods every group at once, one per lane in lock step (its cost is the MAX over groups, and
+// the result then also serves the capture test of the move).  On return l1b / l1w hold the atari classes of the analysed
+// groups and `known` = the points whose neighbour groups are all analysed (apply_stone_lazy wants both).
+template <int N, int T>
+__device__ __forceinline__ BB<N> legal_points_lazy(const Pos<N>& s, BB<N>& l1b, BB<N>& l1w, BB<N>& known) {
+    const BB<N>& black = s.stones[0]; const BB<N>& white = s.stones[1];
+    const BB<N> stones = black | white;
+    const BB<N> empty = bb_not(stones);
+    const BB<N> encl = andn(empty, nbrs(empty));
+    l1b = bb_zero<N>(); l1w = bb_zero<N>();
+    known = encl;
+    if (any(encl)) {                                                                        // tile-uniform branch
+        if (T == 1) analyse_seeded<N, T>(black, white, nbrs(encl) & stones, l1b, l1w);
+        else { analyse_seeded<N, T>(black, white, stones, l1b, l1w); known = bb_full<N>(); }
+    }
+    const bool me_black = s.player == kBlack;
+    const BB<N> own = bb_select(me_black, black, white);
+    const BB<N> l1own = bb_select(me_black, l1b, l1w), l1opp = bb_select(me_black, l1w, l1b);
+    // suicide (board.cc:130-158): enclosed, no own neighbour group with >1 liberty, no enemy neighbour group in atari
+    BB<N> lg = andn(empty, andn(encl, nbrs(andn(own, l1own) | l1opp)));
+    if (s.ko_age == 0 && s.ko_color == s.player && s.ko_loc >= 0 && s.ko_loc < Geo<N>::P)   // board.cc:198-200
+        lg = andn(lg, bb_point<N>(s.ko_loc));
+    return lg;
+}
+
+// One TRUSTED board move (the caller took pb from legal_points_lazy of this very position), given the partial atari sets
+// that call produced.  Same state transition as apply_move (go_env.cc:51-80, board.cc:546-661).
+template <int N, int T>
+__device__ __forceinline__ bool apply_stone_lazy(Pos<N>& s, const BB<N>& pb, int action, BB<N> l1b, BB<N> l1w, const BB<N>& known, int max_step) {
+    const bool me_black = s.player == kBlack;
+    const BB<N> own = bb_select(me_black, s.stones[0], s.stones[1]), opp = bb_select(me_black, s.stones[1], s.stones[0]);
+    const BB<N> around = nbrs(pb);
+    const BB<N> touch = around & opp;
+    if (any(touch) && !any(pb & known))                               // groups next to the stone not analysed yet
+        analyse_seeded<N, T>(s.stones[0], s.stones[1], touch, l1b, l1w);
+    const BB<N> l1opp = bb_select(me_black, l1w, l1b);
+    const BB<N> hit = around & l1opp;                                 // enemy neighbours in atari: they die
+    bool ko = false;
+    if (any(hit)) {                                                   // tile-uniform
+        const BB<N> empty = bb_not(own | opp);
+        if (!any(around & (empty | own))) {                           // board.cc:163-194, 561-570
+            const BB<N> cand = andn(hit, nbrs(opp));
+            ko = count(cand) == 1;
+            if (ko) { s.ko_loc = bb_lowest(cand); s.ko_color = 3 - s.player; s.ko_age = 0; }
+        }
+        const BB<N> dead = flood<N, T>(hit, l1opp);                   // board.cc:606-630
+        const BB<N> left = andn(opp, dead);
+        TG_FOR_W { s.stones[0].w[i] = me_black ? s.stones[0].w[i] : left.w[i]; s.stones[1].w[i] = me_black ? left.w[i] : s.stones[1].w[i]; }
+    }
+    if (!ko) s.ko_age += 1;
+    TG_FOR_W { s.stones[0].w[i] |= me_black ? pb.w[i] : 0; s.stones[1].w[i] |= me_black ? 0 : pb.w[i]; }
+    s.player = 3 - s.player; s.last2 = s.last1; s.last1 = action; s.step += 1;
+    if (s.step > max_step) { s.terminated = 1; return true; }           // go_env.cc:67-73
+    return false;
+}
+// Pass (action P or -1) / resign (-2): board.cc:536-542, 554-558, 656-661; ko fields untouched.
+template <int N>
+__device__ __forceinline__ bool apply_pass(Pos<N>& s, int action, int max_step) {
+    s.player = 3 - s.player; s.last2 = s.last1; s.last1 = action; s.step += 1;
+    const bool done = s.step > 1 && ((s.last1 == kPass && s.last2 == kPass) || s.last1 == kResign);
+    if (done || s.step > max_step) { s.terminated = 1; return true; }
+    return done;
+}
+
 // Points that are suicide for `me` (board.cc:130-158 over every empty point, ko ignored): no empty neighbour,
 // no own neighbour group with >1 liberty, no enemy neighbour group with exactly 1 liberty.
 template <int N> __device__ __forceinline__ BB<N> suicide_points(const BB<N>& own, const BB<N>& opp, const BB<N>& l1own, const BB<N>& l1opp) {

@@ -6,6 +6,7 @@
 #include "../../include/transgo_b200.h"
 #include "tg_board.cuh"
 #include "tg_common.cuh"
+#include "tg_rows.cuh"
 
 namespace tg {
 
@@ -125,18 +126,21 @@ k_playout(uint4* __restrict__ states, long long G, int plies, int max_step, unsi
     for (int t = 0; t < plies; ++t) {
         int action = kInvalid;
         if (!s.terminated) {                  // tile-uniform
-            Groups<N> gr;
-            analyse_groups<N, T, false>(s.stones[0], s.stones[1], s.player, gr);
-            BB<N> lg = legal_points(s, gr);
+            BB<N> l1b, l1w, known;
+            BB<N> lg = legal_points_lazy<N, T>(s, l1b, l1w, known);
             if (no_eye) lg = andn(lg, true_eyes(stones_of(s, s.player), stones_of(s, 3 - s.player)));
             const int nl = count(lg);
-            if (nl == 0) action = GG::P;
-            else {
-                uint32_t r = mix32(seed, (unsigned long long)(game_id0 + g), (unsigned long long)s.step);
-                action = bb_nth<N>(lg, (int)(((unsigned long long)r * (unsigned)nl) >> 32));
+            if (nl == 0) {
+                action = GG::P;
+                apply_pass<N>(s, kPass, max_step);
+            } else {
+                const uint32_t r = mix32(seed, (unsigned long long)(game_id0 + g), (unsigned long long)s.step);
+                int wi, bit;
+                bb_locate<N>(lg, (int)(((unsigned long long)r * (unsigned)nl) >> 32), wi, bit);
+                BB<N> pb; TG_FOR_W pb.w[i] = (i == wi) ? (typename GG::word_t(1) << bit) : typename GG::word_t(0);
+                action = wb_to_pt<N>(wi, bit);
+                apply_stone_lazy<N, T>(s, pb, action, l1b, l1w, known, max_step);
             }
-            bool acc;
-            apply_move<N, T>(s, gr, action, max_step, acc, true);
             played += 1;
         }
         if (trace && Tile<T>::lane() == 0) trace[(long long)t * G + g] = (int16_t)action;
@@ -145,6 +149,61 @@ k_playout(uint4* __restrict__ states, long long G, int plies, int max_step, unsi
         pos_store<N>(s, states, g, G, 1);
         if (plies_done && played) atomicAdd(plies_done, (unsigned long long)played);
     }
+}
+
+// Row-per-lane playout (tg_rows.cuh): 31 / (N+1) games per warp, one board row per lane.  Same move rule, same results.
+template <int N>
+__global__ void __launch_bounds__(kThreads)
+k_playout_rows(uint4* __restrict__ states, long long G, int plies, int max_step, unsigned long long seed, long long game_id0,
+               int no_eye, int16_t* __restrict__ trace, unsigned long long* __restrict__ plies_done) {
+    using R = RowGeo<N>;
+    const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    if (warp * R::GPW >= G) return;                       // whole warps leave together
+    RowLane<N> L; L.init(warp, G);
+    RowPos<N> p; rows_load<N>(p, L, states, G);
+    int played = 0;
+    for (int t = 0; t < plies; ++t) {
+        const bool act = L.rowlane && !p.terminated;
+        int action = kInvalid;
+        if (__any_sync(kFull, act)) {                     // warp-uniform
+            const uint32_t m = act ? R::ROW : 0u;
+            TG_STAT(0, 1);
+            uint32_t lg = rlegal<N>(p, L, m);
+            if (no_eye) {                                 // kernel-uniform
+                const bool me_black = p.player == kBlack;
+                lg &= ~rtrue_eyes<N>((me_black ? p.b : p.w) & m, (me_black ? p.w : p.b) & m, m, L.r);
+            }
+            // per-game count and k-th legal point in ascending action order = (row, bit) order: one warp-wide inclusive scan
+            const int pc = __popc(lg);
+            int incl = pc;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(kFull, incl, d); incl += (L.lane >= d) ? v : 0; }
+            const int base = __shfl_sync(kFull, incl, L.lead - 1);          // separator before the game = sum of earlier games
+            const int nl = __shfl_sync(kFull, incl, L.lead + N - 1) - base;
+            const uint32_t rnd = mix32(seed, (unsigned long long)(game_id0 + L.g), (unsigned long long)p.step);
+            const int k = (int)(((unsigned long long)rnd * (unsigned)nl) >> 32);
+            const int excl = incl - pc - base;
+            const bool placing = act && nl > 0;
+            const bool mine = placing && k >= excl && k < excl + pc;
+            const int bit = mine ? nth_bit(lg, k - excl) : 0;
+            const uint32_t pb = mine ? (1u << bit) : 0u;
+            const uint32_t ob = __ballot_sync(kFull, mine) & L.gm;
+            const int a = __shfl_sync(kFull, L.r * N + bit, ob ? (__ffs((int)ob) - 1) : L.lane);
+            rplace<N>(p, L, m, pb, placing, a);
+            if (act) {
+                action = placing ? a : Geo<N>::P;
+                if (!placing) {                            // pass: board.cc:536-542, 554-558, 656-661
+                    p.player = 3 - p.player; p.last2 = p.last1; p.last1 = kPass; p.step += 1;
+                    if (p.step > 1 && p.last2 == kPass) p.terminated = 1;
+                }
+                if (p.step > max_step) p.terminated = 1;   // go_env.cc:67-73
+                played += 1;
+            }
+        }
+        if (trace && L.rowlane && L.r == 0) trace[(long long)t * G + L.g] = (int16_t)action;
+    }
+    rows_store<N>(p, L, states, G);
+    if (L.rowlane && L.r == 0 && plies_done && played) atomicAdd(plies_done, (unsigned long long)played);
 }
 
 __global__ void k_sub_encode(const float* __restrict__ enc, long long B, int n, int C, int sub, int cuts, float* __restrict__ out) {
@@ -186,6 +245,16 @@ int pick_tile(int tile, long long G) {
         case 1:  FN<NN, 1>(__VA_ARGS__); break;                          \
         default: return set_err(-1, "tile must be 32, 8 or 1");          \
     }
+#define TG_DISPATCH_T6(NN, tile, FN, ...)                                \
+    switch (tile) {                                                      \
+        case 32: FN<NN, 32>(__VA_ARGS__); break;                         \
+        case 16: FN<NN, 16>(__VA_ARGS__); break;                         \
+        case 8:  FN<NN, 8>(__VA_ARGS__); break;                          \
+        case 4:  FN<NN, 4>(__VA_ARGS__); break;                          \
+        case 2:  FN<NN, 2>(__VA_ARGS__); break;                          \
+        case 1:  FN<NN, 1>(__VA_ARGS__); break;                          \
+        default: return set_err(-1, "tile must be a power of two <= 32"); \
+    }
 #define TG_DISPATCH(n, tile, FN, ...)                                    \
     if (n == 9) { TG_DISPATCH_T(9, tile, FN, __VA_ARGS__) }              \
     else if (n == 19) { TG_DISPATCH_T(19, tile, FN, __VA_ARGS__) }       \
@@ -216,6 +285,13 @@ template <int N, int T> void launch_encode(cudaStream_t st, const uint4* states,
 }
 template <int N, int T> void launch_score(cudaStream_t st, const uint4* states, long long G, float komi, float* score, float* territory) {
     k_score<N, T><<<blocks_for(G, T), kThreads, 0, st>>>(states, G, komi, score, territory);
+}
+template <int N> void launch_playout_rows(cudaStream_t st, uint4* states, long long G, int plies, int max_step, unsigned long long seed,
+                                           long long game_id0, int no_eye, int16_t* trace, unsigned long long* plies_done) {
+    const long long warps = (G + RowGeo<N>::GPW - 1) / RowGeo<N>::GPW;
+    constexpr int kRowThreads = 64;       // small CTAs: 1366 warps (4096 games) spread evenly over 148 SMs
+    k_playout_rows<N><<<(unsigned)((warps * 32 + kRowThreads - 1) / kRowThreads), kRowThreads, 0, st>>>(states, G, plies, max_step, seed, game_id0,
+                                                                                                 no_eye, trace, plies_done);
 }
 template <int N, int T> void launch_playout(cudaStream_t st, uint4* states, long long G, int plies, int max_step, unsigned long long seed,
                                             long long game_id0, int no_eye, int16_t* trace, unsigned long long* plies_done) {
@@ -278,14 +354,40 @@ int tg_env_score(int n, const void* states, int64_t G, float komi, float* score,
     return set_err((int)cudaGetLastError(), "tg_env_score");
 }
 
+/* the layout tg_env_playout runs for (n, G, tile): TG_TILE_ROWS or lanes per game */
+int tg_env_playout_tile(int n, int64_t G, int tile) {
+    if (tile == 0) return (n == 19) ? TG_TILE_ROWS : (G < 12288 ? 16 : 1);
+    return tile == TG_TILE_ROWS ? tile : pick_tile(tile, G);
+}
+
 int tg_env_playout(int n, void* states, int64_t G, int plies, int max_step, uint64_t seed, int64_t game_id0, int no_eye,
                    int16_t* trace_actions, unsigned long long* plies_done, int tile, void* stream) {
     if (!states || G <= 0 || plies < 0) return set_err(-1, "tg_env_playout");
     cudaStream_t st = (cudaStream_t)stream;
-    tile = snap_tile(tile, G);
-    TG_DISPATCH(n, tile, launch_playout, st, (uint4*)states, G, plies, max_step, seed, game_id0, no_eye, trace_actions, plies_done);
+    // tile == 0, measured on B200 (profiles/r01_playout_layouts.txt): 19x19 -> rows layout at every batch size (up to 3.6x over
+    // the bitboard tiles); 9x9 -> half-warp tiles while the batch cannot fill the SMs, one thread per game beyond
+    tile = tg_env_playout_tile(n, G, tile);
+    if (tile == TG_TILE_ROWS) {
+        if (n == 9) launch_playout_rows<9>(st, (uint4*)states, G, plies, max_step, seed, game_id0, no_eye, trace_actions, plies_done);
+        else if (n == 19) launch_playout_rows<19>(st, (uint4*)states, G, plies, max_step, seed, game_id0, no_eye, trace_actions, plies_done);
+        else return set_err(-1, "board size must be 9 or 19");
+        return set_err((int)cudaGetLastError(), "tg_env_playout");
+    }
+    tile = pick_tile(tile, G);
+    if (n == 9) { TG_DISPATCH_T6(9, tile, launch_playout, st, (uint4*)states, G, plies, max_step, seed, game_id0, no_eye, trace_actions, plies_done) }
+    else if (n == 19) { TG_DISPATCH_T6(19, tile, launch_playout, st, (uint4*)states, G, plies, max_step, seed, game_id0, no_eye, trace_actions, plies_done) }
+    else return set_err(-1, "board size must be 9 or 19");
     return set_err((int)cudaGetLastError(), "tg_env_playout");
 }
+
+#ifdef TG_ROWS_STATS
+int tg_debug_rows_stats(unsigned long long* out8, int reset) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out8, g_rows_stats, sizeof(unsigned long long) * 8);
+    if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(g_rows_stats, z, sizeof(z)); }
+    return 0;
+}
+#endif
 
 int tg_sub_encode(int n, const float* enc, int64_t B, int channels, int sub, int cuts, float* out, void* stream) {
     if (!enc || !out || B <= 0 || sub <= 0 || sub > n || cuts < 1 || cuts > 5) return set_err(-1, "tg_sub_encode");

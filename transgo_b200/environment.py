@@ -188,6 +188,11 @@ class BatchedGoEnv:
                                            int(game_id0), int(no_eye), _lib.ptr(trace), _lib.ptr(counter), self.tile,
                                            self._s()), "tg_env_playout")
 
+    def playout_layout(self):
+        """Name of the kernel ``playout`` launches for this batch: lanes per game, or 'rows' (one board row per lane)."""
+        t = self.lib.tg_env_playout_tile(self.n, self.G, self.tile)
+        return "rows" if t < 0 else str(t)
+
     # ---- helpers (format conversion only)
     def unpack_legal(self, legal=None):
         """dense mask int32 [G, LW] -> bool [G, A]"""
