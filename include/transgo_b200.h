@@ -195,11 +195,19 @@ int tg_synth_provider(int n, int64_t rows, uint64_t seed, uint64_t wave, float* 
 
 /* ---------------------------------------------------------------- (4) inference epilogue of the policy/value net
  * One pass over NHWC bf16 activations [rows][channels] (channels % 8 == 0):
- *     sum = x + alpha * y   (y may be NULL: sum = x)        -> sum_out (may be NULL)
+ *     sum = x + alpha * (y + ybias[c])   (y may be NULL: sum = x; ybias may be NULL)   -> sum_out (may be NULL)
  *     act = relu(sum * scale[c] + shift[c])                 -> act_out (may be NULL)
  * i.e. a residual junction of model.py:208-262 / :286-314 with the next eval-mode BatchNorm folded to scale/shift (f32). */
-int tg_net_add_bn_relu(const void* x, const void* y, float alpha, const float* scale, const float* shift,
+int tg_net_add_bn_relu(const void* x, const void* y, float alpha, const float* ybias, const float* scale, const float* shift,
                        void* sum_out, void* act_out, int64_t rows, int channels, void* stream);
+
+
+/* Fused single-head spatial self-attention block of model.py:286-314 in inference, NHWC bf16:
+ *   qkv  bf16 [B][P][dq + dq + C]   the three 1x1 convolutions (query | key | value) of x, one GEMM upstream
+ *   out  bf16 [B][P][C] = relu((x + gamma * o) * scale[c] + shift[c]),  o[j] = sum_i softmax_j(q_i . k_j) * v_i
+ * Supports P <= 96 (9x9), dq == 32, C == 128; returns -1 otherwise (callers then use the library GEMM path). */
+int tg_net_attention(const void* qkv, const void* x, float gamma, const float* scale, const float* shift, void* out,
+                     int64_t B, int P, int dq, int channels, void* stream);
 
 #ifdef __cplusplus
 }

@@ -23,9 +23,9 @@ def _perturbed_model(seed=0, features=128):
     return m
 
 
-@pytest.mark.parametrize("rows,C,with_y,want_sum,want_act", [(81 * 7, 128, True, True, True), (81 * 3, 128, False, False, True),
-                                                              (1000, 64, True, True, False), (5, 8, True, False, True)])
-def test_junction_kernel_matches_fp32_reference(rows, C, with_y, want_sum, want_act):
+@pytest.mark.parametrize("rows,C,with_y,want_sum,want_act,with_bias", [(81 * 7, 128, True, True, True, True), (81 * 3, 128, False, False, True, False),
+                                                                        (1000, 64, True, True, False, False), (5, 8, True, False, True, True)])
+def test_junction_kernel_matches_fp32_reference(rows, C, with_y, want_sum, want_act, with_bias):
     from transgo_b200 import _lib
     L = _lib.lib()
     g = torch.Generator(device="cuda"); g.manual_seed(rows + C)
@@ -34,17 +34,46 @@ def test_junction_kernel_matches_fp32_reference(rows, C, with_y, want_sum, want_
     scale = torch.rand([C], device="cuda", generator=g) + 0.5
     shift = torch.randn([C], device="cuda", generator=g)
     alpha = 0.37
+    ybias = torch.randn([C], device="cuda", generator=g) if with_bias else None
     s_out = torch.empty_like(x) if want_sum else None
     a_out = torch.empty_like(x) if want_act else None
-    _lib.check(L.tg_net_add_bn_relu(_lib.ptr(x), _lib.ptr(y), alpha, _lib.ptr(scale), _lib.ptr(shift), _lib.ptr(s_out),
+    _lib.check(L.tg_net_add_bn_relu(_lib.ptr(x), _lib.ptr(y), alpha, _lib.ptr(ybias), _lib.ptr(scale), _lib.ptr(shift), _lib.ptr(s_out),
                                     _lib.ptr(a_out), rows, C, _lib.stream_ptr()))
-    ref_sum = x.float() + (torch.tensor(alpha, device="cuda") * y.float() if with_y else 0.0)
+    yb = (y.float() + ybias) if (with_y and with_bias) else (y.float() if with_y else None)
+    ref_sum = x.float() + (torch.tensor(alpha, device="cuda") * yb if with_y else 0.0)
     ref_sum = ref_sum.to(torch.bfloat16)
     ref_act = torch.relu(ref_sum.float() * scale + shift).to(torch.bfloat16)
     if want_sum:
         assert torch.equal(s_out, ref_sum)
     if want_act:
         assert torch.equal(a_out, ref_act)
+
+
+@pytest.mark.parametrize("B,P", [(5, 81), (300, 81), (3, 96), (4, 49), (2, 1)])
+def test_attention_kernel_matches_fp32_reference(B, P):
+    """tg_net_attention against a plain PyTorch fp32 restatement of model.py:299-314 on the same bf16 inputs.
+    Tolerance: |d| <= 2e-2 + 2e-2 * |ref| (probabilities and outputs are rounded to bf16: 8 mantissa bits)."""
+    from transgo_b200 import _lib
+    L = _lib.lib()
+    g = torch.Generator(device="cuda"); g.manual_seed(B * 100 + P)
+    dq, C = 32, 128
+    qkv = (torch.randn([B, P, 2 * dq + C], device="cuda", generator=g) * 0.8).to(torch.bfloat16)
+    x = torch.randn([B, P, C], device="cuda", generator=g).to(torch.bfloat16)
+    scale = torch.rand([C], device="cuda", generator=g) + 0.5
+    shift = torch.randn([C], device="cuda", generator=g) * 0.3
+    gamma = 0.6
+    out = torch.full_like(x, float("nan"))
+    _lib.check(L.tg_net_attention(_lib.ptr(qkv), _lib.ptr(x), gamma, _lib.ptr(scale), _lib.ptr(shift), _lib.ptr(out),
+                                  B, P, dq, C, _lib.stream_ptr()))
+    q, k, v = qkv[..., :dq].float(), qkv[..., dq:2 * dq].float(), qkv[..., 2 * dq:].float()
+    att = torch.softmax(torch.bmm(q, k.transpose(1, 2)), dim=-1)                 # [B, P(query i), P(key j)]
+    o = torch.bmm(att.transpose(1, 2), v)                                          # o[j] = sum_i att[i, j] v[i]
+    ref = torch.relu((x.float() + gamma * o) * scale + shift)
+    assert not torch.isnan(out.float()).any()
+    err = (out.float() - ref).abs()
+    assert bool((err <= 2e-2 + 2e-2 * ref.abs()).all()), float(err.max())
+    assert L.tg_net_attention(_lib.ptr(qkv), _lib.ptr(x), gamma, _lib.ptr(scale), _lib.ptr(shift), _lib.ptr(out),
+                              B, 97, dq, C, _lib.stream_ptr()) != 0          # unsupported size is refused, not mangled
 
 
 def test_fused_forward_matches_fp32_module():

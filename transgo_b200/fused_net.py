@@ -4,7 +4,9 @@ Same weights, same maths, re-scheduled for a B200: the tensor-core work stays in
 with bias+ReLU epilogue, cuBLAS GEMMs for the 1x1 convolutions / attention / heads), eval-mode BatchNorm is folded
  - into the PRECEDING convolution where one exists (stem, the second BN of every residual block, both head convs), and
  - into a per-channel scale/shift otherwise, applied by ONE hand-written kernel per residual junction
-   (tg_net_add_bn_relu: residual add / gamma*attention + x, next BatchNorm, ReLU in a single NHWC bf16 pass).
+   (tg_net_add_bn_relu: residual add / gamma*attention + x, next BatchNorm, ReLU in a single NHWC bf16 pass);
+ - the four self-attention blocks (scores, softmax, weighted sum, junction) run as ONE hand-written kernel per block
+   (tg_net_attention, mma.sync bf16) fed by a single q|k|v GEMM; boards above 96 points use library batched GEMMs.
 Activations are NHWC bf16 end to end, so the attention blocks read them as [B, P, C] views without layout copies.
 
 ``FusedTransGoInference(model)`` snapshots a ``TransGoNetwork``; ``refresh()`` re-folds after ``set_weights``.
@@ -56,7 +58,8 @@ class FusedTransGoInference:
             if isinstance(blk, _PreActResidual):
                 s1, t1 = _fold(blk.batchnormlize_1)
                 self.blocks.append(("R", dict(s1=s1.contiguous(), t1=t1.contiguous(),
-                                              c1=_conv_bn(blk.conv_1, blk.batchnormlize_2, dt), c2=_conv_bn(blk.conv_2, None, dt))))
+                                              c1=_conv_bn(blk.conv_1, blk.batchnormlize_2, dt), c2=_conv_bn(blk.conv_2, None, dt),
+                                              c2b=blk.conv_2.bias.detach().float().contiguous())))
             else:
                 self.blocks.append(("A", self._attn(blk)))
             i += 1
@@ -89,13 +92,13 @@ class FusedTransGoInference:
                     dq=wq.shape[0], gamma=float(blk.gamma.detach().float().item()), s=s.contiguous(), t=t.contiguous())
 
     # ------------------------------------------------------------------ pieces
-    def _junction(self, x, y, alpha, scale, shift, want_sum, want_act):
-        """x (+ alpha*y) -> (sum, relu(sum*scale+shift)); x, y: channels_last [B,C,n,n] bf16 (NHWC memory)"""
+    def _junction(self, x, y, alpha, scale, shift, want_sum, want_act, ybias=None):
+        """x (+ alpha*(y + ybias)) -> (sum, relu(sum*scale+shift)); x, y: channels_last [B,C,n,n] bf16 (NHWC memory)"""
         B, C = x.shape[0], x.shape[1]
         rows = B * self.P
         s_out = torch.empty_like(x) if want_sum else None
         a_out = torch.empty_like(x) if want_act else None
-        _lib.check(self.lib.tg_net_add_bn_relu(_lib.ptr(x), _lib.ptr(y), float(alpha), _lib.ptr(scale), _lib.ptr(shift),
+        _lib.check(self.lib.tg_net_add_bn_relu(_lib.ptr(x), _lib.ptr(y), float(alpha), _lib.ptr(ybias), _lib.ptr(scale), _lib.ptr(shift),
                                                _lib.ptr(s_out), _lib.ptr(a_out), rows, C, _lib.stream_ptr()),
                    "tg_net_add_bn_relu")
         return s_out, a_out
@@ -106,6 +109,12 @@ class FusedTransGoInference:
         x2 = x.permute(0, 2, 3, 1).reshape(B, self.P, C)                       # free view of channels_last memory
         qkv = F.linear(x2, p["w"], p["b"])
         dq = p["dq"]
+        if self.P <= 96 and dq == 32 and C == 128 and self.dtype == torch.bfloat16:
+            # scores, softmax, att^T . v and the junction in ONE hand-written kernel (csrc/tg_net.cu: k_attention)
+            act = torch.empty_like(x)
+            _lib.check(self.lib.tg_net_attention(_lib.ptr(qkv), _lib.ptr(x), p["gamma"], _lib.ptr(p["s"]), _lib.ptr(p["t"]),
+                                                 _lib.ptr(act), B, self.P, dq, C, _lib.stream_ptr()), "tg_net_attention")
+            return act
         q, k, v = qkv[..., :dq], qkv[..., dq:2 * dq], qkv[..., 2 * dq:]
         att = torch.softmax(torch.bmm(q, k.transpose(1, 2)), dim=-1)           # [B, P, P], rows = query position
         o = torch.bmm(att.transpose(1, 2), v)                                  # out[:, j] = sum_i att[i, j] * v[i]
@@ -133,14 +142,15 @@ class FusedTransGoInference:
                 a1 = pending if pending is not None else self._junction(x, None, 1.0, p["s1"], p["t1"], False, True)[1]
                 pending = None
                 h = conv_relu(a1, p["c1"][0], p["c1"][1], one, pad, one, 1)    # conv_1 + folded batchnormlize_2 + ReLU
-                y = F.conv2d(h, p["c2"][0], p["c2"][1], padding=1)
+                y = F.conv2d(h, p["c2"][0], None, padding=1)                  # bias-free: conv_2's bias rides in the junction
+                b2 = p["c2b"]
                 nxt = self.blocks[i + 1] if i + 1 < nb else None
                 if nxt is not None and nxt[0] == "R":                          # x + y and the next block's BN1 + ReLU in one pass
-                    x, pending = self._junction(x, y, 1.0, nxt[1]["s1"], nxt[1]["t1"], True, True)
+                    x, pending = self._junction(x, y, 1.0, nxt[1]["s1"], nxt[1]["t1"], True, True, b2)
                 elif nxt is None:                                              # last block: x + y, bn_res_end, ReLU
-                    x = self._junction(x, y, 1.0, self.end[0], self.end[1], False, True)[1]
+                    x = self._junction(x, y, 1.0, self.end[0], self.end[1], False, True, b2)[1]
                 else:
-                    x = self._junction(x, y, 1.0, None, None, True, False)[0]
+                    x = self._junction(x, y, 1.0, None, None, True, False, b2)[0]
             else:
                 x = self._attention(x, p)
         # value / ownership head (model.py:93-99)
