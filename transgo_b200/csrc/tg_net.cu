@@ -79,11 +79,14 @@ extern "C" int tg_net_add_bn_relu(const void* x, const void* y, float alpha, con
 //     out = relu(bn(gamma * o + x))
 // Eager PyTorch runs this as two batched GEMMs on [B,P,P] score tensors plus softmax, slicing copies and the junction
 // (45 % of a 4096-position forward); here scores never leave the SM.  P <= 96 points (9x9), 32 query/key channels,
-// 128 value channels.  Warp w owns key rows j in [16w, 16w+16): it forms S^T[j][i] for all i with mma.sync m16n8k16
-// (bf16 in, f32 accumulate), the per-query max / sum over j go through shared memory across the six warps, and the
-// normalised probabilities are re-used straight from the accumulator registers as the A operand of the second product
-// o[j][c] = sum_i att^T[j][i] v[i][c], whose B operand comes from shared memory through ldmatrix.trans.
-// (The problem is 2 MFLOP per position and bound by its 70 KB of HBM traffic, not by tensor throughput.)
+// 128 value channels, six warps:
+//   1. warp w owns the queries i in [16w, 16w+16) and forms S^T[j][i] for EVERY key j (mma.sync m16n8k16, bf16 in, f32
+//      accumulate), so the softmax over j is a reduction inside the warp (registers + three shuffles per column);
+//   2. the normalised probabilities go to shared memory as bf16 att^T[j][i] (over the dead q / k tiles);
+//   3. warp w then owns the OUTPUT rows j in [16w, 16w+16): o[j][c] = sum_i att^T[j][i] v[i][c] with the A operand from
+//      ldmatrix and the B operand (v, row-major) from ldmatrix.trans, 16 channels at a time, junction epilogue on the
+//      accumulators.
+// (2 MFLOP and 72 KB of HBM traffic per position.)
 namespace tg {
 
 constexpr int kAttP = 96;          // padded points
@@ -92,11 +95,20 @@ constexpr int kAttC = 128;
 constexpr int kAttWarps = kAttP / 16;
 constexpr int kQS = kAttDq + 8;    // smem row strides (bf16), padded against bank conflicts
 constexpr int kVS = kAttC + 8;
+constexpr int kAS = kAttP + 8;
 
 __device__ __forceinline__ void mma_bf16(float* d, const uint32_t* a, uint32_t b0, uint32_t b1) {
     asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
                  : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void ldsm_x4(uint32_t* r, const void* p) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"((uint32_t)__cvta_generic_to_shared(p)));
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t* r, const void* p) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"((uint32_t)__cvta_generic_to_shared(p)));
 }
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
@@ -106,129 +118,156 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 __global__ void __launch_bounds__(kAttWarps * 32)
 k_attention(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ x, float gamma,
             const float* __restrict__ scale, const float* __restrict__ shift, __nv_bfloat16* __restrict__ out, int P) {
-    __shared__ __align__(16) __nv_bfloat16 sQ[kAttP * kQS];
-    __shared__ __align__(16) __nv_bfloat16 sK[kAttP * kQS];
+    constexpr int QK_ELEMS = 2 * kAttP * kQS, AT_ELEMS = kAttP * kAS;
+    __shared__ __align__(16) __nv_bfloat16 sA[QK_ELEMS > AT_ELEMS ? QK_ELEMS : AT_ELEMS];   // q | k first, att^T afterwards
     __shared__ __align__(16) __nv_bfloat16 sV[kAttP * kVS];
-    __shared__ float sPart[kAttWarps][kAttP];
-    __shared__ float sStat[kAttP];
-    const int tid = threadIdx.x, lane = tid & 31, wj = tid >> 5, g = lane >> 2, t = lane & 3;
+    __nv_bfloat16* sQ = sA;
+    __nv_bfloat16* sK = sA + kAttP * kQS;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, g = lane >> 2, t = lane & 3;
     const long long b = blockIdx.x;
     constexpr int ROWQ = (2 * kAttDq + kAttC) / 8;                   // 16-byte chunks per qkv row
     const uint4* src = reinterpret_cast<const uint4*>(qkv + b * (long long)P * (2 * kAttDq + kAttC));
-    // asynchronous 16-byte copies straight into shared memory: all of a thread's requests are in flight at once
-    for (int idx = tid; idx < kAttP * ROWQ; idx += blockDim.x) {
-        const int row = idx / ROWQ, ch = idx - row * ROWQ;
-        __nv_bfloat16* dst = ch < kAttDq / 8 ? &sQ[row * kQS + ch * 8]
-                           : ch < 2 * kAttDq / 8 ? &sK[row * kQS + (ch - kAttDq / 8) * 8]
-                                                 : &sV[row * kVS + (ch - 2 * kAttDq / 8) * 8];
+    // asynchronous 16-byte copies straight into shared memory, q | k first and v as a second group, so that the score
+    // product and the softmax run while v is still in flight; the residual rows of x are pulled towards L2 meanwhile
+    constexpr int QKC = 2 * kAttDq / 8;
+    for (int idx = tid; idx < kAttP * QKC; idx += blockDim.x) {
+        const int row = idx / QKC, ch = idx - row * QKC;
+        __nv_bfloat16* dst = ch < kAttDq / 8 ? &sQ[row * kQS + ch * 8] : &sK[row * kQS + (ch - kAttDq / 8) * 8];
         if (row < P) {
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" :: "r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src + idx));
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" :: "r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src + row * ROWQ + ch));
+        } else {
+            *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
+        }
+    }
+    asm volatile("cp.async.commit_group;\n" ::);
+    constexpr int VC = kAttC / 8;
+    for (int idx = tid; idx < kAttP * VC; idx += blockDim.x) {
+        const int row = idx / VC, ch = idx - row * VC;
+        __nv_bfloat16* dst = &sV[row * kVS + ch * 8];
+        if (row < P) {
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" :: "r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src + row * ROWQ + QKC + ch));
         } else {
             *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);  // rows >= P are zero: they add nothing to o
         }
     }
     asm volatile("cp.async.commit_group;\n" ::);
-    asm volatile("cp.async.wait_group 0;\n" ::);
+    {
+        const char* xrow = reinterpret_cast<const char*>(x + b * (long long)P * kAttC);
+        if (tid * 128 < P * kAttC * 2) asm volatile("prefetch.global.L2 [%0];\n" :: "l"(xrow + tid * 128));
+    }
+    asm volatile("cp.async.wait_group 1;\n" ::);
     __syncthreads();
 
-    // ---- S^T[j][i] = k_j . q_i for this warp's 16 key rows j and every query i
-    const int j0 = wj * 16;
-    uint32_t ka[kAttDq / 16][4];
+    // ---- 1. S^T[j][i] = k_j . q_i for every key j and this warp's 16 queries i
+    const int i0 = wid * 16;
+    const int mrow = (lane & 7) + ((lane >> 3) & 1) * 8, mcol = (lane >> 4) * 8;   // ldmatrix.x4 lane -> (row, col) of its 8x8 tile
+    uint32_t qb[2][kAttDq / 16][2];
 #pragma unroll
-    for (int kc = 0; kc < kAttDq / 16; ++kc) {
-        ka[kc][0] = *reinterpret_cast<const uint32_t*>(&sK[(j0 + g) * kQS + kc * 16 + 2 * t]);
-        ka[kc][1] = *reinterpret_cast<const uint32_t*>(&sK[(j0 + g + 8) * kQS + kc * 16 + 2 * t]);
-        ka[kc][2] = *reinterpret_cast<const uint32_t*>(&sK[(j0 + g) * kQS + kc * 16 + 8 + 2 * t]);
-        ka[kc][3] = *reinterpret_cast<const uint32_t*>(&sK[(j0 + g + 8) * kQS + kc * 16 + 8 + 2 * t]);
-    }
-    float s[kAttP / 8][4];
-#pragma unroll
-    for (int nt = 0; nt < kAttP / 8; ++nt) {
-        s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.0f;
+    for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
         for (int kc = 0; kc < kAttDq / 16; ++kc) {
-            const uint32_t b0 = *reinterpret_cast<const uint32_t*>(&sQ[(nt * 8 + g) * kQS + kc * 16 + 2 * t]);
-            const uint32_t b1 = *reinterpret_cast<const uint32_t*>(&sQ[(nt * 8 + g) * kQS + kc * 16 + 8 + 2 * t]);
-            mma_bf16(s[nt], ka[kc], b0, b1);
+            qb[nt][kc][0] = *reinterpret_cast<const uint32_t*>(&sQ[(i0 + nt * 8 + g) * kQS + kc * 16 + 2 * t]);
+            qb[nt][kc][1] = *reinterpret_cast<const uint32_t*>(&sQ[(i0 + nt * 8 + g) * kQS + kc * 16 + 8 + 2 * t]);
+        }
+    float s[kAttWarps][2][4];
+#pragma unroll
+    for (int mt = 0; mt < kAttWarps; ++mt) {
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) s[mt][nt][0] = s[mt][nt][1] = s[mt][nt][2] = s[mt][nt][3] = 0.0f;
+#pragma unroll
+        for (int kc = 0; kc < kAttDq / 16; ++kc) {
+            uint32_t ka[4];
+            ldsm_x4(ka, &sK[(mt * 16 + mrow) * kQS + kc * 16 + mcol]);
+            mma_bf16(s[mt][0], ka, qb[0][kc][0], qb[0][kc][1]);
+            mma_bf16(s[mt][1], ka, qb[1][kc][0], qb[1][kc][1]);
         }
     }
-    // ---- softmax over the keys j (rows of S^T; they are spread over the warps) for every query i (columns)
-    const bool r0 = j0 + g < P, r1 = j0 + g + 8 < P;
+    // softmax over the keys j (rows of S^T) for each of this thread's 4 query columns: registers, then the 8 lanes that
+    // share t.  Rows j >= P do not exist: they are left out of max and sum and get probability 0.
     const float NEG = -3.0e38f;
+    float inv[2][2];
 #pragma unroll
-    for (int nt = 0; nt < kAttP / 8; ++nt) {
-        float m0 = fmaxf(r0 ? s[nt][0] : NEG, r1 ? s[nt][2] : NEG), m1 = fmaxf(r0 ? s[nt][1] : NEG, r1 ? s[nt][3] : NEG);
+    for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
-        for (int o = 4; o < 32; o <<= 1) { m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, o)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, o)); }
-        if (g == 0) { sPart[wj][nt * 8 + 2 * t] = m0; sPart[wj][nt * 8 + 2 * t + 1] = m1; }
-    }
-    __syncthreads();
-    if (tid < kAttP) {
-        float m = sPart[0][tid];
+        for (int e = 0; e < 2; ++e) {
+            float m = NEG;
 #pragma unroll
-        for (int w = 1; w < kAttWarps; ++w) m = fmaxf(m, sPart[w][tid]);
-        sStat[tid] = m;
-    }
-    __syncthreads();
+            for (int mt = 0; mt < kAttWarps; ++mt) {
+                if (mt * 16 + g < P) m = fmaxf(m, s[mt][nt][e]);
+                if (mt * 16 + g + 8 < P) m = fmaxf(m, s[mt][nt][2 + e]);
+            }
 #pragma unroll
-    for (int nt = 0; nt < kAttP / 8; ++nt) {
-        const float mx0 = sStat[nt * 8 + 2 * t], mx1 = sStat[nt * 8 + 2 * t + 1];
-        s[nt][0] = r0 ? __expf(s[nt][0] - mx0) : 0.0f; s[nt][1] = r0 ? __expf(s[nt][1] - mx1) : 0.0f;
-        s[nt][2] = r1 ? __expf(s[nt][2] - mx0) : 0.0f; s[nt][3] = r1 ? __expf(s[nt][3] - mx1) : 0.0f;
-        float z0 = s[nt][0] + s[nt][2], z1 = s[nt][1] + s[nt][3];
+            for (int o = 4; o < 32; o <<= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+            float z = 0.0f;
 #pragma unroll
-        for (int o = 4; o < 32; o <<= 1) { z0 += __shfl_xor_sync(0xffffffffu, z0, o); z1 += __shfl_xor_sync(0xffffffffu, z1, o); }
-        if (g == 0) { sPart[wj][nt * 8 + 2 * t] = z0; sPart[wj][nt * 8 + 2 * t + 1] = z1; }
-    }
-    __syncthreads();
-    if (tid < kAttP) {
-        float z = sPart[0][tid];
+            for (int mt = 0; mt < kAttWarps; ++mt) {
+                const float e0 = (mt * 16 + g < P) ? __expf(s[mt][nt][e] - m) : 0.0f;
+                const float e1 = (mt * 16 + g + 8 < P) ? __expf(s[mt][nt][2 + e] - m) : 0.0f;
+                s[mt][nt][e] = e0; s[mt][nt][2 + e] = e1;
+                z += e0 + e1;
+            }
 #pragma unroll
-        for (int w = 1; w < kAttWarps; ++w) z += sPart[w][tid];
-        sStat[tid] = 1.0f / z;                                       // z >= 1: the row that holds the max contributes exp(0)
-    }
-    __syncthreads();
-    // probabilities as bf16 A fragments (two neighbouring 8-column accumulator tiles make one 16-wide k chunk)
+            for (int o = 4; o < 32; o <<= 1) z += __shfl_xor_sync(0xffffffffu, z, o);
+            inv[nt][e] = 1.0f / z;                                   // z >= 1: the row that holds the max contributes exp(0)
+        }
+    __syncthreads();                                                 // every warp is done with q / k: att^T may overwrite them
+    // ---- 2. att^T[j][i] as bf16
+#pragma unroll
+    for (int mt = 0; mt < kAttWarps; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) {
+            const int col = i0 + nt * 8 + 2 * t;
+            *reinterpret_cast<uint32_t*>(&sA[(mt * 16 + g) * kAS + col]) = pack_bf16(s[mt][nt][0] * inv[nt][0], s[mt][nt][1] * inv[nt][1]);
+            *reinterpret_cast<uint32_t*>(&sA[(mt * 16 + g + 8) * kAS + col]) = pack_bf16(s[mt][nt][2] * inv[nt][0], s[mt][nt][3] * inv[nt][1]);
+        }
+    asm volatile("cp.async.wait_group 0;\n" ::);                    // v has landed (each thread waits for its own copies ...)
+    __syncthreads();                                                 // ... and the barrier makes all of them, and att^T, visible
+    // ---- 3. o[j][c] = sum_i att^T[j][i] * v[i][c] for this warp's 16 output rows j, then the junction epilogue
+    const int j0 = wid * 16;
     uint32_t pa[kAttP / 16][4];
 #pragma unroll
-    for (int kc = 0; kc < kAttP / 16; ++kc) {
-        const float i00 = sStat[kc * 16 + 2 * t], i01 = sStat[kc * 16 + 2 * t + 1], i10 = sStat[kc * 16 + 8 + 2 * t], i11 = sStat[kc * 16 + 8 + 2 * t + 1];
-        pa[kc][0] = pack_bf16(s[2 * kc][0] * i00, s[2 * kc][1] * i01);
-        pa[kc][1] = pack_bf16(s[2 * kc][2] * i00, s[2 * kc][3] * i01);
-        pa[kc][2] = pack_bf16(s[2 * kc + 1][0] * i10, s[2 * kc + 1][1] * i11);
-        pa[kc][3] = pack_bf16(s[2 * kc + 1][2] * i10, s[2 * kc + 1][3] * i11);
-    }
-    // ---- o[j][c] = sum_i att^T[j][i] * v[i][c], 16 channels at a time, then the junction epilogue
-    const int mrow = (lane & 7) + ((lane >> 3) & 1) * 8, mcol = (lane >> 4) * 8;
+    for (int kc = 0; kc < kAttP / 16; ++kc) ldsm_x4(pa[kc], &sA[(j0 + mrow) * kAS + kc * 16 + mcol]);
     const long long rowbase = b * (long long)P;
 #pragma unroll
     for (int ct = 0; ct < kAttC / 16; ++ct) {
         float o[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
 #pragma unroll
         for (int kc = 0; kc < kAttP / 16; ++kc) {
-            uint32_t v0, v1, v2, v3;
-            const uint32_t addr = (uint32_t)__cvta_generic_to_shared(&sV[(kc * 16 + mrow) * kVS + ct * 16 + mcol]);
-            asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];\n"
-                         : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3) : "r"(addr));
-            mma_bf16(o[0], pa[kc], v0, v1);
-            mma_bf16(o[1], pa[kc], v2, v3);
+            uint32_t v[4];
+            ldsm_x4_trans(v, &sV[(kc * 16 + mrow) * kVS + ct * 16 + mcol]);
+            mma_bf16(o[0], pa[kc], v[0], v[1]);
+            mma_bf16(o[1], pa[kc], v[2], v[3]);
         }
+        // the accumulator layout gives each lane 2 channels of 4 (row, half) combinations; a 4x4 transpose inside the quad
+        // (two shuffle rounds) turns that into 8 consecutive channels of ONE combination per lane -> 128-bit accesses
+        uint32_t a[4];
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int c = ct * 16 + h * 8 + 2 * t;
-            const float sc0 = scale[c], sc1 = scale[c + 1], sh0 = shift[c], sh1 = shift[c + 1];
+        for (int k = 0; k < 4; ++k) a[k] = pack_bf16(o[k >> 1][2 * (k & 1)], o[k >> 1][2 * (k & 1) + 1]);
+        {
+            const bool odd = t & 1, hi = t & 2;
+            const uint32_t r0 = __shfl_xor_sync(0xffffffffu, odd ? a[0] : a[1], 1), r1 = __shfl_xor_sync(0xffffffffu, odd ? a[2] : a[3], 1);
+            if (odd) { a[0] = r0; a[2] = r1; } else { a[1] = r0; a[3] = r1; }
+            const uint32_t q0 = __shfl_xor_sync(0xffffffffu, hi ? a[0] : a[2], 2), q1 = __shfl_xor_sync(0xffffffffu, hi ? a[1] : a[3], 2);
+            if (hi) { a[0] = q0; a[1] = q1; } else { a[2] = q0; a[3] = q1; }
+        }
+        const int j = j0 + g + (t & 1) * 8, c = ct * 16 + (t >> 1) * 8;
+        if (j < P) {
+            const long long off = (rowbase + j) * kAttC + c;
+            const uint4 xq = *reinterpret_cast<const uint4*>(x + off);
+            const float4 sc0 = *reinterpret_cast<const float4*>(scale + c), sc1 = *reinterpret_cast<const float4*>(scale + c + 4);
+            const float4 sh0 = *reinterpret_cast<const float4*>(shift + c), sh1 = *reinterpret_cast<const float4*>(shift + c + 4);
+            const float scv[8] = {sc0.x, sc0.y, sc0.z, sc0.w, sc1.x, sc1.y, sc1.z, sc1.w};
+            const float shv[8] = {sh0.x, sh0.y, sh0.z, sh0.w, sh1.x, sh1.y, sh1.z, sh1.w};
+            const uint32_t xw[4] = {xq.x, xq.y, xq.z, xq.w};
+            uint32_t ow[4];
 #pragma unroll
-            for (int rr = 0; rr < 2; ++rr) {
-                const int j = j0 + g + rr * 8;
-                if (j >= P) continue;
-                const long long off = (rowbase + j) * kAttC + c;
-                const float2 xv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(x + off));
-                // same rounding points as the unfused path: o -> bf16, x + gamma * o -> bf16, BatchNorm + ReLU -> bf16
-                const float2 ov = __bfloat1622float2(__floats2bfloat162_rn(o[h][2 * rr], o[h][2 * rr + 1]));
-                const float2 sv = __bfloat1622float2(__floats2bfloat162_rn(xv.x + gamma * ov.x, xv.y + gamma * ov.y));
-                *reinterpret_cast<__nv_bfloat162*>(out + off) =
-                    __floats2bfloat162_rn(fmaxf(sv.x * sc0 + sh0, 0.0f), fmaxf(sv.y * sc1 + sh1, 0.0f));
+            for (int k = 0; k < 4; ++k) {
+                const float2 xv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xw[k]));
+                const float2 ov = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&a[k]));
+                const float s0 = fmaf(gamma, ov.x, xv.x), s1 = fmaf(gamma, ov.y, xv.y);
+                ow[k] = pack_bf16(fmaxf(fmaf(s0, scv[2 * k], shv[2 * k]), 0.0f), fmaxf(fmaf(s1, scv[2 * k + 1], shv[2 * k + 1]), 0.0f));
             }
+            *reinterpret_cast<uint4*>(out + off) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
         }
     }
 }
