@@ -239,3 +239,23 @@ def test_selfplay_worker_labels_and_augmentation(oracle_built):
     assert first.sum().item() == 4 and sorted(zs.tolist()) == sorted(np.where(winner == 1, 1.0, -1.0).tolist())
     aug = w.play_games(augment=True)
     assert aug["obs"].shape[0] == 8 * aug["positions"] and aug["pi"].shape == (8 * aug["positions"], 82)
+
+
+def test_selfplay_round_feeds_the_replay_ring(oracle_built):
+    """BASELINE configs[4] in one process: play -> label -> x8 -> ring, counters advance like SharedStorage's
+    (shared_storage.py:21-43).  The multi-rank form (NCCL broadcast + gather) is exercised by scripts/selfplay_loop.py
+    and, on CPU with gloo, by tests/test_dist_cpu.py."""
+    from transgo_b200.net import TransGoNetwork
+    from transgo_b200.replay import Pacing, ReplayRing
+    from transgo_b200.selfplay import SelfPlayWorker, selfplay_round
+    model = TransGoNetwork(board_size=9, num_features=16).cuda().eval()
+    w = SelfPlayWorker(cpu_provider(9, 6), 6, num_simulation=12, max_step=8, tie_seed=3)   # 12 < 81 children: some roots end
+    ring, pacing = ReplayRing(4096), Pacing()                                               # with every count <= 1 (see mcts.py)
+    called = []
+    st = selfplay_round(w, model, ring, pacing, refresh=lambda: called.append(1))
+    assert called == [1] and st["games"] == 6 and st["appended"] == 8 * st["positions"] == len(ring)
+    assert pacing.now_play_steps == st["positions"] and pacing.now_play_games == 6
+    obs, pi, z, own = ring.sample(32)
+    assert obs.shape == (32, 10, 9, 9) and bool(((pi.sum(1) - 1).abs() < 1e-5).all()) and set(z.cpu().tolist()) <= {1.0, -1.0}
+    st2 = selfplay_round(w, model, ring, pacing, augment=False)
+    assert len(ring) == st["appended"] + st2["positions"]

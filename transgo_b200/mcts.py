@@ -213,8 +213,11 @@ class BatchedMCTS:
         self.search(noise if is_selfplay else None)
         counts, _, _, _ = self.root_stats()
         c = counts.to(torch.float64)
-        c = torch.where(counts == 1, torch.zeros_like(c), c)                    # :668
-        pi = c / c.sum(1, keepdim=True)                                         # :670-671
+        c1 = torch.where(counts == 1, torch.zeros_like(c), c)                   # :668
+        # When no child was visited twice the reference divides by zero and np.random.choice raises (it needs ~2 x K
+        # simulations to be safe; its 210 are).  Here such a game keeps its raw visit counts instead of failing the batch.
+        c = torch.where(c1.sum(1, keepdim=True) > 0, c1, c)
+        pi = c / c.sum(1, keepdim=True).clamp_min(1.0)                          # :670-671 (finished games: all zero)
         if forced_actions is not None:
             actions = forced_actions.to(torch.int16)
         else:
@@ -223,8 +226,8 @@ class BatchedMCTS:
             else:
                 temp = torch.full([self.G], 0.12, dtype=torch.float64, device=self.device)
             tem = torch.pow(c, (1.0 / temp)[:, None])                            # :679
-            cdf = torch.cumsum(tem / tem.sum(1, keepdim=True), 1)
-            cdf = cdf / cdf[:, -1:]
+            cdf = torch.cumsum(tem / tem.sum(1, keepdim=True).clamp_min(1e-300), 1)
+            cdf = cdf / cdf[:, -1:].clamp_min(1e-300)
             if u is None:
                 u = torch.rand([self.G], dtype=torch.float64, device=self.device)
             actions = torch.searchsorted(cdf, u.to(torch.float64)[:, None].contiguous(), right=True).reshape(-1)

@@ -57,3 +57,38 @@ class SelfPlayWorker:
             obs, pi, z, own = augment8(obs, pi, z, own, n)
         return dict(obs=obs, pi=pi, z=z, own=own, winner=winner, score=score, moves=moves,
                     positions=int(valid.sum().item()))
+
+
+def selfplay_round(worker, model, ring=None, pacing=None, src=0, dst=0, augment=True, max_moves=None, refresh=None):
+    """One round of BASELINE configs[4] on every rank of the process group (or a single process without one):
+
+        weights  trainer rank `src` -> all ranks            (replaces shared_storage.get_info("weights"), self_play.py:913)
+        play     this rank's shard of games to the end      (WP_MCTS loop, self_play.py:915-929; no cross-GPU traffic)
+        gather   labelled, augmented positions -> rank `dst` (replaces mem.append.remote x8, self_play.py:956-965)
+        append   into the replay ring on `dst`, bump the play counters (shared_storage.py:21-43)
+
+    `refresh` re-folds inference copies of the weights (e.g. make_fused_evaluator(...).refresh).  Returns the play
+    statistics of this rank plus, on `dst`, the number of rows appended."""
+    import torch.distributed as dist
+    from .dist import broadcast_weights, gather_trajectories
+    multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+    if multi:
+        broadcast_weights(model, src=src)
+    if refresh is not None:
+        refresh()
+    out = worker.play_games(augment=augment, max_moves=max_moves)
+    rows = (out["obs"], out["pi"], out["z"], out["own"])
+    if multi:
+        rows = gather_trajectories(*rows, dst=dst)
+    rank = dist.get_rank() if multi else dst
+    stats = dict(moves=out["moves"], positions=out["positions"], games=int(out["winner"].numel()),
+                 black_wins=int((out["winner"] == 1).sum().item()), appended=0)
+    if rank == dst and rows is not None:
+        if ring is not None:
+            ring.append(*rows)
+        stats["appended"] = int(rows[0].shape[0])
+        if pacing is not None:
+            total_pos = stats["appended"] // (8 if augment else 1)
+            pacing.add_play_steps(total_pos)
+            pacing.add_play_games(stats["games"] * (dist.get_world_size() if multi else 1))
+    return stats
