@@ -64,7 +64,8 @@ def selfplay_round(worker, model, ring=None, pacing=None, src=0, dst=0, augment=
 
         weights  trainer rank `src` -> all ranks            (replaces shared_storage.get_info("weights"), self_play.py:913)
         play     this rank's shard of games to the end      (WP_MCTS loop, self_play.py:915-929; no cross-GPU traffic)
-        gather   labelled, augmented positions -> rank `dst` (replaces mem.append.remote x8, self_play.py:956-965)
+        gather   labelled positions -> rank `dst`           (replaces mem.append.remote, self_play.py:956-965)
+        augment  x8 on the receiver (self_play.py:943-965), so the wire carries each position once
         append   into the replay ring on `dst`, bump the play counters (shared_storage.py:21-43)
 
     `refresh` re-folds inference copies of the weights (e.g. make_fused_evaluator(...).refresh).  Returns the play
@@ -76,11 +77,13 @@ def selfplay_round(worker, model, ring=None, pacing=None, src=0, dst=0, augment=
         broadcast_weights(model, src=src)
     if refresh is not None:
         refresh()
-    out = worker.play_games(augment=augment, max_moves=max_moves)
+    out = worker.play_games(augment=False, max_moves=max_moves)
     rows = (out["obs"], out["pi"], out["z"], out["own"])
     if multi:
         rows = gather_trajectories(*rows, dst=dst)
     rank = dist.get_rank() if multi else dst
+    if augment and rank == dst and rows is not None:
+        rows = augment8(*rows, worker.n)
     stats = dict(moves=out["moves"], positions=out["positions"], games=int(out["winner"].numel()),
                  black_wins=int((out["winner"] == 1).sum().item()), appended=0)
     if rank == dst and rows is not None:
