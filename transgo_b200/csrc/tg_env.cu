@@ -27,15 +27,20 @@ k_step(uint4* __restrict__ states, long long G, const int16_t* __restrict__ acti
     long long g = (blockIdx.x * (long long)blockDim.x + threadIdx.x) / T;
     if (g >= G) return;                       // whole tiles leave together
     Pos<N> s; pos_load<N>(s, states, g, G, 1);
-    Groups<N> gr;
-    analyse_groups<N, T, false>(s.stones[0], s.stones[1], s.player, gr);
-    bool acc;
-    bool done = apply_move<N, T>(s, gr, (int)actions[g], max_step, acc);
-    BB<N> lg = bb_zero<N>();
-    if (legal_out) {                          // uniform
-        analyse_groups<N, T, false>(s.stones[0], s.stones[1], s.player, gr);
-        lg = legal_points(s, gr);
+    // go_env.cc:51-80 with the lazy group analysis of the playout kernel (every branch is tile-uniform)
+    int action = (int)actions[g];
+    if (action == GG::P) action = kPass;                                  // go_env.cc:56-57
+    bool acc = false, done = false;
+    BB<N> l1b, l1w, known;
+    if (s.terminated) done = true;                                        // go_env.cc:52-55
+    else if (action == kPass || action == kResign) { done = apply_pass<N>(s, action, max_step); acc = true; }
+    else if (action >= 0 && action < GG::P) {
+        const BB<N> pb = bb_point<N>(action);
+        const BB<N> lg0 = legal_points_lazy<N, T>(s, l1b, l1w, known);
+        if (any(lg0 & pb)) { done = apply_stone_lazy<N, T>(s, pb, action, l1b, l1w, known, max_step); acc = true; }   // else board.cc:448-462
     }
+    BB<N> lg = bb_zero<N>();
+    if (legal_out) lg = legal_points_lazy<N, T>(s, l1b, l1w, known);     // uniform
     if (Tile<T>::lane() == 0) {
         if (acc) pos_store<N>(s, states, g, G, 1);
         if (done_out) done_out[g] = done ? 1 : 0;
@@ -60,9 +65,8 @@ k_legal(const uint4* __restrict__ states, long long G, uint32_t* __restrict__ le
     long long g = (blockIdx.x * (long long)blockDim.x + threadIdx.x) / T;
     if (g >= G) return;
     Pos<N> s; pos_load<N>(s, states, g, G, 1);
-    Groups<N> gr;
-    analyse_groups<N, T, false>(s.stones[0], s.stones[1], s.player, gr);
-    BB<N> lg = legal_points(s, gr);
+    BB<N> l1b, l1w, known;
+    BB<N> lg = legal_points_lazy<N, T>(s, l1b, l1w, known);
     if (no_eye) lg = andn(lg, true_eyes(stones_of(s, s.player), stones_of(s, 3 - s.player)));    // board.cc:510-512
     if (Tile<T>::lane() == 0) {
         uint32_t d[GG::DQ * 4];
