@@ -497,10 +497,17 @@ def mcts_bench(torch, dist, dev, rank, world, args):
         return p, v
     eng = BatchedMCTS(synth, G, num_simulation=sims, tie_seed=1, game_id0=rank * G, device=dev)
     timed_moves(eng, 1)                                        # warm-up move
+    eng.search_stats()
     rate, ms, n, waves = timed_moves(eng, moves)
+    st = eng.search_stats()
+    d_bar, k_bar = st["mean_depth"], st["mean_fanout"]
+    # SURVEY 8d traffic model with this engine's record sizes: 16 B hot edge per child scanned + 16 B node info per level, 40 B
+    # RMW per path node, 24 B per new child slot, policy row + value, legal mask, two states, the 3240 B of planes
+    bps = d_bar * (16 * k_bar + 16) + 40 * (d_bar + 1) + 24 * k_bar + (4 * 82 + 4) + 16 + 2 * 48 + 3240
     out["tree_only"] = {"value": rate, "unit": "MCTS sims/s", "ms": ms, "sims": n, "moves": moves, "waves": waves,
                         "provider": "tg_synth_provider (device-side synthetic policy/value, NOT the net)",
-                        "gbps_algorithmic": rate * 10.2e3 / 1e9, "bytes_per_sim": 10200}
+                        "mean_depth": d_bar, "mean_fanout": k_bar, "bytes_per_sim": bps,
+                        "gbps_algorithmic": rate * bps / 1e9}
     del eng
     if args.tree_only:
         return out

@@ -187,6 +187,11 @@ int tg_mcts_advance(const TgMctsConfig* cfg, void* ws, const int16_t* actions, u
 int tg_mcts_status(const TgMctsConfig* cfg, void* ws, uint32_t* status, unsigned long long* sims, void* stream);
 /* root game states as a batch in the layout of section (2): returns the device pointer inside the workspace */
 void* tg_mcts_root_states(const TgMctsConfig* cfg, void* ws);
+/* selection statistics since the previous call, summed over the games (and reset): out3[0] descents, out3[1] edges walked
+ * (sum of path lengths), out3[2] children scanned by PUCT -- mean depth and fan-out for the traffic model of SURVEY.md 8d.
+ * out3 must be zeroed by the caller. */
+int tg_mcts_search_stats(const TgMctsConfig* cfg, void* ws, unsigned long long* out3, void* stream);
+
 /* final labels of finished games (self_play.py:931-937): winner u8 [G] (1|2), score f32 [G], territory f32 [G][P] */
 int tg_mcts_outcome(const TgMctsConfig* cfg, void* ws, uint8_t* winner, float* score, float* territory, void* stream);
 /* a device-side synthetic policy/value provider for tree-only throughput runs (bench.py): policy[row] = normalised

@@ -11,7 +11,7 @@
 namespace tg {
 
 enum { H_BUF = 0, H_NNODES, H_NEDGES, H_ROOTN, H_ROOTONS, H_ROOTW, H_ROOTMEAN, H_ROOTVAR, H_TIE, H_N0, H_MOVE, H_FLAGS,
-       H_NPATHS, H_SIMS, H_SPARE0, H_SPARE1, H_WORDS };
+       H_NPATHS, H_SIMS, H_STAT_DESC, H_STAT_DEPTH, H_STAT_FAN, H_SPARE1, H_WORDS_USED, H_WORDS = 20 };   // 80 B per game
 constexpr unsigned kErrAction = 256u;
 constexpr int kMaxReadouts = 8;
 
@@ -151,6 +151,7 @@ __global__ void __launch_bounds__(kThreads) k_select(View v) {
     const bool noisy = (flags & TG_MCTS_NOISY) != 0;
     const float c1f = (float)v.c1, c2f = (float)v.c2;
     int npaths = 0, tie = h[H_TIE], sims = 0;
+    int st_desc = 0, st_depth = 0, st_fan = 0;                        // descents, edges walked, children scanned (bench: d, K)
     unsigned err = 0;
     for (int attempt = 0; attempt < 2 * v.R && npaths < v.R && !err; ++attempt) {      // self_play.py:616-619
         int* path = v.paths + ((size_t)g * v.R + npaths) * v.MAXD;
@@ -160,6 +161,7 @@ __global__ void __launch_bounds__(kThreads) k_select(View v) {
         while (true) {                                                                // :623-627
             const uint4 info = nodes[(size_t)node * (GG::SQ + 1) + GG::SQ];
             const int eb = (int)info.x, K = (int)info.y;
+            st_fan += K;
             const double sq = __dsqrt_rn((double)(Np + onsp));
             double sc[MAXR]; uint32_t pk[MAXR];
             double best = -1.0e300;
@@ -216,6 +218,7 @@ __global__ void __launch_bounds__(kThreads) k_select(View v) {
             Np = pk_n(pk_sel); onsp = pk_ons(pk_sel); node = child;
         }
         if (err) break;
+        st_desc += 1; st_depth += depth;
         __syncwarp();
         // the leaf: step from its parent's state (:629).  `done` follows from the parent's meta alone.
         const int action = pk_act(pk_sel);
@@ -246,6 +249,7 @@ __global__ void __launch_bounds__(kThreads) k_select(View v) {
     }
     if (lane == 0) {
         h[H_TIE] = tie; h[H_NPATHS] = npaths; h[H_SIMS] += sims;
+        h[H_STAT_DESC] += st_desc; h[H_STAT_DEPTH] += st_depth; h[H_STAT_FAN] += st_fan;
         if (err) h[H_FLAGS] = (int)(flags | err);
     }
 }
@@ -588,6 +592,19 @@ __global__ void __launch_bounds__(kThreads) k_advance(View v, const int16_t* __r
     }
 }
 
+// selection statistics since the previous call, summed over the games: descents, edges walked, children scanned
+__global__ void k_search_stats(View v, unsigned long long* __restrict__ out3) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= v.G) return;
+    int* h = v.hdr + (size_t)g * H_WORDS;
+    if (h[H_STAT_DESC]) {
+        atomicAdd(&out3[0], (unsigned long long)h[H_STAT_DESC]);
+        atomicAdd(&out3[1], (unsigned long long)h[H_STAT_DEPTH]);
+        atomicAdd(&out3[2], (unsigned long long)h[H_STAT_FAN]);
+    }
+    h[H_STAT_DESC] = 0; h[H_STAT_DEPTH] = 0; h[H_STAT_FAN] = 0;
+}
+
 __global__ void k_status(View v, uint32_t* __restrict__ status, unsigned long long* __restrict__ sims) {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long mine = 0;
@@ -733,6 +750,12 @@ int tg_mcts_status(const TgMctsConfig* cfg, void* ws, uint32_t* status, unsigned
     if (check_cfg(cfg) || !ws) return set_err(-1, "tg_mcts_status");
     TG_MCTS_N(cfg, { View v = make_view<N>(cfg, ws); k_status<<<(v.G + 127) / 128, 128, 0, (cudaStream_t)stream>>>(v, status, sims); });
     return set_err((int)cudaGetLastError(), "tg_mcts_status");
+}
+
+int tg_mcts_search_stats(const TgMctsConfig* cfg, void* ws, unsigned long long* out3, void* stream) {
+    if (check_cfg(cfg) || !ws || !out3) return set_err(-1, "tg_mcts_search_stats");
+    TG_MCTS_N(cfg, { View v = make_view<N>(cfg, ws); k_search_stats<<<(v.G + 127) / 128, 128, 0, (cudaStream_t)stream>>>(v, out3); });
+    return set_err((int)cudaGetLastError(), "tg_mcts_search_stats");
 }
 
 int tg_mcts_outcome(const TgMctsConfig* cfg, void* ws, uint8_t* winner, float* score, float* territory, void* stream) {

@@ -57,6 +57,7 @@ def _declare(L):
     L.tg_mcts_root_states.argtypes = [P, vp]
     L.tg_mcts_root_states.restype = ctypes.c_void_p
     L.tg_mcts_outcome.argtypes = [P, vp, vp, vp, vp, vp]
+    L.tg_mcts_search_stats.argtypes = [P, vp, vp, vp]
     L.tg_synth_provider.argtypes = [i32, ctypes.c_int64, ctypes.c_uint64, ctypes.c_uint64, vp, vp, vp]
     L._tg_mcts_declared = True
 
@@ -149,6 +150,14 @@ class BatchedMCTS:
         n = int(self.sims.item())
         self.sims.zero_()
         return n
+
+    def search_stats(self):
+        """Selection statistics since the previous call: descents, mean depth (edges per descent), mean fan-out (children
+        scanned per visited node) -- the d and K of the traffic model in SURVEY.md 8d."""
+        out = self.torch.zeros([3], dtype=self.torch.int64, device=self.device)
+        _lib.check(self.lib.tg_mcts_search_stats(self._cfg, self._w(), _lib.ptr(out), self._s()), "tg_mcts_search_stats")
+        n, d, k = (int(x) for x in out.cpu().tolist())
+        return dict(descents=n, mean_depth=d / max(1, n), mean_fanout=k / max(1, d))
 
     # ---------------------------------------------------------------- the reference surface
     def reset_root(self):                                   # self_play.py:595-605
