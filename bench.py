@@ -75,7 +75,8 @@ def cpu_playout_baseline(seconds_per_core=1.5, cores=None):
 
 
 def _cpu_mcts_worker(args):
-    wid, sims = args
+    wid, sims = args[0], args[1]
+    net_device = args[2] if len(args) > 2 else "cpu"
     import torch
     torch.set_num_threads(1)
     import numpy as np
@@ -84,12 +85,14 @@ def _cpu_mcts_worker(args):
     from oracle import provider
     from transgo_b200.net import TransGoNetwork
     torch.manual_seed(0)
-    net = TransGoNetwork(board_size=9).eval()
+    net = TransGoNetwork(board_size=9).eval().to(net_device)
 
-    def ev(obs):
+    def ev(obs):                                               # self_play.py:777-793: H2D, forward, three D2H per wave
         with torch.no_grad():
-            p, v, _ = net.main_prediction(torch.from_numpy(np.stack(obs)))
-        return p.numpy(), v.numpy()
+            p, v, _ = net.main_prediction(torch.from_numpy(np.stack(obs)).to(net_device))
+        return p.cpu().numpy(), v.cpu().numpy()
+    if net_device != "cpu":
+        ev([np.zeros((10, 9, 9), np.float32)] * 4)             # CUDA context + cuDNN autotune outside the timed move
     cnt = [0]
 
     def tie(n):
@@ -102,18 +105,21 @@ def _cpu_mcts_worker(args):
     return m.sims, time.perf_counter() - t0
 
 
-def cpu_mcts_baseline(cores=None, sims=64):
-    """self_play.py WP_MCTS restated (oracle/mcts_oracle.py, pinned bit-exact to the reference) + the TransGo net on one
-    CPU thread per process, one game per process as the reference's actors do (transgo.py:92-96)."""
+def cpu_mcts_baseline(cores=None, sims=64, net_device="cpu"):
+    """self_play.py WP_MCTS restated (oracle/mcts_oracle.py, pinned bit-exact to the reference) + the TransGo net, one game per
+    process as the reference's actors do (transgo.py:92-96).  net_device "cpu": one CPU thread per process; "cuda:0": the
+    reference as shipped (configure.py:66) -- `cores` actor processes (reference default 6, configure.py:25) share the GPU for
+    their batch-of-4 forwards."""
     import multiprocessing as mp
     cores = cores or os.cpu_count() or 1
     ctx = mp.get_context("fork")
     with ctx.Pool(cores) as pool:
-        res = pool.map(_cpu_mcts_worker, [(w, sims) for w in range(cores)])
+        res = pool.map(_cpu_mcts_worker, [(w, sims, net_device) for w in range(cores)])
     total = sum(r[0] for r in res)
     wall = max(r[1] for r in res)
+    where = "net on 1 CPU thread each" if net_device == "cpu" else "python tree search on the host, net forward on %s as the reference ships" % net_device
     return dict(value=total / wall, unit="MCTS sims/s", cores=cores, kind="port",
-                sample="%d processes x one move of %d simulations (4 leaves per net call, net on 1 CPU thread each)" % (cores, sims))
+                sample="%d processes x one move of %d simulations (4 leaves per net call, %s)" % (cores, sims, where))
 
 
 # ------------------------------------------------------------------------------------------------ clocks
@@ -175,11 +181,15 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    cpu_mcts = None
+    cpu_mcts = cpu_mcts_gpu_net = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu, _ = cpu_playout_baseline()                        # before CUDA is initialised (fork-safe)
         if not args.no_mcts:
             cpu_mcts = cpu_mcts_baseline()
+            try:                                               # children create their own CUDA contexts; the parent has none yet
+                cpu_mcts_gpu_net = cpu_mcts_baseline(cores=6, sims=210, net_device="cuda:%d" % local)
+            except Exception as e:  # pragma: no cover
+                cpu_mcts_gpu_net = {"unavailable": str(e)[:200]}
     import torch
     import torch.distributed as dist
     from transgo_b200 import _lib
@@ -341,6 +351,8 @@ def run_ours(args):
         if mcts is not None:
             if cpu_mcts is not None:
                 mcts["cpu_baseline"] = cpu_mcts
+            if cpu_mcts_gpu_net is not None:
+                mcts["reference_style_gpu_net"] = cpu_mcts_gpu_net
             line["mcts"] = mcts
         if c4 is not None:
             line["c4_19x19"] = c4
