@@ -501,13 +501,14 @@ def mcts_bench(torch, dist, dev, rank, world, args):
     pol_r = torch.empty([G, 82], dtype=torch.float32, device=dev)
     val_r = torch.empty([G], dtype=torch.float32, device=dev)
 
-    def synth(obs):
+    wave_dev = torch.zeros([1], dtype=torch.int64, device=dev)
+
+    def synth(obs):                                            # capturable: the wave index lives on the device
         B = obs.shape[0]
         p, v = (pol, val) if B == G * 4 else (pol_r, val_r)
-        _lib.check(L.tg_synth_provider(9, B, 99, wave[0], _lib.ptr(p), _lib.ptr(v), _lib.stream_ptr()))
-        wave[0] += 1
+        _lib.check(L.tg_synth_provider_dev(9, B, 99, _lib.ptr(wave_dev), _lib.ptr(p), _lib.ptr(v), _lib.stream_ptr()))
         return p, v
-    eng = BatchedMCTS(synth, G, num_simulation=sims, tie_seed=1, game_id0=rank * G, device=dev)
+    eng = BatchedMCTS(synth, G, num_simulation=sims, tie_seed=1, game_id0=rank * G, device=dev, graph_waves=True)
     timed_moves(eng, 1)                                        # warm-up move
     eng.search_stats()
     rate, ms, n, waves = timed_moves(eng, moves)
@@ -517,7 +518,8 @@ def mcts_bench(torch, dist, dev, rank, world, args):
     # RMW per path node, 24 B per new child slot, policy row + value, legal mask, two states, the 3240 B of planes
     bps = d_bar * (16 * k_bar + 16) + 40 * (d_bar + 1) + 24 * k_bar + (4 * 82 + 4) + 16 + 2 * 48 + 3240
     out["tree_only"] = {"value": rate, "unit": "MCTS sims/s", "ms": ms, "sims": n, "moves": moves, "waves": waves,
-                        "provider": "tg_synth_provider (device-side synthetic policy/value, NOT the net)",
+                        "provider": "tg_synth_provider (device-side synthetic policy/value, NOT the net); each wave (select, leaves, "
+                                    "provider, expand) replayed as one CUDA graph",
                         "mean_depth": d_bar, "mean_fanout": k_bar, "bytes_per_sim": bps,
                         "gbps_algorithmic": rate * bps / 1e9}
     del eng
@@ -529,11 +531,12 @@ def mcts_bench(torch, dist, dev, rank, world, args):
     for name, dtype in (("e2e_net_bf16_fused", "fused"), ("e2e_net_bf16", torch.bfloat16), ("e2e_net_fp32", None)):
         if args.quick and dtype is None:
             continue
-        ev = make_fused_evaluator(net, cuda_graph=True) if dtype == "fused" else \
+        # fused: the whole wave (tree kernels + net) is one CUDA graph, the root batch has its own; eager nets: graph per forward
+        ev = make_fused_evaluator(net, cuda_graph="roots") if dtype == "fused" else \
             make_evaluator(net, dtype=dtype, channels_last=dtype is not None, cuda_graph=True)
-        eng = BatchedMCTS(ev, G, num_simulation=sims, tie_seed=1, game_id0=rank * G, device=dev)
-        for _ in range(3):
-            eng._eval(eng.obs)                                 # warm-up: captures the wave-shaped CUDA graph outside the timed move
+        eng = BatchedMCTS(ev, G, num_simulation=sims, tie_seed=1, game_id0=rank * G, device=dev, graph_waves=dtype == "fused")
+        for _ in range(3):                                     # warm-up waves: lazy initialisation and CUDA-graph capture happen here,
+            eng.run_wave()                                     # outside the timed move (they only add visits to the fresh roots)
         rate, ms, n, waves = timed_moves(eng, 1)
         out[name] = {"value": rate, "unit": "MCTS sims/s", "ms": ms, "sims": n, "moves": 1, "waves": waves,
                      "net": "TransGoNetwork 2.97 M params random init (seed 0), eval mode, 0.457 GFLOP/position" +

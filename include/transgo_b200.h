@@ -197,6 +197,8 @@ int tg_mcts_outcome(const TgMctsConfig* cfg, void* ws, uint8_t* winner, float* s
 /* a device-side synthetic policy/value provider for tree-only throughput runs (bench.py): policy[row] = normalised
  * heavy-tailed hash weights of (seed, row, wave), value in (-1, 1).  NOT the reference net. */
 int tg_synth_provider(int n, int64_t rows, uint64_t seed, uint64_t wave, float* policy, float* value, void* stream);
+/* same, with the wave index read from (and then incremented in) device memory, so that the call can sit inside a replayed CUDA graph */
+int tg_synth_provider_dev(int n, int64_t rows, uint64_t seed, unsigned long long* wave_counter, float* policy, float* value, void* stream);
 
 /* ---------------------------------------------------------------- (4) inference epilogue of the policy/value net
  * One pass over NHWC bf16 activations [rows][channels] (channels % 8 == 0):

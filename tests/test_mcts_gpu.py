@@ -259,3 +259,33 @@ def test_selfplay_round_feeds_the_replay_ring(oracle_built):
     assert obs.shape == (32, 10, 9, 9) and bool(((pi.sum(1) - 1).abs() < 1e-5).all()) and set(z.cpu().tolist()) <= {1.0, -1.0}
     st2 = selfplay_round(w, model, ring, pacing, augment=False)
     assert len(ring) == st["appended"] + st2["positions"]
+
+
+def test_graphed_waves_replay_bit_for_bit():
+    """BatchedMCTS(graph_waves=True) captures one wave (select, leaves, evaluator, expand) as a CUDA graph; replaying it must
+    give exactly the search the eager launches give (same counts, same chosen actions) over several moves."""
+    from transgo_b200 import _lib
+    from transgo_b200.mcts import BatchedMCTS, _declare
+    L = _lib.lib(); _declare(L)
+    G = 96
+
+    def make(graph):
+        pol = torch.empty([G * 4, 82], dtype=torch.float32, device="cuda"); val = torch.empty([G * 4], dtype=torch.float32, device="cuda")
+        pol_r = torch.empty([G, 82], dtype=torch.float32, device="cuda"); val_r = torch.empty([G], dtype=torch.float32, device="cuda")
+        wave = torch.zeros([1], dtype=torch.int64, device="cuda")
+
+        def synth(obs):
+            p, v = (pol, val) if obs.shape[0] == G * 4 else (pol_r, val_r)
+            _lib.check(L.tg_synth_provider_dev(9, obs.shape[0], 5, _lib.ptr(wave), _lib.ptr(p), _lib.ptr(v), _lib.stream_ptr()))
+            return p, v
+        return BatchedMCTS(synth, G, num_simulation=40, tie_seed=9, graph_waves=graph)
+    a, b = make(False), make(True)
+    g = torch.Generator(device="cuda"); g.manual_seed(4)
+    for move in range(4):
+        noise = a.make_noise(generator=g)
+        u = torch.rand([G], dtype=torch.float64, device="cuda", generator=g)
+        act_a, pi_a, _ = a.get_action_probs(True, noise=noise, u=u)
+        act_b, pi_b, _ = b.get_action_probs(True, noise=noise, u=u)
+        assert torch.equal(a.counts, b.counts) and torch.equal(act_a, act_b) and torch.equal(pi_a, pi_b), move
+        a.update_with_action(act_a); b.update_with_action(act_b)
+    assert b._wave_graph is not None and a._wave_graph is None

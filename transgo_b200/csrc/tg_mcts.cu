@@ -625,11 +625,15 @@ __global__ void k_winner(const float* __restrict__ score, uint8_t* __restrict__ 
     if (g < G) winner[g] = score[g] > 0.0f ? kBlack : kWhite;                          // environment.py:118-119
 }
 
+__global__ void k_bump(unsigned long long* c) { *c += 1ull; }
+
 // synthetic provider (bench only): heavy-tailed integer weights -> one f32 division per entry
-__global__ void k_synth(int A, long long rows, unsigned long long seed, unsigned long long wave, float* __restrict__ policy, float* __restrict__ value) {
+__global__ void k_synth(int A, long long rows, unsigned long long seed, unsigned long long wave, const unsigned long long* __restrict__ wave_dev,
+                        float* __restrict__ policy, float* __restrict__ value) {
     const long long row = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (row >= rows) return;
+    if (wave_dev) wave += *wave_dev;            // the wave index lives on the device when the wave is replayed from a CUDA graph
     unsigned long long sum = 0;
     for (int a = lane; a < A; a += 32) {
         const unsigned long long r = mix32(seed + wave * 0x632BE59BD9B4E019ull, (unsigned long long)row, (unsigned long long)a) & 0xFFFFu;
@@ -768,8 +772,15 @@ int tg_mcts_outcome(const TgMctsConfig* cfg, void* ws, uint8_t* winner, float* s
 
 int tg_synth_provider(int n, int64_t rows, uint64_t seed, uint64_t wave, float* policy, float* value, void* stream) {
     if (!policy || !value || rows <= 0 || (n != 9 && n != 19)) return set_err(-1, "tg_synth_provider");
-    k_synth<<<warp_blocks(rows), kThreads, 0, (cudaStream_t)stream>>>(n * n + 1, rows, seed, wave, policy, value);
+    k_synth<<<warp_blocks(rows), kThreads, 0, (cudaStream_t)stream>>>(n * n + 1, rows, seed, wave, nullptr, policy, value);
     return set_err((int)cudaGetLastError(), "tg_synth_provider");
+}
+
+int tg_synth_provider_dev(int n, int64_t rows, uint64_t seed, unsigned long long* wave_counter, float* policy, float* value, void* stream) {
+    if (!policy || !value || !wave_counter || rows <= 0 || (n != 9 && n != 19)) return set_err(-1, "tg_synth_provider_dev");
+    k_synth<<<warp_blocks(rows), kThreads, 0, (cudaStream_t)stream>>>(n * n + 1, rows, seed, 0ull, wave_counter, policy, value);
+    k_bump<<<1, 1, 0, (cudaStream_t)stream>>>(wave_counter);
+    return set_err((int)cudaGetLastError(), "tg_synth_provider_dev");
 }
 
 }  // extern "C"

@@ -168,12 +168,15 @@ class FusedTransGoInference:
 
 
 def make_fused_evaluator(model, dtype=torch.bfloat16, cuda_graph=True):
-    """evaluator(obs) -> (policy, value) for BatchedMCTS, forward captured once per static input tensor as a CUDA graph."""
+    """evaluator(obs) -> (policy, value) for BatchedMCTS, forward captured once per static input tensor as a CUDA graph.
+    cuda_graph=False: plain launches (use it when the caller captures a larger graph, e.g. BatchedMCTS(graph_waves=True));
+    cuda_graph="roots": plain launches while the current stream is being captured, own graphs otherwise (the search's wave
+    batch is captured by the engine, the per-move root batch runs outside it)."""
     net = FusedTransGoInference(model, dtype)
     graphs = {}
 
     def evaluator(obs):
-        if not cuda_graph:
+        if not cuda_graph or (cuda_graph == "roots" and torch.cuda.is_current_stream_capturing()):
             p, v, _ = net(obs)
             return p, v
         key = (obs.data_ptr(), tuple(obs.shape))

@@ -59,6 +59,7 @@ def _declare(L):
     L.tg_mcts_outcome.argtypes = [P, vp, vp, vp, vp, vp]
     L.tg_mcts_search_stats.argtypes = [P, vp, vp, vp]
     L.tg_synth_provider.argtypes = [i32, ctypes.c_int64, ctypes.c_uint64, ctypes.c_uint64, vp, vp, vp]
+    L.tg_synth_provider_dev.argtypes = [i32, ctypes.c_int64, ctypes.c_uint64, vp, vp, vp, vp]
     L._tg_mcts_declared = True
 
 
@@ -68,7 +69,7 @@ class BatchedMCTS:
 
     def __init__(self, evaluator, num_games, board_size=9, num_simulation=210, c_puct1=3, c_puct2=0.05, wu_loss=2,
                  parallel_readouts=4, max_step=None, komi=7.5, tie_mode="hash", tie_seed=0, game_id0=0,
-                 node_cap=None, edge_cap=None, max_depth=64, device="cuda", check_every=4):
+                 node_cap=None, edge_cap=None, max_depth=64, device="cuda", check_every=4, graph_waves=False):
         import torch
         self.torch = torch
         if not torch.cuda.is_available():
@@ -83,6 +84,12 @@ class BatchedMCTS:
         self.num_simulation = int(num_simulation)
         self.device = torch.device(device)
         self.check_every = check_every
+        # graph_waves: capture one whole wave (select + leaves kernels, the evaluator's kernels, expand) as a CUDA graph on its
+        # second call and replay it afterwards -- the wave loop is launch bound (a dozen launches around ~80 us of tree kernels).
+        # The evaluator must then be capturable: device-only work on static tensors, no host synchronisation, no own graph.
+        self.graph_waves = bool(graph_waves)
+        self._wave_graph = None
+        self._wave_calls = 0
         max_step = DEFAULT_MAX_STEP.get(self.n, 2 * self.P) if max_step is None else int(max_step)
         # every net-evaluated simulation adds one node; the kept subtree can carry several moves' worth of visits
         node_cap = node_cap or (6 * self.num_simulation + 64)
@@ -170,12 +177,27 @@ class BatchedMCTS:
         _lib.check(self.lib.tg_mcts_reset_games(self._cfg, self._w(), _lib.ptr(mask), self._s()), "tg_mcts_reset_games")
         self._expand_roots()
 
-    def run_wave(self):                                     # self_play.py:607-654
+    def _wave_body(self):
         _lib.check(self.lib.tg_mcts_wave_begin(self._cfg, self._w(), _lib.ptr(self.obs), self._s()), "tg_mcts_wave_begin")
         policy, value = self._eval(self.obs)
         self.pending.zero_()
         _lib.check(self.lib.tg_mcts_wave_end(self._cfg, self._w(), _lib.ptr(policy), _lib.ptr(value), _lib.ptr(self.pending),
                                              self._s()), "tg_mcts_wave_end")
+
+    def run_wave(self):                                     # self_play.py:607-654
+        torch = self.torch
+        if self._wave_graph is not None:
+            self._wave_graph.replay()
+        elif self.graph_waves and self._wave_calls >= 1:    # the first wave ran eagerly (lazy inits, autotuning); capture this one
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._wave_body()
+            self._wave_graph = g
+            g.replay()                                      # capture does not execute
+        else:
+            self._wave_body()
+        self._wave_calls += 1
         self.waves += 1
 
     def make_noise(self, alpha=0.03, generator=None):
