@@ -86,8 +86,11 @@ __device__ __forceinline__ double warp_max(double x) {
 
 // value backup along a recorded path (self_play.py:758-764 + Node_V.value_mean_var :84-88); lane-parallel: edge i of a
 // path of `len` edges receives v * (-1)^(len-1-i), the root itself v * (-1)^len.
+// ons_delta (a multiple of wu_loss, usually -wu_loss) is applied to the same nodes in the same pass: revert_incomplete_update
+// (:770-774) and backpropagate touch exactly the same records.
 template <int N>
-__device__ __forceinline__ void backup(const View& v, int* h, uint4* hot, uint2* cold, const int* path, int len, float value, unsigned& err) {
+__device__ __forceinline__ void backup(const View& v, int* h, uint4* hot, uint2* cold, const int* path, int len, float value, unsigned& err,
+                                       int ons_delta = 0) {
     const int lane = threadIdx.x & 31;
     for (int i = lane; i <= len; i += 32) {
         const float sv = ((len - 1 - i) & 1) ? -value : value;       // i == len -> (-1)^(-1) handled below
@@ -99,6 +102,7 @@ __device__ __forceinline__ void backup(const View& v, int* h, uint4* hot, uint2*
             const float mean = __fdiv_rn(W, (float)(n + 1));
             const float var = __fadd_rn(__int_as_float(h[H_ROOTVAR]), __fmul_rn(__fsub_rn(rv, t), __fsub_rn(rv, mean)));
             h[H_ROOTW] = __float_as_int(W); h[H_ROOTN] = n; h[H_ROOTMEAN] = __float_as_int(mean); h[H_ROOTVAR] = __float_as_int(var);
+            h[H_ROOTONS] += ons_delta;
         } else {
             const int e = path[i];
             uint4 q = hot[e];
@@ -109,7 +113,7 @@ __device__ __forceinline__ void backup(const View& v, int* h, uint4* hot, uint2*
             const float t = __uint_as_float(c.x);
             const float mean = __fdiv_rn(W, (float)(n + 1));
             const float var = __fadd_rn(__uint_as_float(q.z), __fmul_rn(__fsub_rn(sv, t), __fsub_rn(sv, mean)));
-            q.y = __float_as_uint(W); q.z = __float_as_uint(var); q.w += (1u << 16);
+            q.y = __float_as_uint(W); q.z = __float_as_uint(var); q.w = (uint32_t)((int)q.w + (1 << 16) + ons_delta * 512);
             c.x = __float_as_uint(mean);
             hot[e] = q; cold[e] = c;
         }
@@ -163,14 +167,15 @@ __global__ void __launch_bounds__(kThreads) k_select(View v) {
             const int eb = (int)info.x, K = (int)info.y;
             st_fan += K;
             const double sq = __dsqrt_rn((double)(Np + onsp));
-            double sc[MAXR]; uint32_t pk[MAXR];
-            double best = -1.0e300;
+            double sc[MAXR]; uint32_t pk[MAXR], ch[MAXR];            // ch: child node of each scanned edge (cold record), loaded
+            double best = -1.0e300;                                  // with the hot record so that the descent needs no second trip
 #pragma unroll
             for (int r = 0; r < MAXR; ++r) {
                 const int k = lane + 32 * r;
-                sc[r] = -1.0e300; pk[r] = 0;
+                sc[r] = -1.0e300; pk[r] = 0; ch[r] = 0xffffffffu;
                 if (k < K) {
                     const uint4 q = hot[eb + k];
+                    ch[r] = cold[eb + k].y;
                     const float prior = __uint_as_float(q.x), W = __uint_as_float(q.y), var = __uint_as_float(q.z);
                     const int nc = pk_n(q.w), oc = pk_ons(q.w);
                     // prior_score = c1 * prior * sqrt(Np + ons_p) / (Nc + ons_c + 1)          (:718-719)
@@ -200,6 +205,7 @@ __global__ void __launch_bounds__(kThreads) k_select(View v) {
                 tie += 1;
             }
             int ksel = -1;
+            uint32_t ch_sel = 0xffffffffu;
 #pragma unroll
             for (int r = 0; r < MAXR; ++r) {
                 const int c = __popc(bal[r]);
@@ -207,13 +213,14 @@ __global__ void __launch_bounds__(kThreads) k_select(View v) {
                     const int src = nth_bit(bal[r], j);
                     ksel = src + 32 * r;
                     pk_sel = __shfl_sync(0xffffffffu, pk[r], src);
+                    ch_sel = __shfl_sync(0xffffffffu, ch[r], src);
                 } else if (ksel < 0) j -= c;
             }
             const int e = eb + ksel;
             if (depth >= v.MAXD) { err |= TG_MCTS_ERR_DEPTH; break; }
             if (lane == 0) path[depth] = e;
             depth += 1;
-            const int child = (int)cold[e].y;
+            const int child = (int)ch_sel;
             if (child < 0) break;
             Np = pk_n(pk_sel); onsp = pk_ons(pk_sel); node = child;
         }
@@ -342,15 +349,14 @@ __global__ void __launch_bounds__(kThreads) k_expand(View v, const float* __rest
         const size_t slot = (size_t)g * v.R + j;
         const int* path = v.paths + slot * v.MAXD;
         const int len = v.path_len[slot];
-        add_ons(h, hot, path, len, -v.wu);                                            // :653
         const int e = path[len - 1];
-        if ((int)cold[e].y >= 0 || err) continue;                                      // :733-734 duplicate leaf: no backup
-        const float val = value[slot];
+        const float val = value[slot];                                                // (issued with the loads below, used later)
+        if ((int)cold[e].y >= 0 || err) { add_ons(h, hot, path, len, -v.wu); continue; }   // :653, :733-734 duplicate leaf: no backup
         const int K = compact_legal<N>(v.leaf_legal + slot * GG::DQ * 4, policy + slot * GG::A, sp, sa);
         const int node = nn, eb = ne;
         if (node + 1 > v.NC) err |= TG_MCTS_ERR_NODES;
         if (eb + K > v.EC) err |= TG_MCTS_ERR_EDGES;
-        if (err) continue;
+        if (err) { add_ons(h, hot, path, len, -v.wu); continue; }
         float scale = 0.0f;                                                           // :739 python sum(): sequential float32
         if (lane == 0) for (int k = 0; k < K; ++k) scale = __fadd_rn(scale, sp[k]);
         scale = __shfl_sync(0xffffffffu, scale, 0);
@@ -369,7 +375,7 @@ __global__ void __launch_bounds__(kThreads) k_expand(View v, const float* __rest
         }
         nn = node + 1; ne = eb + K;
         __syncwarp();
-        backup<N>(v, h, hot, cold, path, len, val, err);                               // :755
+        backup<N>(v, h, hot, cold, path, len, val, err, -v.wu);                        // :653 + :755 in one pass over the path
         sims += 1;
         __syncwarp();
     }
