@@ -289,3 +289,15 @@ def test_graphed_waves_replay_bit_for_bit():
         assert torch.equal(a.counts, b.counts) and torch.equal(act_a, act_b) and torch.equal(pi_a, pi_b), move
         a.update_with_action(act_a); b.update_with_action(act_b)
     assert b._wave_graph is not None and a._wave_graph is None
+
+
+def test_evaluate_match_alternates_colours_and_counts_wins(oracle_built):
+    """self_play.py:987-1040 batched: a provider that always wants to capture the centre vs. the same one -- the bookkeeping
+    (colour alternation, winner from the area score with komi, win + lose = games) is what is checked here."""
+    from transgo_b200.selfplay import evaluate_match
+    out = evaluate_match(cpu_provider(3, 6), cpu_provider(4, 6), n_games=6, num_simulation=24, max_step=12, tie_seed=2)
+    assert out["win"] + out["lose"] == 6 and 0.0 <= out["win_ratio"] <= 1.0
+    assert out["new_plays_black"].cpu().tolist() == [True, False, True, False, True, False]
+    assert set(out["winners"].cpu().tolist()) <= {1, 2} and 1 <= out["plies"] <= 13
+    w = out["winners"].cpu().numpy(); nb = out["new_plays_black"].cpu().numpy()
+    assert out["win"] == int(((w == 1) & nb).sum() + ((w == 2) & ~nb).sum())

@@ -95,3 +95,53 @@ def selfplay_round(worker, model, ring=None, pacing=None, src=0, dst=0, augment=
             pacing.add_play_steps(total_pos)
             pacing.add_play_games(stats["games"] * (dist.get_world_size() if multi else 1))
     return stats
+
+
+def _root_state_view(search):
+    """int32 [SQ, G, 4] view of the engine's root states inside its workspace (same layout as BatchedGoEnv.states)."""
+    sq = search.lib.tg_state_bytes(search.n) // 16
+    base = search.lib.tg_mcts_root_states(search._cfg, search._w())
+    off = (base - search.ws.data_ptr()) // 4
+    return search.ws.reshape(-1)[off:off + sq * search.G * 4].reshape(sq, search.G, 4)
+
+
+def evaluate_match(evaluator_new, evaluator_old, n_games=10, board_size=9, device="cuda", seed=0, **mcts_kw):
+    """Batched form of SelfPlay.policy_evaluate (self_play.py:987-1040): `n_games` games between the newest weights and the
+    "evaluate" weights, colours alternating from game to game (:1000, :1026), every move chosen by a FRESH search of the side
+    to move from the current position (select_action, :689-704: no tree reuse, no root noise, temperature 0.12).
+
+    All games advance together.  At every ply the new net searches the games in which it is to move and the old net the
+    others, each in its own engine of n_games / 2 slots.  Returns dict(win, lose, win_ratio, winners, new_plays_black)."""
+    from . import _lib
+    from .environment import BatchedGoEnv
+    assert n_games % 2 == 0, "colours alternate: use an even number of games"
+    G, half = int(n_games), int(n_games) // 2
+    env = BatchedGoEnv(G, board_size=board_size, device=device, max_step=mcts_kw.get("max_step"), komi=mcts_kw.get("komi", 7.5))
+    eng_new = BatchedMCTS(evaluator_new, half, board_size=board_size, device=device, **mcts_kw)
+    eng_old = BatchedMCTS(evaluator_old, half, board_size=board_size, device=device, **mcts_kw)
+    dev = env.device
+    new_black = torch.arange(G, device=dev) % 2 == 0                   # game i: the new net holds BLACK iff i is even
+    idx_a, idx_b = torch.nonzero(new_black).reshape(-1), torch.nonzero(~new_black).reshape(-1)
+    gen = torch.Generator(device=dev); gen.manual_seed(seed)
+    fresh = BatchedGoEnv(1, board_size=board_size, device=device).states      # an empty board for finished slots
+    ply = 0
+    while not bool(env.done.all()) and ply <= env.max_step + 1:
+        black_to_move = ply % 2 == 0                                      # every game alternates strictly (a pass is a move)
+        actions = torch.zeros([G], dtype=torch.int16, device=dev)
+        for eng, idx in ((eng_new, idx_a if black_to_move else idx_b), (eng_old, idx_b if black_to_move else idx_a)):
+            _lib.check(eng.lib.tg_mcts_init(eng._cfg, eng._w(), eng._s()), "tg_mcts_init")
+            st = env.states[:, idx]
+            over = env.done[idx].bool()
+            st = torch.where(over[None, :, None], fresh.expand(-1, half, -1), st)
+            _root_state_view(eng).copy_(st)
+            eng._expand_roots()
+            u = torch.rand([half], dtype=torch.float64, device=dev, generator=gen)
+            a, _, _ = eng.get_action_probs(is_selfplay=False, u=u)
+            actions[idx] = a
+        env.step(actions, want_legal=False)
+        ply += 1
+    score = env.score()
+    winners = torch.where(score > 0, 1, 2)                                # environment.py:118-119
+    new_won = torch.where(new_black, winners == 1, winners == 2)
+    win = int(new_won.sum().item())
+    return dict(win=win, lose=G - win, win_ratio=win / G, winners=winners, new_plays_black=new_black, plies=ply)
