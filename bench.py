@@ -339,7 +339,7 @@ def run_ours(args):
             "gpu_launches": launches[0],
             "clocks": sampler.summary(),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "tg::k_playout_rows<9>" if env.playout_layout() == "rows" else "tg::k_playout<9,%s>" % env.playout_layout(),
+                         "traffic": traffic, "kernel": playout_kernel_name(env),
                          "launch_ms": launch_ms,
                          "bytes_per_ply": BYTES_PER_PLY, "plies_per_launch": plies_per_launch,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
@@ -359,6 +359,13 @@ def run_ours(args):
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def playout_kernel_name(env):
+    t = env.lib.tg_env_playout_tile(env.n, env.G, env.tile)
+    if t < 0:
+        return "tg::k_playout_rows<%d>" % env.n
+    return ("tg::k_playout_wu<%d,%d>" if t & 64 else "tg::k_playout<%d,%d>") % (env.n, t & 63)
 
 
 def stepwise_and_sweep(torch, dev, BatchedGoEnv):

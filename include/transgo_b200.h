@@ -74,6 +74,9 @@ int         tg_legal_words(int n);              /* u32 words of a dense legal ma
  * very large batches); 0 lets the library choose from G.  tg_env_playout also takes TG_TILE_ROWS: one board ROW per lane,
  * 31 / (n + 1) games side by side in a warp (csrc/tg_rows.cuh) -- the fastest layout at the BASELINE batch sizes. */
 #define TG_TILE_ROWS (-1)
+/* tg_env_playout: OR into a tile width of 4, 8 or 16 to run the tiles that share a warp in lock step (warp-uniform control
+ * flow: one warp never executes two games' branches one after the other) */
+#define TG_TILE_UNIFORM 64
 
 /* board.cc:13-26 + go_env.cc:34-41 */
 int tg_env_reset(int n, void* states, int64_t G, void* stream);

@@ -15,9 +15,9 @@ def t(env, reps=4):
     return best
 
 
-print("games   " + "  ".join("%8s" % x for x in ("T=32", "T=16", "T=8", "T=1", "rows")))
+print("games   " + "  ".join("%8s" % x for x in ("T=32", "T=16", "WU16", "WU8", "WU4", "rows")))
 for G in (148, 592, 1184, 2368, 4096, 8192, 16384):
     row = []
-    for tile in (32, 16, 8, 1, -1):
+    for tile in (32, 16, 16 | 64, 8 | 64, 4 | 64, -1):
         row.append(t(BatchedGoEnv(G, tile=tile)))
     print("%6d  " % G + "  ".join("%6.3fms" % x for x in row), flush=True)

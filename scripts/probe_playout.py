@@ -18,7 +18,7 @@ def time_it(fn, reps=5):
 ref = {}
 for n, Gs in ((9, (4096, 16384, 65536, 1 << 20)), (19, (512, 8192))):
     for G in Gs:
-        for tile in (-1, 32, 16, 8, 4, 1):
+        for tile in (-1, 32, 16, 16 | 64, 8, 8 | 64, 4 | 64, 1):
             if G >= 65536 and tile > 8:
                 continue
             env = BatchedGoEnv(G, board_size=n, tile=tile)

@@ -86,7 +86,7 @@ def _replay_trace_with_oracle(n, trace, game_ids, seed, max_step, no_eye=False):
 
 @pytest.mark.parametrize("n,G,tile,no_eye", [(9, 4096, 32, False), (9, 4096, 8, False), (9, 4096, 1, False),
                                              (9, 1024, 32, True), (19, 256, 32, False), (19, 256, 1, False),
-                                             (9, 4096, 16, False), (9, 4096, -1, False), (9, 1000, -1, True), (9, 1, -1, False),
+                                             (9, 4096, 16, False), (9, 4099, 16 | 64, False), (9, 1001, 8 | 64, True), (19, 67, 4 | 64, False), (19, 200, 8 | 64, False), (9, 4096, -1, False), (9, 1000, -1, True), (9, 1, -1, False),
                                              (19, 256, -1, False), (19, 37, -1, True)])
 def test_playout_matches_oracle(oracle_built, n, G, tile, no_eye):
     """G concurrent random playouts in one launch; a sample of games is replayed on the CPU."""
@@ -180,13 +180,13 @@ def test_step_kernel_per_ply_against_oracle(oracle_built, n, G, tile):
 
 
 def test_tiles_agree_bit_for_bit_at_full_size():
-    """Size-independent property at the BASELINE C2 size and beyond: the tile widths (32, 8, 1 lanes per game) and the
-    row-per-lane layout (-1, a different formulation of the rules) are different programs and must produce identical final
+    """Size-independent property at the BASELINE C2 size and beyond: the tile widths (32, 8, 1 lanes per game), the lock-step variant
+    (8 | 64) and the row-per-lane layout (-1, a different formulation of the rules) are different programs and must produce identical final
     states, scores and planes."""
     from transgo_b200.environment import BatchedGoEnv
     G = 65536
     ref = None
-    for tile in (32, 8, 1, -1):
+    for tile in (32, 8, 1, -1, 8 | 64):
         env = BatchedGoEnv(G, board_size=9, tile=tile)
         env.playout(122, seed=99)
         out = (env.states.clone(), env.score(), env.encode(), env.legal_mask().clone())

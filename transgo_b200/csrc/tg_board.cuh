@@ -327,11 +327,42 @@ template <int T> struct Tile {
 template <int N, int T> __device__ __forceinline__ BB<N> tile_or(const BB<N>& a) {
     BB<N> r; TG_FOR_W r.w[i] = Tile<T>::template reduce_or<typename Geo<N>::word_t>(a.w[i]); return r;
 }
+// the same when the whole warp is known to be converged (warp-uniform kernels): butterflies under the constant full mask
+// stay inside the aligned T-lane tile and spare the variable-mask synchronisation protocol
+template <int N, int T> __device__ __forceinline__ BB<N> tile_or_converged(const BB<N>& a) {
+    using word_t = typename Geo<N>::word_t;
+    if constexpr (T == 1) return a;
+    else if constexpr (T == 32) return tile_or<N, 32>(a);
+    else {
+        BB<N> r = a;
+#pragma unroll
+        for (int s = T / 2; s >= 1; s >>= 1)
+            TG_FOR_W {
+                if constexpr (sizeof(word_t) == 4) r.w[i] |= __shfl_xor_sync(0xffffffffu, r.w[i], s);
+                else r.w[i] |= (word_t)__shfl_xor_sync(0xffffffffu, (unsigned long long)r.w[i], s);
+            }
+        return r;
+    }
+}
+
+// Loop / branch votes.  WU ("warp-uniform"): the tiles that share a warp vote together, so every lane of the warp follows
+// the same control flow -- a game whose own condition is false runs harmless extra iterations instead of forcing the
+// warp to execute the two games' paths one after the other.
+template <int T, bool WU> __device__ __forceinline__ bool vote_any(bool p) {
+    if (WU && T < 32) return __any_sync(0xffffffffu, p);
+    return Tile<T>::any(p);
+}
+
+// a condition that is already the same in every lane of a tile (it depends on the position only): WU widens it to the warp
+template <int T, bool WU> __device__ __forceinline__ bool uniform_cond(bool p) {
+    if (WU && T < 32) return __any_sync(0xffffffffu, p);
+    return p;
+}
 
 // flood `seed` through `mask` (4-connectivity) until no lane of the tile changes any more.
-template <int N, int T> __device__ __forceinline__ BB<N> flood(BB<N> g, const BB<N>& mask) {
+template <int N, int T, bool WU = false> __device__ __forceinline__ BB<N> flood(BB<N> g, const BB<N>& mask) {
     bool ch = any(g);
-    while (Tile<T>::any(ch)) {
+    while (vote_any<T, WU>(ch)) {
         BB<N> n1 = (g | nbrs(g)) & mask;
         BB<N> n2 = (n1 | nbrs(n1)) & mask;
         ch = differs(n2, g);
@@ -344,7 +375,7 @@ template <int N, int T> __device__ __forceinline__ BB<N> flood(BB<N> g, const BB
 // callers only distinguish 1 / 2 / >=3 liberties (board_feature.cc:17-41, board.cc:130-158), and big groups reach the
 // limit in the first step.  On return `complete` tells whether g is the whole group (then libs is exact); otherwise
 // libs >= lim.  The loop is tile-uniform: it runs until no lane still needs another step.
-template <int N, int T>
+template <int N, int T, bool WU = false>
 __device__ __forceinline__ void flood_group(BB<N>& g, const BB<N>& col, const BB<N>& empty, int lim, int& libs, bool& complete) {
     bool ch = any(g);
     libs = 0;
@@ -356,7 +387,7 @@ __device__ __forceinline__ void flood_group(BB<N>& g, const BB<N>& col, const BB
         ch = differs(n1, g);
         g = n1;
         complete = !ch;
-        if (!Tile<T>::any(ch && libs < lim)) break;
+        if (!vote_any<T, WU>(ch && libs < lim)) break;
     }
 }
 
@@ -441,7 +472,7 @@ __device__ __forceinline__ void analyse_groups(const BB<N>& black, const BB<N>& 
 // places -- StoneLibertyAnalysis of a point with no empty neighbour (board.cc:90-158) and the capture test around the
 // stone just played (board.cc:606-630) -- so a playout ply floods the handful of groups next to those points instead of
 // every group on the board.  l1b / l1w are OR-ed into (callers pass zero or an earlier partial result).
-template <int N, int T>
+template <int N, int T, bool WU = false>
 __device__ __forceinline__ void analyse_seeded(const BB<N>& black, const BB<N>& white, const BB<N>& seeds, BB<N>& l1b, BB<N>& l1w) {
     using G = Geo<N>;
     const BB<N> empty = bb_not(black | white);
@@ -471,21 +502,22 @@ __device__ __forceinline__ void analyse_seeded(const BB<N>& black, const BB<N>& 
     sb = andn(andn(sb, shift_e(sb)), shift_s(sb));
     sw = andn(andn(sw, shift_e(sw)), shift_s(sw));
     const int nb = count(sb), total = nb + count(sw);
-    for (int base = 0; base < total; base += T) {               // tile-uniform trip count
+    for (int base = 0; uniform_cond<T, WU>(base < total); base += T) {   // tile-uniform (WU: warp-uniform) trip count
         const int j = base + Tile<T>::lane();
         const bool valid = j < total;
         const bool is_w = j >= nb;
         BB<N> g = bb_nth_bit<N>(is_w ? sw : sb, valid ? (is_w ? j - nb : j) : -1);
         const BB<N> col = bb_select(is_w, white, black);
         int c; bool complete;
-        flood_group<N, T>(g, col, empty, 2, c, complete);
+        flood_group<N, T, WU>(g, col, empty, 2, c, complete);
         const bool is1 = valid && complete && c == 1;
         TG_FOR_W {
             const typename G::word_t m1 = is1 ? g.w[i] : 0;
             p1b.w[i] |= is_w ? 0 : m1; p1w.w[i] |= is_w ? m1 : 0;
         }
     }
-    if (total > 0) { l1b = l1b | tile_or<N, T>(p1b); l1w = l1w | tile_or<N, T>(p1w); }
+    if (WU) { l1b = l1b | tile_or_converged<N, T>(p1b); l1w = l1w | tile_or_converged<N, T>(p1w); }
+    else if (total > 0) { l1b = l1b | tile_or<N, T>(p1b); l1w = l1w | tile_or<N, T>(p1w); }
 }
 
 // Empty points with no empty neighbour: the only points whose legality depends on group liberties.
@@ -499,7 +531,7 @@ template <int N> __device__ __forceinline__ BB<N> enclosed_points(const BB<N>& b
 // groups), while a wider tile floods every group at once, one per lane in lock step (its cost is the MAX over groups, and
 // the result then also serves the capture test of the move).  On return l1b / l1w hold the atari classes of the analysed
 // groups and `known` = the points whose neighbour groups are all analysed (apply_stone_lazy wants both).
-template <int N, int T>
+template <int N, int T, bool WU = false>
 __device__ __forceinline__ BB<N> legal_points_lazy(const Pos<N>& s, BB<N>& l1b, BB<N>& l1w, BB<N>& known) {
     const BB<N>& black = s.stones[0]; const BB<N>& white = s.stones[1];
     const BB<N> stones = black | white;
@@ -507,9 +539,9 @@ __device__ __forceinline__ BB<N> legal_points_lazy(const Pos<N>& s, BB<N>& l1b, 
     const BB<N> encl = andn(empty, nbrs(empty));
     l1b = bb_zero<N>(); l1w = bb_zero<N>();
     known = encl;
-    if (any(encl)) {                                                                        // tile-uniform branch
+    if (uniform_cond<T, WU>(any(encl))) {                                                       // tile- (WU: warp-) uniform branch
         if (T == 1) analyse_seeded<N, T>(black, white, nbrs(encl) & stones, l1b, l1w);
-        else { analyse_seeded<N, T>(black, white, stones, l1b, l1w); known = bb_full<N>(); }
+        else { analyse_seeded<N, T, WU>(black, white, stones, l1b, l1w); known = bb_full<N>(); }
     }
     const bool me_black = s.player == kBlack;
     const BB<N> own = bb_select(me_black, black, white);
@@ -523,28 +555,30 @@ __device__ __forceinline__ BB<N> legal_points_lazy(const Pos<N>& s, BB<N>& l1b, 
 
 // One TRUSTED board move (the caller took pb from legal_points_lazy of this very position), given the partial atari sets
 // that call produced.  Same state transition as apply_move (go_env.cc:51-80, board.cc:546-661).
-template <int N, int T>
-__device__ __forceinline__ bool apply_stone_lazy(Pos<N>& s, const BB<N>& pb, int action, BB<N> l1b, BB<N> l1w, const BB<N>& known, int max_step) {
+template <int N, int T, bool WU = false>
+__device__ __forceinline__ bool apply_stone_lazy(Pos<N>& s, const BB<N>& pb, int action, BB<N> l1b, BB<N> l1w, const BB<N>& known, int max_step,
+                                                 bool placing = true) {
     const bool me_black = s.player == kBlack;
     const BB<N> own = bb_select(me_black, s.stones[0], s.stones[1]), opp = bb_select(me_black, s.stones[1], s.stones[0]);
     const BB<N> around = nbrs(pb);
     const BB<N> touch = around & opp;
-    if (any(touch) && !any(pb & known))                               // groups next to the stone not analysed yet
-        analyse_seeded<N, T>(s.stones[0], s.stones[1], touch, l1b, l1w);
+    if (uniform_cond<T, WU>(any(touch) && !any(pb & known)))               // groups next to the stone not analysed yet
+        analyse_seeded<N, T, WU>(s.stones[0], s.stones[1], touch, l1b, l1w);
     const BB<N> l1opp = bb_select(me_black, l1w, l1b);
     const BB<N> hit = around & l1opp;                                 // enemy neighbours in atari: they die
     bool ko = false;
-    if (any(hit)) {                                                   // tile-uniform
+    if (uniform_cond<T, WU>(any(hit))) {                                  // tile- (WU: warp-) uniform
         const BB<N> empty = bb_not(own | opp);
-        if (!any(around & (empty | own))) {                           // board.cc:163-194, 561-570
+        if (any(hit) && !any(around & (empty | own))) {               // board.cc:163-194, 561-570
             const BB<N> cand = andn(hit, nbrs(opp));
             ko = count(cand) == 1;
             if (ko) { s.ko_loc = bb_lowest(cand); s.ko_color = 3 - s.player; s.ko_age = 0; }
         }
-        const BB<N> dead = flood<N, T>(hit, l1opp);                   // board.cc:606-630
+        const BB<N> dead = flood<N, T, WU>(hit, l1opp);               // board.cc:606-630
         const BB<N> left = andn(opp, dead);
         TG_FOR_W { s.stones[0].w[i] = me_black ? s.stones[0].w[i] : left.w[i]; s.stones[1].w[i] = me_black ? left.w[i] : s.stones[1].w[i]; }
     }
+    if (!placing) return false;
     if (!ko) s.ko_age += 1;
     TG_FOR_W { s.stones[0].w[i] |= me_black ? pb.w[i] : 0; s.stones[1].w[i] |= me_black ? 0 : pb.w[i]; }
     s.player = 3 - s.player; s.last2 = s.last1; s.last1 = action; s.step += 1;

@@ -155,6 +155,48 @@ k_playout(uint4* __restrict__ states, long long G, int plies, int max_step, unsi
     }
 }
 
+// Warp-uniform variant of k_playout for T < 32: the tiles that share a warp vote together (vote_any<T, true>), so the warp
+// never executes two games' control paths one after the other.
+template <int N, int T>
+__global__ void __launch_bounds__(kThreads)
+k_playout_wu(uint4* __restrict__ states, long long G, int plies, int max_step, unsigned long long seed, long long game_id0,
+             int no_eye, int16_t* __restrict__ trace, unsigned long long* __restrict__ plies_done) {
+    using GG = Geo<N>;
+    long long g = (blockIdx.x * (long long)blockDim.x + threadIdx.x) / T;
+    const bool exists = g < G;
+    if (!__any_sync(0xffffffffu, exists)) return;
+    Pos<N> s; pos_reset(s); s.terminated = 1;
+    if (exists) pos_load<N>(s, states, g, G, 1);
+    int played = 0;
+    for (int t = 0; t < plies; ++t) {
+        int action = kInvalid;
+        const bool active = !s.terminated;
+        if (__any_sync(0xffffffffu, active)) {
+            BB<N> l1b, l1w, known;
+            BB<N> lg = legal_points_lazy<N, T, true>(s, l1b, l1w, known);
+            if (no_eye) lg = andn(lg, true_eyes(stones_of(s, s.player), stones_of(s, 3 - s.player)));
+            const int nl = count(lg);
+            const bool placing = active && nl > 0;
+            const uint32_t r = mix32(seed, (unsigned long long)(game_id0 + g), (unsigned long long)s.step);
+            int wi, bit;
+            bb_locate<N>(lg, placing ? (int)(((unsigned long long)r * (unsigned)nl) >> 32) : -1, wi, bit);
+            BB<N> pb; TG_FOR_W pb.w[i] = (placing && i == wi) ? (typename GG::word_t(1) << bit) : typename GG::word_t(0);
+            const int a = wb_to_pt<N>(wi < 0 ? 0 : wi, bit);
+            apply_stone_lazy<N, T, true>(s, pb, a, l1b, l1w, known, max_step, placing);
+            if (active) {
+                action = placing ? a : GG::P;
+                if (!placing) apply_pass<N>(s, kPass, max_step);
+                played += 1;
+            }
+        }
+        if (trace && exists && Tile<T>::lane() == 0) trace[(long long)t * G + g] = (int16_t)action;
+    }
+    if (exists && Tile<T>::lane() == 0) {
+        pos_store<N>(s, states, g, G, 1);
+        if (plies_done && played) atomicAdd(plies_done, (unsigned long long)played);
+    }
+}
+
 // Row-per-lane playout (tg_rows.cuh): 31 / (N+1) games per warp, one board row per lane.  Same move rule, same results.
 template <int N>
 __global__ void __launch_bounds__(kThreads)
@@ -257,6 +299,9 @@ int pick_tile(int tile, long long G) {
         case 4:  FN<NN, 4>(__VA_ARGS__); break;                          \
         case 2:  FN<NN, 2>(__VA_ARGS__); break;                          \
         case 1:  FN<NN, 1>(__VA_ARGS__); break;                          \
+        case 16 | TG_TILE_UNIFORM: FN<NN, 16 | TG_TILE_UNIFORM>(__VA_ARGS__); break; \
+        case 8 | TG_TILE_UNIFORM:  FN<NN, 8 | TG_TILE_UNIFORM>(__VA_ARGS__); break;  \
+        case 4 | TG_TILE_UNIFORM:  FN<NN, 4 | TG_TILE_UNIFORM>(__VA_ARGS__); break;  \
         default: return set_err(-1, "tile must be a power of two <= 32"); \
     }
 #define TG_DISPATCH(n, tile, FN, ...)                                    \
@@ -297,9 +342,17 @@ template <int N> void launch_playout_rows(cudaStream_t st, uint4* states, long l
     k_playout_rows<N><<<(unsigned)((warps * 32 + kRowThreads - 1) / kRowThreads), kRowThreads, 0, st>>>(states, G, plies, max_step, seed, game_id0,
                                                                                                  no_eye, trace, plies_done);
 }
-template <int N, int T> void launch_playout(cudaStream_t st, uint4* states, long long G, int plies, int max_step, unsigned long long seed,
-                                            long long game_id0, int no_eye, int16_t* trace, unsigned long long* plies_done) {
-    k_playout<N, T><<<blocks_for(G, T), kThreads, 0, st>>>(states, G, plies, max_step, seed, game_id0, no_eye, trace, plies_done);
+template <int N, int TC> void launch_playout(cudaStream_t st, uint4* states, long long G, int plies, int max_step, unsigned long long seed,
+                                             long long game_id0, int no_eye, int16_t* trace, unsigned long long* plies_done) {
+    constexpr int T = TC & (TG_TILE_UNIFORM - 1);  // TC = lanes per game (+ TG_TILE_UNIFORM: the tiles of a warp run in lock step)
+    if constexpr ((TC & TG_TILE_UNIFORM) != 0) {
+        // a playout CTA lives for the whole game: with few warps per SM one-warp CTAs spread them evenly over the 148 SMs
+        const long long warps = (G * T + 31) / 32;
+        const int threads = warps < 148LL * 16 ? 32 : kThreads;
+        k_playout_wu<N, T><<<(unsigned)((G * T + threads - 1) / threads), threads, 0, st>>>(states, G, plies, max_step, seed, game_id0, no_eye, trace, plies_done);
+    }
+    else
+        k_playout<N, T><<<blocks_for(G, T), kThreads, 0, st>>>(states, G, plies, max_step, seed, game_id0, no_eye, trace, plies_done);
 }
 
 }  // namespace tg
@@ -360,7 +413,11 @@ int tg_env_score(int n, const void* states, int64_t G, float komi, float* score,
 
 /* the layout tg_env_playout runs for (n, G, tile): TG_TILE_ROWS or lanes per game */
 int tg_env_playout_tile(int n, int64_t G, int tile) {
-    if (tile == 0) return (n == 19) ? TG_TILE_ROWS : (G < 12288 ? 16 : 1);
+    if (tile == 0) return (n == 19) ? TG_TILE_ROWS : (G < 12288 ? (8 | TG_TILE_UNIFORM) : 1);
+    if (tile > 0 && (tile & TG_TILE_UNIFORM)) {
+        const int t = tile & (TG_TILE_UNIFORM - 1);
+        return (t == 16 || t == 8 || t == 4) ? tile : pick_tile(0, G);
+    }
     return tile == TG_TILE_ROWS ? tile : pick_tile(tile, G);
 }
 
@@ -369,7 +426,7 @@ int tg_env_playout(int n, void* states, int64_t G, int plies, int max_step, uint
     if (!states || G <= 0 || plies < 0) return set_err(-1, "tg_env_playout");
     cudaStream_t st = (cudaStream_t)stream;
     // tile == 0, measured on B200 (profiles/r01_playout_layouts.txt): 19x19 -> rows layout at every batch size (up to 3.6x over
-    // the bitboard tiles); 9x9 -> half-warp tiles while the batch cannot fill the SMs, one thread per game beyond
+    // the bitboard tiles); 9x9 -> four games per warp in lock step while the batch cannot fill the SMs, one thread per game beyond
     tile = tg_env_playout_tile(n, G, tile);
     if (tile == TG_TILE_ROWS) {
         if (n == 9) launch_playout_rows<9>(st, (uint4*)states, G, plies, max_step, seed, game_id0, no_eye, trace_actions, plies_done);
@@ -377,7 +434,6 @@ int tg_env_playout(int n, void* states, int64_t G, int plies, int max_step, uint
         else return set_err(-1, "board size must be 9 or 19");
         return set_err((int)cudaGetLastError(), "tg_env_playout");
     }
-    tile = pick_tile(tile, G);
     if (n == 9) { TG_DISPATCH_T6(9, tile, launch_playout, st, (uint4*)states, G, plies, max_step, seed, game_id0, no_eye, trace_actions, plies_done) }
     else if (n == 19) { TG_DISPATCH_T6(19, tile, launch_playout, st, (uint4*)states, G, plies, max_step, seed, game_id0, no_eye, trace_actions, plies_done) }
     else return set_err(-1, "board size must be 9 or 19");

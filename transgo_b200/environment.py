@@ -191,7 +191,7 @@ class BatchedGoEnv:
     def playout_layout(self):
         """Name of the kernel ``playout`` launches for this batch: lanes per game, or 'rows' (one board row per lane)."""
         t = self.lib.tg_env_playout_tile(self.n, self.G, self.tile)
-        return "rows" if t < 0 else str(t)
+        return "rows" if t < 0 else ("%d lanes per game, %d games per warp in lock step" % (t & 63, 32 // (t & 63)) if t & 64 else str(t))
 
     # ---- helpers (format conversion only)
     def unpack_legal(self, legal=None):
