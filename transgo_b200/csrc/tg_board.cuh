@@ -501,9 +501,15 @@ __device__ __forceinline__ void analyse_seeded(const BB<N>& black, const BB<N>& 
     // seeds whose west / north neighbour is a same-colour seed belong to that seed's group: drop them
     sb = andn(andn(sb, shift_e(sb)), shift_s(sb));
     sw = andn(andn(sw, shift_e(sw)), shift_s(sw));
-    const int nb = count(sb), total = nb + count(sw);
-    for (int base = 0; uniform_cond<T, WU>(base < total); base += T) {   // tile-uniform (WU: warp-uniform) trip count
-        const int j = base + Tile<T>::lane();
+    // Each pass gives the first T seeds to the T lanes.  When seeds are left over, everything the floods of this pass reached
+    // is struck from them first: a group usually owns several seeds (every "north-west corner" of its shape is one), so the
+    // second pass rarely has much to do.
+    bool any_pass = false;
+    while (true) {
+        const int nb = count(sb), total = nb + count(sw);
+        if (!uniform_cond<T, WU>(total > 0)) break;                 // tile- (WU: warp-) uniform
+        any_pass = true;
+        const int j = Tile<T>::lane();
         const bool valid = j < total;
         const bool is_w = j >= nb;
         BB<N> g = bb_nth_bit<N>(is_w ? sw : sb, valid ? (is_w ? j - nb : j) : -1);
@@ -515,9 +521,12 @@ __device__ __forceinline__ void analyse_seeded(const BB<N>& black, const BB<N>& 
             const typename G::word_t m1 = is1 ? g.w[i] : 0;
             p1b.w[i] |= is_w ? 0 : m1; p1w.w[i] |= is_w ? m1 : 0;
         }
+        if (!uniform_cond<T, WU>(total > T)) break;
+        const BB<N> covered = WU ? tile_or_converged<N, T>(g) : tile_or<N, T>(g);     // includes the T seeds just used
+        sb = andn(sb, covered); sw = andn(sw, covered);
     }
     if (WU) { l1b = l1b | tile_or_converged<N, T>(p1b); l1w = l1w | tile_or_converged<N, T>(p1w); }
-    else if (total > 0) { l1b = l1b | tile_or<N, T>(p1b); l1w = l1w | tile_or<N, T>(p1w); }
+    else if (any_pass) { l1b = l1b | tile_or<N, T>(p1b); l1w = l1w | tile_or<N, T>(p1w); }
 }
 
 // Empty points with no empty neighbour: the only points whose legality depends on group liberties.
