@@ -477,8 +477,8 @@ __device__ __forceinline__ void analyse_seeded(const BB<N>& black, const BB<N>& 
     using G = Geo<N>;
     const BB<N> empty = bb_not(black | white);
     BB<N> sb = seeds & black, sw = seeds & white;
-    BB<N> p1b = bb_zero<N>(), p1w = p1b;
     if (T == 1) {
+        BB<N> p1b = bb_zero<N>(), p1w = p1b;
         // one thread: take the lowest remaining seed, flood its group, strike the flooded stones from the seed sets
         while (any(sb | sw)) {
             const bool is_w = !any(sb);
@@ -503,7 +503,9 @@ __device__ __forceinline__ void analyse_seeded(const BB<N>& black, const BB<N>& 
     sw = andn(andn(sw, shift_e(sw)), shift_s(sw));
     // Each pass gives the first T seeds to the T lanes.  When seeds are left over, everything the floods of this pass reached
     // is struck from them first: a group usually owns several seeds (every "north-west corner" of its shape is one), so the
-    // second pass rarely has much to do.
+    // second pass rarely has much to do.  Atari groups of both colours are collected in ONE set (a group has one colour, so
+    // the set is split by colour after the reduction: half the reduction traffic).
+    BB<N> p1 = bb_zero<N>();
     bool any_pass = false;
     while (true) {
         const int nb = count(sb), total = nb + count(sw);
@@ -517,16 +519,15 @@ __device__ __forceinline__ void analyse_seeded(const BB<N>& black, const BB<N>& 
         int c; bool complete;
         flood_group<N, T, WU>(g, col, empty, 2, c, complete);
         const bool is1 = valid && complete && c == 1;
-        TG_FOR_W {
-            const typename G::word_t m1 = is1 ? g.w[i] : 0;
-            p1b.w[i] |= is_w ? 0 : m1; p1w.w[i] |= is_w ? m1 : 0;
-        }
+        TG_FOR_W p1.w[i] |= is1 ? g.w[i] : 0;
         if (!uniform_cond<T, WU>(total > T)) break;
         const BB<N> covered = WU ? tile_or_converged<N, T>(g) : tile_or<N, T>(g);     // includes the T seeds just used
         sb = andn(sb, covered); sw = andn(sw, covered);
     }
-    if (WU) { l1b = l1b | tile_or_converged<N, T>(p1b); l1w = l1w | tile_or_converged<N, T>(p1w); }
-    else if (any_pass) { l1b = l1b | tile_or<N, T>(p1b); l1w = l1w | tile_or<N, T>(p1w); }
+    if (WU || any_pass) {
+        const BB<N> all1 = WU ? tile_or_converged<N, T>(p1) : tile_or<N, T>(p1);
+        l1b = l1b | (all1 & black); l1w = l1w | (all1 & white);
+    }
 }
 
 // Empty points with no empty neighbour: the only points whose legality depends on group liberties.
