@@ -375,6 +375,15 @@ template <int N, int T, bool WU = false> __device__ __forceinline__ BB<N> flood(
 // callers only distinguish 1 / 2 / >=3 liberties (board_feature.cc:17-41, board.cc:130-158), and big groups reach the
 // limit in the first step.  On return `complete` tells whether g is the whole group (then libs is exact); otherwise
 // libs >= lim.  The loop is tile-uniform: it runs until no lane still needs another step.
+// Eastward fill of the seeds g (a subset of mk) to the end of their rows' runs in mk: adding the seeds to the mask lets the
+// carry ripple up each run of ones; the always-zero guard bit between rows stops it.
+template <int N> __device__ __forceinline__ BB<N> efill(const BB<N>& g, const BB<N>& mk) {
+    using word_t = typename Geo<N>::word_t;
+    BB<N> r;
+    TG_FOR_W { const word_t t = mk.w[i] + g.w[i]; r.w[i] = ((t ^ mk.w[i]) & mk.w[i]) | g.w[i]; }
+    return r;
+}
+
 template <int N, int T, bool WU = false>
 __device__ __forceinline__ void flood_group(BB<N>& g, const BB<N>& col, const BB<N>& empty, int lim, int& libs, bool& complete) {
     bool ch = any(g);
@@ -382,7 +391,9 @@ __device__ __forceinline__ void flood_group(BB<N>& g, const BB<N>& col, const BB
     complete = true;
     while (true) {
         const BB<N> nb = nbrs(g);
-        const BB<N> n1 = (g | nb) & col;
+        // one step in every direction, then east to the end of each row's run: floods start at a group's north-west corner
+        // (its leader stone), so most of the growth is eastward and southward
+        const BB<N> n1 = efill<N>((g | nb) & col, col);
         libs = count(nb & empty);
         ch = differs(n1, g);
         g = n1;
