@@ -359,12 +359,21 @@ template <int T, bool WU> __device__ __forceinline__ bool uniform_cond(bool p) {
     return p;
 }
 
+// Eastward fill of the seeds g (a subset of mk) to the end of their rows' runs in mk: adding the seeds to the mask lets the
+// carry ripple up each run of ones; the always-zero guard bit between rows stops it.
+template <int N> __device__ __forceinline__ BB<N> efill(const BB<N>& g, const BB<N>& mk) {
+    using word_t = typename Geo<N>::word_t;
+    BB<N> r;
+    TG_FOR_W { const word_t t = mk.w[i] + g.w[i]; r.w[i] = ((t ^ mk.w[i]) & mk.w[i]) | g.w[i]; }
+    return r;
+}
+
 // flood `seed` through `mask` (4-connectivity) until no lane of the tile changes any more.
 template <int N, int T, bool WU = false> __device__ __forceinline__ BB<N> flood(BB<N> g, const BB<N>& mask) {
     bool ch = any(g);
     while (vote_any<T, WU>(ch)) {
-        BB<N> n1 = (g | nbrs(g)) & mask;
-        BB<N> n2 = (n1 | nbrs(n1)) & mask;
+        BB<N> n1 = efill<N>((g | nbrs(g)) & mask, mask);
+        BB<N> n2 = efill<N>((n1 | nbrs(n1)) & mask, mask);
         ch = differs(n2, g);
         g = n2;
     }
@@ -375,15 +384,6 @@ template <int N, int T, bool WU = false> __device__ __forceinline__ BB<N> flood(
 // callers only distinguish 1 / 2 / >=3 liberties (board_feature.cc:17-41, board.cc:130-158), and big groups reach the
 // limit in the first step.  On return `complete` tells whether g is the whole group (then libs is exact); otherwise
 // libs >= lim.  The loop is tile-uniform: it runs until no lane still needs another step.
-// Eastward fill of the seeds g (a subset of mk) to the end of their rows' runs in mk: adding the seeds to the mask lets the
-// carry ripple up each run of ones; the always-zero guard bit between rows stops it.
-template <int N> __device__ __forceinline__ BB<N> efill(const BB<N>& g, const BB<N>& mk) {
-    using word_t = typename Geo<N>::word_t;
-    BB<N> r;
-    TG_FOR_W { const word_t t = mk.w[i] + g.w[i]; r.w[i] = ((t ^ mk.w[i]) & mk.w[i]) | g.w[i]; }
-    return r;
-}
-
 template <int N, int T, bool WU = false>
 __device__ __forceinline__ void flood_group(BB<N>& g, const BB<N>& col, const BB<N>& empty, int lim, int& libs, bool& complete) {
     bool ch = any(g);
