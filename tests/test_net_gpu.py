@@ -112,3 +112,27 @@ def test_search_runs_on_the_fused_evaluator_and_graph_replay_is_stable():
     assert torch.equal(c1, eng2.counts) and torch.equal(a1, a2)          # graph replay == eager, bit for bit
     assert bool((eng.root_n >= 32).all())
     eng.update_with_action(a1)
+
+
+def test_fused_forward_on_19x19_uses_the_library_attention_path():
+    """Boards above 96 points are outside tg_net_attention's range: the fused forward must fall back to batched GEMMs for the
+    attention blocks (not to a wrong answer).  Same tolerances as the 9x9 test."""
+    from transgo_b200.fused_net import FusedTransGoInference
+    from transgo_b200.net import TransGoNetwork
+    torch.manual_seed(5)
+    m = TransGoNetwork(board_size=19).cuda().eval()
+    with torch.no_grad():
+        for mod in m.modules():
+            if isinstance(mod, torch.nn.BatchNorm2d):
+                mod.running_mean.normal_(0, 0.2); mod.running_var.uniform_(0.5, 1.5)
+        for k, p in m.named_parameters():
+            if k.endswith("gamma"):
+                p.fill_(0.3)
+    fused = FusedTransGoInference(m)
+    g = torch.Generator(device="cuda"); g.manual_seed(8)
+    obs = (torch.rand([5, 10, 19, 19], device="cuda", generator=g) > 0.75).float()
+    with torch.no_grad():
+        p0, v0, o0 = m.main_prediction(obs)
+    p1, v1, o1 = fused(obs)
+    assert p1.shape == (5, 362) and o1.shape == (5, 361)
+    assert float((p1 - p0).abs().max()) <= 4e-3 and float((v1 - v0.reshape(-1)).abs().max()) <= 4e-2 and float((o1 - o0).abs().max()) <= 4e-2
