@@ -136,3 +136,24 @@ def test_fused_forward_on_19x19_uses_the_library_attention_path():
     p1, v1, o1 = fused(obs)
     assert p1.shape == (5, 362) and o1.shape == (5, 361)
     assert float((p1 - p0).abs().max()) <= 4e-3 and float((v1 - v0.reshape(-1)).abs().max()) <= 4e-2 and float((o1 - o0).abs().max()) <= 4e-2
+
+
+def test_refresh_updates_weights_inside_captured_graphs():
+    """set_weights + refresh() must reach forwards that were already captured as CUDA graphs (folded tensors are updated in
+    place; gamma is folded into the value projection, so no host scalar is baked into a graph)."""
+    from transgo_b200.fused_net import FusedTransGoInference, make_fused_evaluator
+    m = _perturbed_model(2)
+    ev = make_fused_evaluator(m, cuda_graph=True)
+    g = torch.Generator(device="cuda"); g.manual_seed(11)
+    obs = (torch.rand([64, 10, 9, 9], device="cuda", generator=g) > 0.75).float()
+    p_old = ev(obs)[0].clone()
+    with torch.no_grad():
+        for k, p in m.named_parameters():
+            if k.endswith("gamma"):
+                p.fill_(-0.7)
+            elif "fc_act" in k or "conv_act" in k:
+                p.mul_(1.5)
+    ev.refresh()
+    p_new = ev(obs)[0].clone()                                   # replayed graph, new weights
+    p_ref = FusedTransGoInference(m)(obs)[0]                     # folded from scratch
+    assert torch.equal(p_new, p_ref) and not torch.equal(p_new, p_old)

@@ -38,58 +38,87 @@ def _conv_bn(conv, bn, dtype, pad_in=None):
     return w.to(dtype).contiguous(memory_format=torch.channels_last), b.to(dtype).contiguous()
 
 
+def _copy_tree(old, new):
+    """copy every tensor of the nested structure `new` into the same place of `old` (same layout by construction)"""
+    if isinstance(old, torch.Tensor):
+        old.copy_(new)
+    elif isinstance(old, dict):
+        for k in old:
+            _copy_tree(old[k], new[k])
+    elif isinstance(old, (list, tuple)):
+        for a, b in zip(old, new):
+            _copy_tree(a, b)
+
+
 class FusedTransGoInference:
     def __init__(self, model, dtype=torch.bfloat16):
         self.model, self.dtype = model, dtype
         self.lib = _lib.lib()
+        self._w = None
         self.refresh()
 
     # ------------------------------------------------------------------ weight folding
     def refresh(self):
+        """(Re-)fold the module's current weights.  After the first call the folded tensors are updated IN PLACE, so CUDA
+        graphs that captured this forward (the evaluator's own, or a whole search wave) keep seeing the new weights."""
+        new = self._fold_all()
+        if getattr(self, "_w", None) is None:
+            self._w = new
+            for k, v in new.items():
+                setattr(self, k, v)
+            self._bufs = {}
+        else:
+            _copy_tree(self._w, new)
+
+    def _fold_all(self):
         m, dt = self.model.main_network, self.dtype
         self.n = m.board_width
         self.P = self.n * self.n
-        dev = next(m.parameters()).device
-        self.stem = _conv_bn(m.conv1.conv[0], m.conv1.conv[1], dt, pad_in=16)
-        self.blocks = []
+        self.device = next(m.parameters()).device
+        w = {}
+        w["stem"] = _conv_bn(m.conv1.conv[0], m.conv1.conv[1], dt, pad_in=16)
+        blocks = []
         i = 2
         while hasattr(m, "res_conv%d" % i):
             blk = getattr(m, "res_conv%d" % i)
             if isinstance(blk, _PreActResidual):
                 s1, t1 = _fold(blk.batchnormlize_1)
-                self.blocks.append(("R", dict(s1=s1.contiguous(), t1=t1.contiguous(),
-                                              c1=_conv_bn(blk.conv_1, blk.batchnormlize_2, dt), c2=_conv_bn(blk.conv_2, None, dt),
-                                              c2b=blk.conv_2.bias.detach().float().contiguous())))
+                blocks.append(("R", dict(s1=s1.contiguous(), t1=t1.contiguous(),
+                                         c1=_conv_bn(blk.conv_1, blk.batchnormlize_2, dt), c2=_conv_bn(blk.conv_2, None, dt),
+                                         c2b=blk.conv_2.bias.detach().float().contiguous())))
             else:
-                self.blocks.append(("A", self._attn(blk)))
+                blocks.append(("A", self._attn(blk)))
             i += 1
-        self.end = tuple(t.contiguous() for t in _fold(m.bn_res_end))
-        C, P = m.fc_val_own.in_features // (self.P), self.P
+        w["blocks"] = blocks
+        w["end"] = tuple(t.contiguous() for t in _fold(m.bn_res_end))
+        P = self.P
 
         def nhwc_fc(fc, ch):                   # the reference flattens NCHW (c*P + p); our activations flatten as p*ch + c
-            w = fc.weight.detach().float().view(fc.out_features, ch, P).permute(0, 2, 1).reshape(fc.out_features, P * ch)
-            return w.to(dt).contiguous(), fc.bias.detach().to(dt).contiguous()
-        self.val_conv = _conv_bn(m.conv_val_own.conv[0], m.conv_val_own.conv[1], dt)
-        self.val_conv = (F.pad(self.val_conv[0], (0, 0, 0, 0, 0, 0, 0, 6)).contiguous(memory_format=torch.channels_last),
-                         F.pad(self.val_conv[1], (0, 6)))                      # 2 -> 8 output channels (tensor-core friendly)
-        self.fc_val_own = nhwc_fc(m.fc_val_own, 2)
-        self.fc_val = (m.fc_val.weight.detach().to(dt).contiguous(), m.fc_val.bias.detach().to(dt))
-        self.fc_own = (m.fc_own.weight.detach().to(dt).contiguous(), m.fc_own.bias.detach().to(dt))
-        self.act_attn = self._attn(m.attention_act)
-        self.act_conv = _conv_bn(m.conv_act.conv[0], m.conv_act.conv[1], dt)
-        self.act_conv = (F.pad(self.act_conv[0], (0, 0, 0, 0, 0, 0, 0, 4)).contiguous(memory_format=torch.channels_last),
-                         F.pad(self.act_conv[1], (0, 4)))                      # 4 -> 8 output channels
-        self.fc_act = nhwc_fc(m.fc_act, 4)
-        self.device = dev
-        self._bufs = {}
+            wt = fc.weight.detach().float().view(fc.out_features, ch, P).permute(0, 2, 1).reshape(fc.out_features, P * ch)
+            return wt.to(dt).contiguous(), fc.bias.detach().to(dt).contiguous()
+        vc = _conv_bn(m.conv_val_own.conv[0], m.conv_val_own.conv[1], dt)
+        w["val_conv"] = (F.pad(vc[0], (0, 0, 0, 0, 0, 0, 0, 6)).contiguous(memory_format=torch.channels_last),
+                         F.pad(vc[1], (0, 6)))                                  # 2 -> 8 output channels (tensor-core friendly)
+        w["fc_val_own"] = nhwc_fc(m.fc_val_own, 2)
+        w["fc_val"] = (m.fc_val.weight.detach().to(dt).contiguous(), m.fc_val.bias.detach().to(dt).contiguous())
+        w["fc_own"] = (m.fc_own.weight.detach().to(dt).contiguous(), m.fc_own.bias.detach().to(dt).contiguous())
+        w["act_attn"] = self._attn(m.attention_act)
+        ac = _conv_bn(m.conv_act.conv[0], m.conv_act.conv[1], dt)
+        w["act_conv"] = (F.pad(ac[0], (0, 0, 0, 0, 0, 0, 0, 4)).contiguous(memory_format=torch.channels_last),
+                         F.pad(ac[1], (0, 4)))                                  # 4 -> 8 output channels
+        w["fc_act"] = nhwc_fc(m.fc_act, 4)
+        return w
 
     def _attn(self, blk):
+        """q | k | v as one GEMM.  gamma (model.py:312) is folded into the value projection -- gamma * sum_i att * v_i =
+        sum_i att * (gamma * v_i) -- so that no host scalar is baked into captured graphs."""
         dt = self.dtype
         wq, wk, wv = (c.weight.detach().float().flatten(1) for c in (blk.query_conv, blk.key_conv, blk.value_conv))
         bq, bk, bv = (c.bias.detach().float() for c in (blk.query_conv, blk.key_conv, blk.value_conv))
+        gamma = blk.gamma.detach().float().reshape(1, 1)
         s, t = _fold(blk.bn)
-        return dict(w=torch.cat([wq, wk, wv], 0).to(dt).contiguous(), b=torch.cat([bq, bk, bv], 0).to(dt).contiguous(),
-                    dq=wq.shape[0], gamma=float(blk.gamma.detach().float().item()), s=s.contiguous(), t=t.contiguous())
+        return dict(w=torch.cat([wq, wk, wv * gamma], 0).to(dt).contiguous(), b=torch.cat([bq, bk, bv * gamma.reshape(1)], 0).to(dt).contiguous(),
+                    dq=wq.shape[0], gamma=1.0, s=s.contiguous(), t=t.contiguous())
 
     # ------------------------------------------------------------------ pieces
     def _junction(self, x, y, alpha, scale, shift, want_sum, want_act, ybias=None):
@@ -195,5 +224,5 @@ def make_fused_evaluator(model, dtype=torch.bfloat16, cuda_graph=True):
         g.replay()
         return out[0], out[1]
     evaluator.net = net
-    evaluator.refresh = lambda: (net.refresh(), graphs.clear())
+    evaluator.refresh = net.refresh                       # in place: captured graphs stay valid
     return evaluator
