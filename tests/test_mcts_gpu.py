@@ -301,3 +301,19 @@ def test_evaluate_match_alternates_colours_and_counts_wins(oracle_built):
     assert set(out["winners"].cpu().tolist()) <= {1, 2} and 1 <= out["plies"] <= 13
     w = out["winners"].cpu().numpy(); nb = out["new_plays_black"].cpu().numpy()
     assert out["win"] == int(((w == 1) & nb).sum() + ((w == 2) & ~nb).sum())
+
+
+def test_continuous_selfplay_restarts_finished_slots(oracle_built):
+    """continuous_self_play (self_play.py:902-968) batched: slots restart as their games end; every returned position belongs
+    to a finished game, first positions are empty boards with black to move, labels are +-1 from the mover's view."""
+    from transgo_b200.selfplay import SelfPlayWorker
+    w = SelfPlayWorker(cpu_provider(7, 6), 5, num_simulation=16, max_step=6, tie_seed=1)
+    out = w.play_continuous(min_positions=40, augment=False)
+    n = out["positions"]
+    assert n >= 40 and out["games"] >= 7 and out["obs"].shape == (n, 10, 9, 9) and out["pi"].shape == (n, 82)
+    assert set(out["z"].cpu().tolist()) <= {1.0, -1.0} and bool(((out["pi"].sum(1) - 1).abs() < 1e-5).all())
+    empties = int((out["obs"].reshape(n, -1).abs().sum(1) == 0).sum().item())
+    assert empties == out["games"]                               # exactly one empty-board position per finished game
+    assert n <= 6 * out["games"]                                 # max_step 6: at most 6 positions per game
+    more = w.play_continuous(min_positions=10, augment=True)     # the unfinished games carry on
+    assert more["obs"].shape[0] == 8 * more["positions"] and more["positions"] >= 10

@@ -59,6 +59,60 @@ class SelfPlayWorker:
                     positions=int(valid.sum().item()))
 
 
+def _play_continuous(self, min_positions, augment=True, max_moves=None):
+    """continuous_self_play (self_play.py:902-968) for a batch: every slot plays game after game; a slot whose game ends is
+    labelled (winner z and ownership from the mover's view), handed out and restarted at once, so the search batch stays
+    full while games end at different plies.  Returns at least `min_positions` labelled positions (x8 when `augment`) of
+    FINISHED games; unfinished games stay in their slots for the next call."""
+    s = self.search
+    G, n, A = s.G, self.n, s.A
+    T = int(s.cfg.max_step) + 1
+    dev = s.device
+    if getattr(self, "_hist", None) is None:
+        s.reset_root()
+        self._hist = dict(obs=torch.zeros([G, T, 10, n, n], dtype=torch.float32, device=dev),
+                          pi=torch.zeros([G, T, A], dtype=torch.float32, device=dev),
+                          player=torch.zeros([G, T], dtype=torch.int32, device=dev),
+                          length=torch.zeros([G], dtype=torch.int64, device=dev))
+    h = self._hist
+    rows = torch.arange(G, device=dev)
+    cols = torch.arange(T, device=dev)
+    out = dict(obs=[], pi=[], z=[], own=[])
+    positions = games = moves = 0
+    while positions < min_positions and (max_moves is None or moves < max_moves):
+        actions, pi, obs = s.get_action_probs(is_selfplay=True)
+        t = h["length"].clamp_max(T - 1)
+        h["obs"][rows, t] = obs
+        h["pi"][rows, t] = pi.to(torch.float32)
+        h["player"][rows, t] = 1 + ((s.step - 1) % 2)            # black moves on odd step counts (board.cc:15,19,537)
+        h["length"] += 1
+        fin = s.update_with_action(actions).bool()
+        moves += 1
+        if bool(fin.any()):
+            winner, _, terr = s.outcome(want_territory=True)       # self_play.py:931-937 (roots of finished games are final)
+            valid = (cols[None, :] < h["length"][:, None]) & fin[:, None]
+            gidx = rows[:, None].expand(G, T)[valid]
+            pl = h["player"][valid]
+            out["obs"].append(h["obs"][valid]); out["pi"].append(h["pi"][valid])
+            out["z"].append(torch.where(pl == winner[gidx].to(pl.dtype), 1.0, -1.0))
+            out["own"].append(torch.where((pl == 1)[:, None], terr[gidx], -terr[gidx]))
+            positions += int(valid.sum().item())
+            games += int(fin.sum().item())
+            h["length"][fin] = 0
+            s.reset_games(fin)
+    if out["obs"]:
+        obs, pi, z, own = (torch.cat(out[k]) for k in ("obs", "pi", "z", "own"))
+    else:
+        obs, pi = torch.zeros([0, 10, n, n], device=dev), torch.zeros([0, A], device=dev)
+        z, own = torch.zeros([0], device=dev), torch.zeros([0, n * n], device=dev)
+    if augment and obs.shape[0]:
+        obs, pi, z, own = augment8(obs, pi, z, own, n)
+    return dict(obs=obs, pi=pi, z=z, own=own, positions=positions, games=games, moves=moves)
+
+
+SelfPlayWorker.play_continuous = _play_continuous
+
+
 def selfplay_round(worker, model, ring=None, pacing=None, src=0, dst=0, augment=True, max_moves=None, refresh=None):
     """One round of BASELINE configs[4] on every rank of the process group (or a single process without one):
 
