@@ -27,34 +27,47 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
 
 // x, y, sum_out, act_out: bf16 [rows][C] (NHWC flattened), C % 8 == 0; scale/shift: f32 [C].
 // y == nullptr -> sum = x.  sum_out / act_out may be nullptr.  One thread = 8 channels of one row.
+__device__ __forceinline__ void junction8(const uint4& xq, const uint4& yq, bool has_y, float alpha, const float* __restrict__ ybias,
+                                          const float* __restrict__ scale, const float* __restrict__ shift, int c0,
+                                          uint4* __restrict__ sum_out, uint4* __restrict__ act_out, long long i) {
+    float a[8], b[8];
+    unpack8(xq, a);
+    if (has_y) {
+        unpack8(yq, b);
+        if (ybias) {
+            const float4 b0 = *reinterpret_cast<const float4*>(ybias + c0), b1 = *reinterpret_cast<const float4*>(ybias + c0 + 4);
+            b[0] += b0.x; b[1] += b0.y; b[2] += b0.z; b[3] += b0.w; b[4] += b1.x; b[5] += b1.y; b[6] += b1.z; b[7] += b1.w;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a[k] = a[k] + alpha * b[k];
+    }
+    uint4 s = pack8(a);
+    if (sum_out) sum_out[i] = s;
+    if (act_out) {
+        unpack8(s, a);                      // BatchNorm sees the bf16-rounded sum, like the unfused bf16 model
+        const float4 s0 = *reinterpret_cast<const float4*>(scale + c0), s1 = *reinterpret_cast<const float4*>(scale + c0 + 4);
+        const float4 h0 = *reinterpret_cast<const float4*>(shift + c0), h1 = *reinterpret_cast<const float4*>(shift + c0 + 4);
+        const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+        const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a[k] = fmaxf(a[k] * sc[k] + sh[k], 0.0f);
+        act_out[i] = pack8(a);
+    }
+}
+
+// Two 128-bit vectors per thread and iteration, all four loads issued before the first use (more bytes in flight per thread).
 __global__ void __launch_bounds__(256)
 k_add_bn_relu(const uint4* __restrict__ x, const uint4* __restrict__ y, float alpha, const float* __restrict__ ybias, const float* __restrict__ scale,
               const float* __restrict__ shift, uint4* __restrict__ sum_out, uint4* __restrict__ act_out, long long n_vec, int cvec) {
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_vec; i += (long long)gridDim.x * blockDim.x) {
-        const int c0 = (int)(i % cvec) * 8;
-        float a[8], b[8];
-        unpack8(x[i], a);
-        if (y) {
-            unpack8(y[i], b);
-            if (ybias) {
-                const float4 b0 = *reinterpret_cast<const float4*>(ybias + c0), b1 = *reinterpret_cast<const float4*>(ybias + c0 + 4);
-                b[0] += b0.x; b[1] += b0.y; b[2] += b0.z; b[3] += b0.w; b[4] += b1.x; b[5] += b1.y; b[6] += b1.z; b[7] += b1.w;
-            }
-#pragma unroll
-            for (int k = 0; k < 8; ++k) a[k] = a[k] + alpha * b[k];
-        }
-        uint4 s = pack8(a);
-        if (sum_out) sum_out[i] = s;
-        if (act_out) {
-            unpack8(s, a);                      // BatchNorm sees the bf16-rounded sum, like the unfused bf16 model
-            const float4 s0 = *reinterpret_cast<const float4*>(scale + c0), s1 = *reinterpret_cast<const float4*>(scale + c0 + 4);
-            const float4 h0 = *reinterpret_cast<const float4*>(shift + c0), h1 = *reinterpret_cast<const float4*>(shift + c0 + 4);
-            const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-            const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
-#pragma unroll
-            for (int k = 0; k < 8; ++k) a[k] = fmaxf(a[k] * sc[k] + sh[k], 0.0f);
-            act_out[i] = pack8(a);
-        }
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_vec; i += 2 * stride) {
+        const long long i2 = i + stride;
+        const bool two = i2 < n_vec;
+        const uint4 z = make_uint4(0, 0, 0, 0);
+        const uint4 x0 = x[i], x1 = two ? x[i2] : z;
+        const uint4 y0 = y ? y[i] : z, y1 = (y && two) ? y[i2] : z;
+        junction8(x0, y0, y != nullptr, alpha, ybias, scale, shift, (int)(i % cvec) * 8, sum_out, act_out, i);
+        if (two) junction8(x1, y1, y != nullptr, alpha, ybias, scale, shift, (int)(i2 % cvec) * 8, sum_out, act_out, i2);
     }
 }
 
