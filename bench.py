@@ -465,6 +465,24 @@ def c4_bench(torch, dev, BatchedGoEnv):
     out["mcts_tree_only_sims_per_s"] = n / a.elapsed_time(b) * 1e3
     out["mcts_ms_per_move"] = a.elapsed_time(b)
     out["workspace_gb"] = eng.workspace_bytes / 1e9
+    del eng
+    # the same search with the random-init 19x19 TransGo net (fused bf16 forward; its attention blocks use the library
+    # batched-GEMM path above 96 points), one move
+    from transgo_b200.fused_net import make_fused_evaluator
+    from transgo_b200.net import TransGoNetwork
+    torch.manual_seed(0)
+    net = TransGoNetwork(board_size=19).to(dev).eval()
+    eng = BatchedMCTS(make_fused_evaluator(net, cuda_graph=True), G, board_size=19, num_simulation=sims, tie_seed=1, device=dev)
+    for _ in range(2):
+        eng.run_wave()
+    eng.total_sims()
+    torch.cuda.synchronize()
+    a.record()
+    actions, _, _ = eng.get_action_probs(True)
+    eng.update_with_action(actions)
+    b.record(); torch.cuda.synchronize()
+    out["mcts_e2e_net_bf16_fused_sims_per_s"] = eng.total_sims() / a.elapsed_time(b) * 1e3
+    out["mcts_e2e_ms_per_move"] = a.elapsed_time(b)
     return out
 
 
