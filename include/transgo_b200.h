@@ -215,7 +215,8 @@ int tg_net_add_bn_relu(const void* x, const void* y, float alpha, const float* y
 /* Fused single-head spatial self-attention block of model.py:286-314 in inference, NHWC bf16:
  *   qkv  bf16 [B][P][dq + dq + C]   the three 1x1 convolutions (query | key | value) of x, one GEMM upstream
  *   out  bf16 [B][P][C] = relu((x + gamma * o) * scale[c] + shift[c]),  o[j] = sum_i softmax_j(q_i . k_j) * v_i
- * Supports P <= 96 (9x9), dq == 32, C == 128; returns -1 otherwise (callers then use the library GEMM path). */
+ * Supports P <= 368 (one kernel with scores in registers up to 96 points, a two-pass one above: 19x19), dq == 32, C == 128;
+ * returns -1 otherwise (callers then use the library GEMM path). */
 int tg_net_attention(const void* qkv, const void* x, float gamma, const float* scale, const float* shift, void* out,
                      int64_t B, int P, int dq, int channels, void* stream);
 

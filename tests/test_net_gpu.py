@@ -49,7 +49,7 @@ def test_junction_kernel_matches_fp32_reference(rows, C, with_y, want_sum, want_
         assert torch.equal(a_out, ref_act)
 
 
-@pytest.mark.parametrize("B,P", [(5, 81), (300, 81), (3, 96), (4, 49), (2, 1)])
+@pytest.mark.parametrize("B,P", [(5, 81), (300, 81), (3, 96), (4, 49), (2, 1), (3, 361), (40, 361), (2, 97), (2, 368), (3, 200)])
 def test_attention_kernel_matches_fp32_reference(B, P):
     """tg_net_attention against a plain PyTorch fp32 restatement of model.py:299-314 on the same bf16 inputs.
     Tolerance: |d| <= 2e-2 + 2e-2 * |ref| (probabilities and outputs are rounded to bf16: 8 mantissa bits)."""
@@ -73,7 +73,7 @@ def test_attention_kernel_matches_fp32_reference(B, P):
     err = (out.float() - ref).abs()
     assert bool((err <= 2e-2 + 2e-2 * ref.abs()).all()), float(err.max())
     assert L.tg_net_attention(_lib.ptr(qkv), _lib.ptr(x), gamma, _lib.ptr(scale), _lib.ptr(shift), _lib.ptr(out),
-                              B, 97, dq, C, _lib.stream_ptr()) != 0          # unsupported size is refused, not mangled
+                              B, 369, dq, C, _lib.stream_ptr()) != 0         # unsupported size is refused, not mangled
 
 
 def test_fused_forward_matches_fp32_module():
@@ -114,9 +114,8 @@ def test_search_runs_on_the_fused_evaluator_and_graph_replay_is_stable():
     eng.update_with_action(a1)
 
 
-def test_fused_forward_on_19x19_uses_the_library_attention_path():
-    """Boards above 96 points are outside tg_net_attention's range: the fused forward must fall back to batched GEMMs for the
-    attention blocks (not to a wrong answer).  Same tolerances as the 9x9 test."""
+def test_fused_forward_on_19x19():
+    """19x19 runs the two-pass attention kernel (361 points).  Same tolerances as the 9x9 test."""
     from transgo_b200.fused_net import FusedTransGoInference
     from transgo_b200.net import TransGoNetwork
     torch.manual_seed(5)

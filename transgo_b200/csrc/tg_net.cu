@@ -285,14 +285,192 @@ k_attention(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restri
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// The same block for boards of up to 368 points (19x19 = 361): scores no longer fit in registers, so the CTA (12 warps,
+// one position, q | k | v resident in 160 KB of shared memory) makes two passes over the score matrix and never stores it:
+//   A. warp w owns 16-query tiles and streams all keys: S[i][j] = q_i . k_j by mma.sync, per-row running max / sum kept per
+//      thread over its own columns and merged inside the quad at the end -> m_i and 1 / z_i in shared memory;
+//   B. warp w owns 16-key (= output row) tiles and streams all queries 16 at a time: S^T[j][i] recomputed by mma.sync,
+//      p = exp(s - m_i) / z_i, re-used from the accumulator registers as the A operand of o[j][c] += p^T[j][i] v[i][c]
+//      (B operand: ldmatrix.trans on row-major v), 128 output channels in registers; junction epilogue as above.
+constexpr int kBigP = 368;                      // 23 tiles of 16
+constexpr int kBigTiles = kBigP / 16;
+constexpr int kBigWarps = 12;
+constexpr size_t kBigSmem = (size_t)kBigP * kQS * 2 * 2 + (size_t)kBigP * kVS * 2 + (size_t)kBigP * 4 * 2;
+
+__global__ void __launch_bounds__(kBigWarps * 32, 1)
+k_attention_big(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ x, float gamma,
+                const float* __restrict__ scale, const float* __restrict__ shift, __nv_bfloat16* __restrict__ out, int P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(smem_raw);
+    __nv_bfloat16* sK = sQ + kBigP * kQS;
+    __nv_bfloat16* sV = sK + kBigP * kQS;
+    float* sM = reinterpret_cast<float*>(sV + kBigP * kVS);
+    float* sIZ = sM + kBigP;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, g = lane >> 2, t = lane & 3;
+    const long long b = blockIdx.x;
+    constexpr int ROWQ = (2 * kAttDq + kAttC) / 8, QKC = 2 * kAttDq / 8, VC = kAttC / 8;
+    const uint4* src = reinterpret_cast<const uint4*>(qkv + b * (long long)P * (2 * kAttDq + kAttC));
+    for (int idx = tid; idx < kBigP * QKC; idx += blockDim.x) {
+        const int row = idx / QKC, ch = idx - row * QKC;
+        __nv_bfloat16* dst = ch < kAttDq / 8 ? &sQ[row * kQS + ch * 8] : &sK[row * kQS + (ch - kAttDq / 8) * 8];
+        if (row < P) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" :: "r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src + row * ROWQ + ch));
+        else *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
+    }
+    asm volatile("cp.async.commit_group;\n" ::);
+    for (int idx = tid; idx < kBigP * VC; idx += blockDim.x) {
+        const int row = idx / VC, ch = idx - row * VC;
+        __nv_bfloat16* dst = &sV[row * kVS + ch * 8];
+        if (row < P) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" :: "r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src + row * ROWQ + QKC + ch));
+        else *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);       // rows >= P are zero: they add nothing to o
+    }
+    asm volatile("cp.async.commit_group;\n" ::);
+    asm volatile("cp.async.wait_group 1;\n" ::);
+    __syncthreads();
+    const int mrow = (lane & 7) + ((lane >> 3) & 1) * 8, mcol = (lane >> 4) * 8;   // ldmatrix.x4 lane -> (row, col) of its 8x8 tile
+    const float NEG = -3.0e38f;
+
+    // ---- A. row statistics of S = Q K^T: this warp's query tiles against every key
+    for (int it = wid; it < kBigTiles; it += kBigWarps) {
+        uint32_t qa[kAttDq / 16][4];
+#pragma unroll
+        for (int kc = 0; kc < kAttDq / 16; ++kc) ldsm_x4(qa[kc], &sQ[(it * 16 + mrow) * kQS + kc * 16 + mcol]);
+        float m[2] = {NEG, NEG}, z[2] = {0.0f, 0.0f};                  // rows g and g + 8, over this thread's own columns
+        for (int jt = 0; jt < kBigTiles; ++jt) {
+            float s[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+                for (int kc = 0; kc < kAttDq / 16; ++kc) {
+                    const uint32_t b0 = *reinterpret_cast<const uint32_t*>(&sK[(jt * 16 + nt * 8 + g) * kQS + kc * 16 + 2 * t]);
+                    const uint32_t b1 = *reinterpret_cast<const uint32_t*>(&sK[(jt * 16 + nt * 8 + g) * kQS + kc * 16 + 8 + 2 * t]);
+                    mma_bf16(s[nt], qa[kc], b0, b1);
+                }
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {                               // accumulator rows: c0,c1 -> row g ; c2,c3 -> row g + 8
+                float v[4]; bool ok[4];
+#pragma unroll
+                for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        v[nt * 2 + e] = s[nt][2 * r + e];
+                        ok[nt * 2 + e] = jt * 16 + nt * 8 + 2 * t + e < P;   // keys >= P do not exist
+                    }
+                float tm = NEG;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) tm = ok[q] ? fmaxf(tm, v[q]) : tm;
+                const float nm = fmaxf(m[r], tm);
+                float acc = z[r] * __expf(m[r] - nm);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) acc += ok[q] ? __expf(v[q] - nm) : 0.0f;
+                m[r] = nm; z[r] = acc;
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {                                   // merge the four threads of the quad (they split the columns)
+            float mm = m[r];
+            mm = fmaxf(mm, __shfl_xor_sync(0xffffffffu, mm, 1));
+            mm = fmaxf(mm, __shfl_xor_sync(0xffffffffu, mm, 2));
+            float zz = z[r] * __expf(m[r] - mm);
+            zz += __shfl_xor_sync(0xffffffffu, zz, 1);
+            zz += __shfl_xor_sync(0xffffffffu, zz, 2);
+            if (t == 0) { sM[it * 16 + g + 8 * r] = mm; sIZ[it * 16 + g + 8 * r] = 1.0f / zz; }
+        }
+    }
+    asm volatile("cp.async.wait_group 0;\n" ::);
+    __syncthreads();                                                     // statistics and v visible to every warp
+
+    // ---- B. o[j][c] = sum_i p[i][j] v[i][c] for this warp's output-row tiles
+    const long long rowbase = b * (long long)P;
+    for (int jt = wid; jt < kBigTiles; jt += kBigWarps) {
+        uint32_t ka[kAttDq / 16][4];
+#pragma unroll
+        for (int kc = 0; kc < kAttDq / 16; ++kc) ldsm_x4(ka[kc], &sK[(jt * 16 + mrow) * kQS + kc * 16 + mcol]);
+        const bool r0 = jt * 16 + g < P, r1 = jt * 16 + g + 8 < P;
+        float o[kAttC / 8][4];
+#pragma unroll
+        for (int n = 0; n < kAttC / 8; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.0f;
+        for (int ic = 0; ic < kBigTiles; ++ic) {
+            float s[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+                for (int kc = 0; kc < kAttDq / 16; ++kc) {
+                    const uint32_t b0 = *reinterpret_cast<const uint32_t*>(&sQ[(ic * 16 + nt * 8 + g) * kQS + kc * 16 + 2 * t]);
+                    const uint32_t b1 = *reinterpret_cast<const uint32_t*>(&sQ[(ic * 16 + nt * 8 + g) * kQS + kc * 16 + 8 + 2 * t]);
+                    mma_bf16(s[nt], ka[kc], b0, b1);
+                }
+            uint32_t pa[4];
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) {
+                const int col = ic * 16 + nt * 8 + 2 * t;
+                const float2 mm = *reinterpret_cast<const float2*>(&sM[col]), iz = *reinterpret_cast<const float2*>(&sIZ[col]);
+                const float p0 = r0 ? __expf(s[nt][0] - mm.x) * iz.x : 0.0f, p1 = r0 ? __expf(s[nt][1] - mm.y) * iz.y : 0.0f;
+                const float p2 = r1 ? __expf(s[nt][2] - mm.x) * iz.x : 0.0f, p3 = r1 ? __expf(s[nt][3] - mm.y) * iz.y : 0.0f;
+                pa[2 * nt] = pack_bf16(p0, p1);
+                pa[2 * nt + 1] = pack_bf16(p2, p3);
+            }
+#pragma unroll
+            for (int ct = 0; ct < kAttC / 16; ++ct) {
+                uint32_t v[4];
+                ldsm_x4_trans(v, &sV[(ic * 16 + mrow) * kVS + ct * 16 + mcol]);
+                mma_bf16(o[2 * ct], pa, v[0], v[1]);
+                mma_bf16(o[2 * ct + 1], pa, v[2], v[3]);
+            }
+        }
+#pragma unroll
+        for (int ct = 0; ct < kAttC / 16; ++ct) {
+            uint32_t a[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) a[k] = pack_bf16(o[2 * ct + (k >> 1)][2 * (k & 1)], o[2 * ct + (k >> 1)][2 * (k & 1) + 1]);
+            {
+                const bool odd = t & 1, hi = t & 2;
+                const uint32_t x0 = __shfl_xor_sync(0xffffffffu, odd ? a[0] : a[1], 1), x1 = __shfl_xor_sync(0xffffffffu, odd ? a[2] : a[3], 1);
+                if (odd) { a[0] = x0; a[2] = x1; } else { a[1] = x0; a[3] = x1; }
+                const uint32_t q0 = __shfl_xor_sync(0xffffffffu, hi ? a[0] : a[2], 2), q1 = __shfl_xor_sync(0xffffffffu, hi ? a[1] : a[3], 2);
+                if (hi) { a[0] = q0; a[1] = q1; } else { a[2] = q0; a[3] = q1; }
+            }
+            const int j = jt * 16 + g + (t & 1) * 8, c = ct * 16 + (t >> 1) * 8;
+            if (j < P) {
+                const long long off = (rowbase + j) * kAttC + c;
+                const uint4 xq = *reinterpret_cast<const uint4*>(x + off);
+                const float4 sc0 = *reinterpret_cast<const float4*>(scale + c), sc1 = *reinterpret_cast<const float4*>(scale + c + 4);
+                const float4 sh0 = *reinterpret_cast<const float4*>(shift + c), sh1 = *reinterpret_cast<const float4*>(shift + c + 4);
+                const float scv[8] = {sc0.x, sc0.y, sc0.z, sc0.w, sc1.x, sc1.y, sc1.z, sc1.w};
+                const float shv[8] = {sh0.x, sh0.y, sh0.z, sh0.w, sh1.x, sh1.y, sh1.z, sh1.w};
+                const uint32_t xw[4] = {xq.x, xq.y, xq.z, xq.w};
+                uint32_t ow[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float2 xv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xw[k]));
+                    const float2 ov = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&a[k]));
+                    const float s0 = fmaf(gamma, ov.x, xv.x), s1 = fmaf(gamma, ov.y, xv.y);
+                    ow[k] = pack_bf16(fmaxf(fmaf(s0, scv[2 * k], shv[2 * k]), 0.0f), fmaxf(fmaf(s1, scv[2 * k + 1], shv[2 * k + 1]), 0.0f));
+                }
+                *reinterpret_cast<uint4*>(out + off) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+            }
+        }
+    }
+}
+
 }  // namespace tg
 
 extern "C" int tg_net_attention(const void* qkv, const void* x, float gamma, const float* scale, const float* shift, void* out,
                                 int64_t B, int P, int dq, int channels, void* stream) {
     using namespace tg;
-    if (!qkv || !x || !scale || !shift || !out || B <= 0 || P <= 0 || P > kAttP || dq != kAttDq || channels != kAttC)
-        return set_err(-1, "tg_net_attention (supports P <= 96, 32 query channels, 128 value channels)");
-    k_attention<<<(unsigned)B, kAttWarps * 32, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)qkv, (const __nv_bfloat16*)x, gamma, scale,
-                                                                           shift, (__nv_bfloat16*)out, P);
+    if (!qkv || !x || !scale || !shift || !out || B <= 0 || P <= 0 || P > kBigP || dq != kAttDq || channels != kAttC)
+        return set_err(-1, "tg_net_attention (supports P <= 368, 32 query channels, 128 value channels)");
+    if (P <= kAttP) {
+        k_attention<<<(unsigned)B, kAttWarps * 32, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)qkv, (const __nv_bfloat16*)x, gamma, scale,
+                                                                               shift, (__nv_bfloat16*)out, P);
+    } else {
+        static bool attr_done = false;
+        if (!attr_done) {
+            cudaFuncSetAttribute(k_attention_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBigSmem);
+            attr_done = true;
+        }
+        k_attention_big<<<(unsigned)B, kBigWarps * 32, kBigSmem, (cudaStream_t)stream>>>((const __nv_bfloat16*)qkv, (const __nv_bfloat16*)x, gamma,
+                                                                                          scale, shift, (__nv_bfloat16*)out, P);
+    }
     return set_err((int)cudaGetLastError(), "tg_net_attention");
 }

@@ -6,7 +6,8 @@ with bias+ReLU epilogue, cuBLAS GEMMs for the 1x1 convolutions / attention / hea
  - into a per-channel scale/shift otherwise, applied by ONE hand-written kernel per residual junction
    (tg_net_add_bn_relu: residual add / gamma*attention + x, next BatchNorm, ReLU in a single NHWC bf16 pass);
  - the four self-attention blocks (scores, softmax, weighted sum, junction) run as ONE hand-written kernel per block
-   (tg_net_attention, mma.sync bf16) fed by a single q|k|v GEMM; boards above 96 points use library batched GEMMs.
+   (tg_net_attention, mma.sync bf16: scores in registers up to 96 points, a two-pass variant up to 368) fed by a single
+   q|k|v GEMM; larger boards use library batched GEMMs.
 Activations are NHWC bf16 end to end, so the attention blocks read them as [B, P, C] views without layout copies.
 
 ``FusedTransGoInference(model)`` snapshots a ``TransGoNetwork``; ``refresh()`` re-folds after ``set_weights``.
@@ -138,7 +139,7 @@ class FusedTransGoInference:
         x2 = x.permute(0, 2, 3, 1).reshape(B, self.P, C)                       # free view of channels_last memory
         qkv = F.linear(x2, p["w"], p["b"])
         dq = p["dq"]
-        if self.P <= 96 and dq == 32 and C == 128 and self.dtype == torch.bfloat16:
+        if self.P <= 368 and dq == 32 and C == 128 and self.dtype == torch.bfloat16:
             # scores, softmax, att^T . v and the junction in ONE hand-written kernel (csrc/tg_net.cu: k_attention)
             act = torch.empty_like(x)
             _lib.check(self.lib.tg_net_attention(_lib.ptr(qkv), _lib.ptr(x), p["gamma"], _lib.ptr(p["s"]), _lib.ptr(p["t"]),
