@@ -109,6 +109,9 @@ constexpr int kAttWarps = kAttP / 16;
 constexpr int kQS = kAttDq + 8;    // smem row strides (bf16), padded against bank conflicts
 constexpr int kVS = kAttC + 8;
 constexpr int kAS = kAttP + 8;
+constexpr float kLog2e = 1.4426950408889634f;
+// exp(x) = ex2(x * log2 e): one FFMA + one MUFU
+__device__ __forceinline__ float ex2_fast(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
 __device__ __forceinline__ void mma_bf16(float* d, const uint32_t* a, uint32_t b0, uint32_t b1) {
     asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
@@ -214,8 +217,8 @@ k_attention(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restri
             float z = 0.0f;
 #pragma unroll
             for (int mt = 0; mt < kAttWarps; ++mt) {
-                const float e0 = (mt * 16 + g < P) ? __expf(s[mt][nt][e] - m) : 0.0f;
-                const float e1 = (mt * 16 + g + 8 < P) ? __expf(s[mt][nt][2 + e] - m) : 0.0f;
+                const float e0 = (mt * 16 + g < P) ? ex2_fast(fmaf(s[mt][nt][e], kLog2e, -m * kLog2e)) : 0.0f;
+                const float e1 = (mt * 16 + g + 8 < P) ? ex2_fast(fmaf(s[mt][nt][2 + e], kLog2e, -m * kLog2e)) : 0.0f;
                 s[mt][nt][e] = e0; s[mt][nt][2 + e] = e1;
                 z += e0 + e1;
             }
@@ -296,6 +299,7 @@ k_attention(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restri
 constexpr int kBigP = 368;                      // 23 tiles of 16
 constexpr int kBigTiles = kBigP / 16;
 constexpr int kBigWarps = 12;
+
 constexpr size_t kBigSmem = (size_t)kBigP * kQS * 2 * 2 + (size_t)kBigP * kVS * 2 + (size_t)kBigP * 4 * 2;
 
 __global__ void __launch_bounds__(kBigWarps * 32, 1)
@@ -346,23 +350,21 @@ k_attention_big(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __re
                     const uint32_t b1 = *reinterpret_cast<const uint32_t*>(&sK[(jt * 16 + nt * 8 + g) * kQS + kc * 16 + 8 + 2 * t]);
                     mma_bf16(s[nt], qa[kc], b0, b1);
                 }
+            const bool full = jt * 16 + 16 <= P;                         // warp-uniform: only the last key tile is ragged
 #pragma unroll
             for (int r = 0; r < 2; ++r) {                               // accumulator rows: c0,c1 -> row g ; c2,c3 -> row g + 8
-                float v[4]; bool ok[4];
+                float v[4];                                             // scores in units of log2(e): exp(x) = exp2(x * log2 e)
 #pragma unroll
                 for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
-                        v[nt * 2 + e] = s[nt][2 * r + e];
-                        ok[nt * 2 + e] = jt * 16 + nt * 8 + 2 * t + e < P;   // keys >= P do not exist
+                        const bool ok = full || jt * 16 + nt * 8 + 2 * t + e < P;    // keys >= P do not exist
+                        v[nt * 2 + e] = ok ? s[nt][2 * r + e] * kLog2e : NEG;
                     }
-                float tm = NEG;
+                const float nm = fmaxf(fmaxf(m[r], fmaxf(v[0], v[1])), fmaxf(v[2], v[3]));
+                float acc = z[r] * ex2_fast(m[r] - nm);
 #pragma unroll
-                for (int q = 0; q < 4; ++q) tm = ok[q] ? fmaxf(tm, v[q]) : tm;
-                const float nm = fmaxf(m[r], tm);
-                float acc = z[r] * __expf(m[r] - nm);
-#pragma unroll
-                for (int q = 0; q < 4; ++q) acc += ok[q] ? __expf(v[q] - nm) : 0.0f;
+                for (int q = 0; q < 4; ++q) acc += ex2_fast(v[q] - nm);    // ex2_fast(NEG - nm) == 0
                 m[r] = nm; z[r] = acc;
             }
         }
@@ -371,10 +373,10 @@ k_attention_big(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __re
             float mm = m[r];
             mm = fmaxf(mm, __shfl_xor_sync(0xffffffffu, mm, 1));
             mm = fmaxf(mm, __shfl_xor_sync(0xffffffffu, mm, 2));
-            float zz = z[r] * __expf(m[r] - mm);
+            float zz = z[r] * ex2_fast(m[r] - mm);
             zz += __shfl_xor_sync(0xffffffffu, zz, 1);
             zz += __shfl_xor_sync(0xffffffffu, zz, 2);
-            if (t == 0) { sM[it * 16 + g + 8 * r] = mm; sIZ[it * 16 + g + 8 * r] = 1.0f / zz; }
+            if (t == 0) { sM[it * 16 + g + 8 * r] = mm; sIZ[it * 16 + g + 8 * r] = 1.0f / zz; }   // mm in log2 units
         }
     }
     asm volatile("cp.async.wait_group 0;\n" ::);
@@ -405,8 +407,8 @@ k_attention_big(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __re
             for (int nt = 0; nt < 2; ++nt) {
                 const int col = ic * 16 + nt * 8 + 2 * t;
                 const float2 mm = *reinterpret_cast<const float2*>(&sM[col]), iz = *reinterpret_cast<const float2*>(&sIZ[col]);
-                const float p0 = r0 ? __expf(s[nt][0] - mm.x) * iz.x : 0.0f, p1 = r0 ? __expf(s[nt][1] - mm.y) * iz.y : 0.0f;
-                const float p2 = r1 ? __expf(s[nt][2] - mm.x) * iz.x : 0.0f, p3 = r1 ? __expf(s[nt][3] - mm.y) * iz.y : 0.0f;
+                const float p0 = r0 ? ex2_fast(fmaf(s[nt][0], kLog2e, -mm.x)) * iz.x : 0.0f, p1 = r0 ? ex2_fast(fmaf(s[nt][1], kLog2e, -mm.y)) * iz.y : 0.0f;
+                const float p2 = r1 ? ex2_fast(fmaf(s[nt][2], kLog2e, -mm.x)) * iz.x : 0.0f, p3 = r1 ? ex2_fast(fmaf(s[nt][3], kLog2e, -mm.y)) * iz.y : 0.0f;
                 pa[2 * nt] = pack_bf16(p0, p1);
                 pa[2 * nt + 1] = pack_bf16(p2, p3);
             }
