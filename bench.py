@@ -555,6 +555,8 @@ def mcts_bench(torch, dist, dev, rank, world, args):
     torch.manual_seed(0)
     net = TransGoNetwork(board_size=9).to(dev).eval()
     from transgo_b200.fused_net import make_fused_evaluator
+    if rank == 0 and not args.quick:
+        out["c1_single_game_facade"] = c1_facade(torch, net)
     for name, dtype in (("e2e_net_bf16_fused", "fused"), ("e2e_net_bf16", torch.bfloat16), ("e2e_net_fp32", None)):
         if args.quick and dtype is None:
             continue
@@ -572,6 +574,31 @@ def mcts_bench(torch, dist, dev, rank, world, args):
                      "net_tflops": rate * 0.457e9 / 1e12}
         del eng
     return out
+
+
+def c1_facade(torch, net):
+    """BASELINE configs[0] through the drop-in facade: ONE game, the reference's default search (configure.py:25-33: 210
+    simulations, 4 leaves per wave), the scalar WP_MCTS / GoEnv surface of self_play.py:906-926, fp32 net in eager mode --
+    what a user gets by only swapping the two imports.  Three moves after one warm-up move."""
+    from transgo_b200.environment import GoEnv
+    from transgo_b200.mcts import WP_MCTS
+
+    class Cfg:
+        board_size, num_simulation, c_puct1, c_puct2, wu_loss, parallel_readouts = 9, 210, 3, 0.05, 2, 4
+    agent = WP_MCTS(Cfg(), GoEnv(Cfg()), net, None)
+    a, _, _ = agent.get_action_probs(True)
+    agent.update_with_action(a)
+    agent._b.total_sims()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        a, _, _ = agent.get_action_probs(True)
+        agent.update_with_action(a)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    n = agent._b.total_sims()
+    return {"value": n / dt, "unit": "MCTS sims/s", "moves": 3, "sims": n, "wall_s": dt,
+            "what": "one game, 210 simulations per move, WP_MCTS facade + fp32 eager net on the GPU (host wall clock)"}
 
 
 # ------------------------------------------------------------------------------------------------ reference arm
