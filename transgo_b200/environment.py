@@ -117,6 +117,11 @@ class BatchedGoEnv:
 
     ``step`` keeps the reference semantics per game (go_env.cc:51-80): terminated games stay put and report
     done, illegal actions leave the state unchanged and report accepted = 0.
+
+    ``tile`` = lanes cooperating on one game: 0 lets the library choose from (board, G) by measurement (see
+    ``playout_layout``); 32 / 16 / 8 / 4 / 2 / 1 force a bitboard tile; ``n | 64`` (n in 16, 8, 4) runs the tiles that share
+    a warp in lock step; -1 is the row-per-lane layout.  The last two only exist for ``playout``; the other kernels then
+    fall back to the library's choice.  Every layout produces identical results (tests/test_env_gpu.py).
     """
 
     def __init__(self, num_games, board_size=9, max_step=None, komi=7.5, device="cuda", tile=0):
