@@ -33,6 +33,7 @@ struct View {
     double* root_prior64;   // [G][A]
     uint4* hot;             // [2][G][EC]
     uint2* cold;            // [2][G][EC]
+    uint32_t* kid;          // [2][G][EC]  edge base | edge count << 22 of the edge's child node (valid when the child exists)
     uint4* nodes;           // [2][G][NC][SQ+1]
     int* paths;             // [G][R][MAXD]
     int* path_len;          // [G][R]
@@ -60,6 +61,7 @@ static View make_view(const TgMctsConfig* c, void* ws) {
     v.root_prior64 = (double*)take(G * GG::A * 8);
     v.hot = (uint4*)take(2 * G * (size_t)v.EC * 16);
     v.cold = (uint2*)take(2 * G * (size_t)v.EC * 8);
+    v.kid = (uint32_t*)take(2 * G * (size_t)v.EC * 4);
     v.nodes = (uint4*)take(2 * G * (size_t)v.NC * (GG::SQ + 1) * 16);
     v.paths = (int*)take(G * R * (size_t)v.MAXD * 4);
     v.path_len = (int*)take(G * R * 4);
@@ -73,6 +75,8 @@ static View make_view(const TgMctsConfig* c, void* ws) {
 
 template <int N> __device__ __forceinline__ uint4* hot_of(const View& v, int buf, int g) { return v.hot + ((size_t)buf * v.G + g) * v.EC; }
 template <int N> __device__ __forceinline__ uint2* cold_of(const View& v, int buf, int g) { return v.cold + ((size_t)buf * v.G + g) * v.EC; }
+template <int N> __device__ __forceinline__ uint32_t* kid_of(const View& v, int buf, int g) { return v.kid + ((size_t)buf * v.G + g) * v.EC; }
+__device__ __forceinline__ uint32_t pack_kid(int eb, int K) { return (uint32_t)eb | ((uint32_t)K << 22); }
 template <int N> __device__ __forceinline__ uint4* nodes_of(const View& v, int buf, int g) { return v.nodes + ((size_t)buf * v.G + g) * v.NC * (Geo<N>::SQ + 1); }
 
 __device__ __forceinline__ double warp_max(double x) {
@@ -150,7 +154,9 @@ __global__ void __launch_bounds__(kThreads) k_select(View v) {
     const int buf = h[H_BUF];
     uint4* hot = hot_of<N>(v, buf, g);
     uint2* cold = cold_of<N>(v, buf, g);
+    const uint32_t* kid = kid_of<N>(v, buf, g);
     const uint4* nodes = nodes_of<N>(v, buf, g);
+    const uint32_t root_kid = pack_kid((int)nodes[GG::SQ].x, (int)nodes[GG::SQ].y);     // the root's edges: read once per wave
     const double* p64 = v.root_prior64 + (size_t)g * GG::A;
     const bool noisy = (flags & TG_MCTS_NOISY) != 0;
     const float c1f = (float)v.c1, c2f = (float)v.c2;
@@ -161,21 +167,22 @@ __global__ void __launch_bounds__(kThreads) k_select(View v) {
         int* path = v.paths + ((size_t)g * v.R + npaths) * v.MAXD;
         int node = 0, depth = 0;
         int Np = h[H_ROOTN], onsp = h[H_ROOTONS];
-        uint32_t pk_sel = 0;
+        uint32_t pk_sel = 0, kid_cur = root_kid;
         while (true) {                                                                // :623-627
-            const uint4 info = nodes[(size_t)node * (GG::SQ + 1) + GG::SQ];
-            const int eb = (int)info.x, K = (int)info.y;
+            // where the node's edges live came with the edge that led here: no dependent load of the node record
+            const int eb = (int)(kid_cur & 0x3fffffu), K = (int)(kid_cur >> 22);
             st_fan += K;
             const double sq = __dsqrt_rn((double)(Np + onsp));
-            double sc[MAXR]; uint32_t pk[MAXR], ch[MAXR];            // ch: child node of each scanned edge (cold record), loaded
+            double sc[MAXR]; uint32_t pk[MAXR], ch[MAXR], kd[MAXR];            // ch: child node of each scanned edge (cold record), loaded
             double best = -1.0e300;                                  // with the hot record so that the descent needs no second trip
 #pragma unroll
             for (int r = 0; r < MAXR; ++r) {
                 const int k = lane + 32 * r;
-                sc[r] = -1.0e300; pk[r] = 0; ch[r] = 0xffffffffu;
+                sc[r] = -1.0e300; pk[r] = 0; ch[r] = 0xffffffffu; kd[r] = 0;
                 if (k < K) {
                     const uint4 q = hot[eb + k];
                     ch[r] = cold[eb + k].y;
+                    kd[r] = kid[eb + k];
                     const float prior = __uint_as_float(q.x), W = __uint_as_float(q.y), var = __uint_as_float(q.z);
                     const int nc = pk_n(q.w), oc = pk_ons(q.w);
                     // prior_score = c1 * prior * sqrt(Np + ons_p) / (Nc + ons_c + 1)          (:718-719)
@@ -205,7 +212,7 @@ __global__ void __launch_bounds__(kThreads) k_select(View v) {
                 tie += 1;
             }
             int ksel = -1;
-            uint32_t ch_sel = 0xffffffffu;
+            uint32_t ch_sel = 0xffffffffu, kd_sel = 0;
 #pragma unroll
             for (int r = 0; r < MAXR; ++r) {
                 const int c = __popc(bal[r]);
@@ -214,6 +221,7 @@ __global__ void __launch_bounds__(kThreads) k_select(View v) {
                     ksel = src + 32 * r;
                     pk_sel = __shfl_sync(0xffffffffu, pk[r], src);
                     ch_sel = __shfl_sync(0xffffffffu, ch[r], src);
+                    kd_sel = __shfl_sync(0xffffffffu, kd[r], src);
                 } else if (ksel < 0) j -= c;
             }
             const int e = eb + ksel;
@@ -222,7 +230,7 @@ __global__ void __launch_bounds__(kThreads) k_select(View v) {
             depth += 1;
             const int child = (int)ch_sel;
             if (child < 0) break;
-            Np = pk_n(pk_sel); onsp = pk_ons(pk_sel); node = child;
+            Np = pk_n(pk_sel); onsp = pk_ons(pk_sel); node = child; kid_cur = kd_sel;
         }
         if (err) break;
         st_desc += 1; st_depth += depth;
@@ -341,6 +349,7 @@ __global__ void __launch_bounds__(kThreads) k_expand(View v, const float* __rest
     const int buf = h[H_BUF];
     uint4* hot = hot_of<N>(v, buf, g);
     uint2* cold = cold_of<N>(v, buf, g);
+    uint32_t* kid = kid_of<N>(v, buf, g);
     uint4* nodes = nodes_of<N>(v, buf, g);
     unsigned err = 0;
     int sims = 0;
@@ -372,6 +381,7 @@ __global__ void __launch_bounds__(kThreads) k_expand(View v, const float* __rest
         if (lane == 0) {
             rec[GG::SQ] = make_uint4((uint32_t)eb, (uint32_t)K, 0u, 0u);
             cold[e].y = (uint32_t)node;
+            kid[e] = pack_kid(eb, K);
         }
         nn = node + 1; ne = eb + K;
         __syncwarp();
@@ -553,8 +563,9 @@ __global__ void __launch_bounds__(kThreads) k_advance(View v, const int16_t* __r
         const int dbuf = 1 - buf;
         uint4* dhot = hot_of<N>(v, dbuf, g);
         uint2* dcold = cold_of<N>(v, dbuf, g);
+        uint32_t* dkid = kid_of<N>(v, dbuf, g);
         uint4* dnodes = nodes_of<N>(v, dbuf, g);
-        if (lane == 0) dnodes[GG::SQ].z = (uint32_t)child;
+        if (lane == 0) { dnodes[GG::SQ].z = (uint32_t)child; dnodes[GG::SQ].w = 0xffffffffu; }   // .w: the copied edge that leads here
         __syncwarp();
         nd = 1;
         for (int i = 0; i < nd; ++i) {
@@ -563,6 +574,8 @@ __global__ void __launch_bounds__(kThreads) k_advance(View v, const int16_t* __r
             const uint4* srec = snodes + (size_t)src * (GG::SQ + 1);
             const uint4 sinfo = srec[GG::SQ];
             const int seb = (int)sinfo.x, K = (int)sinfo.y;
+            const uint32_t pe = drec[GG::SQ].w;                                        // set when this node was enqueued
+            if (lane == 0 && pe != 0xffffffffu) dkid[pe] = pack_kid(ne, K);             // its edges now start at ne
             if (lane < GG::SQ) drec[lane] = srec[lane];
             for (int base = 0; base < K; base += 32) {
                 const int k = base + lane;
@@ -573,6 +586,7 @@ __global__ void __launch_bounds__(kThreads) k_advance(View v, const int16_t* __r
                 if (has) {
                     const int my = nd + __popc(b & ((1u << lane) - 1u));
                     dnodes[(size_t)my * (GG::SQ + 1) + GG::SQ].z = c.y;
+                    dnodes[(size_t)my * (GG::SQ + 1) + GG::SQ].w = (uint32_t)(ne + k);
                     c.y = (uint32_t)my;
                 }
                 if (k < K) { dhot[ne + k] = q; dcold[ne + k] = c; }
