@@ -63,6 +63,12 @@ class OracleEnv:
         L.og_territory.argtypes = [S, ctypes.c_void_p]
         L.og_territory.restype = ctypes.c_float
         L.og_sub_encode.argtypes = [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int] * 4
+        L.og_replay_playout.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_void_p, ctypes.c_longlong,
+                                        ctypes.c_longlong, ctypes.c_uint64, ctypes.c_longlong, ctypes.c_int, ctypes.c_void_p,
+                                        ctypes.c_void_p]
+        L.og_replay_playout.restype = ctypes.c_longlong
+        L.og_batch_observe.argtypes = [ctypes.c_void_p, ctypes.c_longlong] + [ctypes.c_void_p] * 5
+        L.og_batch_observe.restype = None
 
     def reset(self):
         s = _OgState()
@@ -116,6 +122,29 @@ class OracleEnv:
         t = np.zeros([self.P], dtype=np.float32)
         sc = self.lib.og_territory(state, t.ctypes.data)
         return float(sc), t
+
+    # ---- whole-batch checkers (C loops; used to replay every game of a full-size playout launch)
+    def replay_playout(self, trace, seed, game_id0=0, no_eye=False):
+        """trace: int16 [plies, G] of device-chosen actions.  Verifies the move rule ply by ply (raises on the first
+        mismatch) and returns (plies replayed, array of final states)."""
+        trace = np.ascontiguousarray(trace, dtype=np.int16)
+        plies, G = trace.shape
+        finals = (_OgState * G)()
+        bad = np.zeros(4, dtype=np.int32)
+        n = self.lib.og_replay_playout(self.board_size, self.max_step, self.komi, trace.ctypes.data, plies, G, int(seed),
+                                       int(game_id0), int(no_eye), ctypes.byref(finals), bad.ctypes.data)
+        if n < 0:
+            raise AssertionError("playout trace differs from the move rule: game %d ply %d expected %d got %d" % tuple(bad))
+        return int(n), finals
+
+    def batch_observe(self, finals):
+        """(planes f32 [G,10,n,n], score f32 [G], territory f32 [G,P], legal bool [G,P+1] (python rule), noeye bool [G,P+1])"""
+        G, n, P = len(finals), self.board_size, self.P
+        planes = np.zeros([G, 10, n, n], np.float32); score = np.zeros([G], np.float32); terr = np.zeros([G, P], np.float32)
+        legal = np.zeros([G, P + 1], np.uint8); noeye = np.zeros([G, P + 1], np.uint8)
+        self.lib.og_batch_observe(ctypes.byref(finals), G, planes.ctypes.data, score.ctypes.data, terr.ctypes.data,
+                                  legal.ctypes.data, noeye.ctypes.data)
+        return planes, score, terr, legal.astype(bool), noeye.astype(bool)
 
     def getPlayer(self, state):
         return int(state.next_player)

@@ -301,3 +301,68 @@ void og_sub_encode(const float* enc, float* sub, int n, int sub_n, int channels,
                     sub[(i * channels + j) * sub_n * sub_n + y * sub_n + x] = enc[j * n * n + (y + y0) * n + (x + x0)];
     }
 }
+
+/* ---- batch trace replay (checker for tg_env_playout; SURVEY.md 8d C2 move rule) ---------------------------------
+ * mix32: the hash the playout kernels draw moves with (tests/helpers.py: mix32, provider.mix32 are its twins). */
+static uint32_t og_mix32(uint64_t seed, uint64_t a, uint64_t b) {
+    uint64_t z = seed + a * 0x9E3779B97F4A7C15ull + b * 0xBF58476D1CE4E5B9ull;
+    z ^= z >> 30; z *= 0xBF58476D1CE4E5B9ull;
+    z ^= z >> 27; z *= 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    return (uint32_t)(z >> 32);
+}
+
+/* Replays trace[plies][G] (device-chosen actions, -3 after the game ended) for games [0, G): every action must be the
+ * k-th legal point, k = (mix32(seed, game_id0 + g, step_count) * n_legal) >> 32, PASS iff there is none
+ * (environment.py:121-129 rule).  Fills finals[G] (nullable).  Returns the number of plies replayed, or -(1 + index of
+ * the first mismatch) with bad[0..3] = game, ply, expected, got. */
+long long og_replay_playout(int n, int max_step, float komi, const int16_t* trace, long long plies, long long G,
+                            uint64_t seed, long long game_id0, int no_eye, OgState* finals, int32_t* bad) {
+    int P = n * n;
+    long long total = 0;
+    int32_t legal[OG_MAX_P + 1];
+    for (long long g = 0; g < G; ++g) {
+        OgState s;
+        og_reset(&s, n, max_step, komi);
+        for (long long t = 0; t < plies; ++t) {
+            int got = trace[t * G + g], want;
+            if (s.terminated) want = OG_INVALID;
+            else {
+                int k = (no_eye ? og_legal_noeye(&s, legal) : og_legal(&s, legal)) - 1;   /* drop the appended PASS */
+                if (k == 0) want = P;
+                else want = legal[((uint64_t)og_mix32(seed, (uint64_t)(game_id0 + g), (uint64_t)s.step_count) * (uint64_t)k) >> 32];
+            }
+            if (got != want) {
+                if (bad) { bad[0] = (int32_t)g; bad[1] = (int32_t)t; bad[2] = want; bad[3] = got; }
+                return -(1 + g * plies + t);
+            }
+            if (!s.terminated) { int acc; og_step(&s, want, &acc); total++; }
+        }
+        if (finals) finals[g] = s;
+    }
+    return total;
+}
+
+/* observables of many states at once: planes [G][10P], score [G], territory [G][P], legal (python rule) [G][P+1] u8 */
+void og_batch_observe(const OgState* st, long long G, float* planes, float* score, float* terr, uint8_t* legal, uint8_t* noeye) {
+    int32_t buf[OG_MAX_P + 1];
+    for (long long g = 0; g < G; ++g) {
+        const OgState* s = &st[g];
+        int P = P_OF(s);
+        if (planes) og_encode10(s, planes + g * 10 * P);
+        if (terr) { float sc = og_territory(s, terr + g * P); if (score) score[g] = sc; }
+        else if (score) score[g] = og_score(s);
+        if (legal) {
+            int k = og_legal(s, buf);
+            memset(legal + g * (P + 1), 0, (size_t)P + 1);
+            if (k == 1) legal[g * (P + 1) + P] = 1;
+            else for (int i = 0; i < k - 1; ++i) legal[g * (P + 1) + buf[i]] = 1;
+        }
+        if (noeye) {
+            int k = og_legal_noeye(s, buf);
+            memset(noeye + g * (P + 1), 0, (size_t)P + 1);
+            if (k == 1) noeye[g * (P + 1) + P] = 1;
+            else for (int i = 0; i < k - 1; ++i) noeye[g * (P + 1) + buf[i]] = 1;
+        }
+    }
+}

@@ -89,3 +89,33 @@ def choice_from_u(p, u):
     cdf = np.cumsum(np.asarray(p, dtype=np.float64))
     cdf /= cdf[-1]
     return int(cdf.searchsorted(u, side="right"))
+
+
+# ---- a second stand-in net whose arithmetic is also expressible as exact int64 tensor ops + one float32 division, so the
+# CUDA engine can evaluate it ON THE DEVICE (tests/helpers.py: torch_hash_provider; capturable in a CUDA graph) while the
+# oracle evaluates this numpy twin: identical bits on both sides.
+def hash_eval_tables(seed, n_inputs, A):
+    coef = (_mix32_vec(seed, 11, np.arange(n_inputs)) | np.uint64(1)).astype(np.int64)        # < 2^32
+    mul = ((_mix32_vec(seed, 12, np.arange(A)) >> np.uint64(1)) | np.uint64(1)).astype(np.int64)   # < 2^31
+    add = _mix32_vec(seed, 13, np.arange(A)).astype(np.int64)
+    return coef, mul, add
+
+
+def hash_eval_batch(obs_batch, seed=77, sharp=3):
+    """obs [B, 10, n, n] of 0/1 -> (policy f32 [B, A], value f32 [B, 1]); heavy-tailed integer weights / their sum."""
+    obs = np.asarray(obs_batch, dtype=np.float32)
+    B = obs.shape[0]
+    A = obs.shape[-1] * obs.shape[-2] + 1
+    bits = obs.reshape(B, -1).astype(np.int64)
+    coef, mul, add = hash_eval_tables(seed, bits.shape[1], A)
+    h = (bits * coef[None, :]).sum(1) & np.int64(0x7FFFFFFF)
+    r = ((h[:, None] * mul[None, :] + add[None, :]) >> np.int64(13)) & np.int64(0xFFFF)
+    w = r
+    for _ in range(sharp - 1):
+        w = (w * r) >> np.int64(16)
+    w = w + np.int64(1)
+    total = w.sum(1).astype(np.float32)
+    policy = w.astype(np.float32) / total[:, None]
+    v = (((h * np.int64(2654435761)) >> np.int64(9)) & np.int64(0xFFFF)) - np.int64(32768)
+    value = v.astype(np.float32) / np.float32(32832.0)
+    return policy.astype(np.float32), value.reshape(-1, 1).astype(np.float32)

@@ -110,3 +110,27 @@ def check_mcts_move_against_golden(t, row, acts, N, W, var, action, pi, done, rt
     assert int(action) == int(t["action"][row]), ("action", row)
     assert np.array_equal(np.asarray(pi, dtype=np.float64), t["pi"][row]), ("pi", row)
     assert bool(done) == bool(t["done"][row])
+
+
+def torch_hash_provider(seed, n, sharp=3, device="cuda"):
+    """Device twin of oracle.provider.hash_eval_batch: exact int64 tensor ops + one IEEE float32 division per output, no
+    host round trip -> usable as the evaluator of a CUDA-graphed wave, and bit-identical to the numpy twin."""
+    import torch
+    from oracle import provider
+    A = n * n + 1
+    coef, mul, add = (torch.from_numpy(t).to(device) for t in provider.hash_eval_tables(seed, 10 * n * n, A))
+
+    def evaluator(obs):
+        B = obs.shape[0]
+        bits = obs.reshape(B, -1).to(torch.int64)
+        h = (bits * coef[None, :]).sum(1) & 0x7FFFFFFF
+        r = ((h[:, None] * mul[None, :] + add[None, :]) >> 13) & 0xFFFF
+        w = r
+        for _ in range(sharp - 1):
+            w = (w * r) >> 16
+        w = w + 1
+        total = w.sum(1).to(torch.float32)
+        policy = w.to(torch.float32) / total[:, None]
+        v = (((h * 2654435761) >> 9) & 0xFFFF) - 32768
+        return policy, v.to(torch.float32) / 32832.0
+    return evaluator

@@ -226,3 +226,85 @@ def test_encode_writes_in_place_into_a_larger_tensor():
     ref = env.encode()
     torch.cuda.synchronize()
     assert torch.equal(big[1], ref) and bool((big[0] == 7.0).all())
+
+
+# ------------------------------------------------------------------ the headline launch, every game
+def _headline_launch(G, tile, no_eye, seed, n=9):
+    from transgo_b200.environment import BatchedGoEnv
+    env = BatchedGoEnv(G, board_size=n, tile=tile)
+    plies = env.max_step + 2
+    trace = torch.full([plies, G], -9, dtype=torch.int16, device="cuda")
+    counter = torch.zeros([1], dtype=torch.int64, device="cuda")
+    env.playout(plies, seed=seed, no_eye=no_eye, trace=trace, counter=counter)
+    torch.cuda.synchronize()
+    return env, trace.cpu().numpy(), int(counter.item())
+
+
+@pytest.mark.parametrize("G,tile,no_eye", [(4096, 0, False), (4096, 0, True), (16384, 0, False), (4096, 4 | 64, False),
+                                           (4099, 16 | 64, True)])
+def test_headline_launch_replayed_on_every_game(oracle_built, G, tile, no_eye):
+    """BASELINE configs[1] exactly as bench.py launches it (BatchedGoEnv(4096, tile=0): the library's own layout choice),
+    with EVERY game replayed ply by ply on the C oracle (move rule, then final planes / score / territory / legal masks /
+    meta of all games), not a sample."""
+    seed = 0x7261
+    env, tr, played = _headline_launch(G, tile, no_eye, seed)
+    o = _oracle(9, max_step=env.max_step)
+    n, finals = o.replay_playout(tr, seed, 0, no_eye)
+    assert n == played == int((tr != -3).sum())
+    planes, score, terr, legal, noeye = o.batch_observe(finals)
+    sc, te = env.score(want_territory=True)
+    assert np.array_equal(sc.cpu().numpy(), score) and np.array_equal(te.cpu().numpy(), terr)
+    assert np.array_equal(env.encode().cpu().numpy(), planes)
+    assert np.array_equal(env.unpack_legal(env.legal_mask()).cpu().numpy(), legal)
+    assert np.array_equal(env.unpack_legal(env.legal_mask(no_eye=True)).cpu().numpy(), noeye)
+    meta = {k: v.cpu().numpy() for k, v in env.meta().items()}
+    assert meta["terminated"].all()
+    assert np.array_equal(meta["step"], np.array([f.step_count for f in finals]))
+    assert np.array_equal(meta["player"], np.array([f.next_player for f in finals]))
+    assert np.array_equal(meta["last1"], np.array([f.last1 for f in finals]))
+    assert np.array_equal(meta["last2"], np.array([f.last2 for f in finals]))
+
+
+def test_headline_launch_against_the_reference_engine_itself():
+    """The same launch checked against the UNMODIFIED reference library (oracle/_ref/go_env9.so, compiled from
+    /root/reference by oracle/Makefile; it travels to the GPU box): every ply of every game goes through the reference's
+    own getLegalAction / Step, the final positions through its Encode / getTerritory."""
+    import ctypes
+    from helpers import mix32
+    from oracle.go_oracle import RefEnv, have_ref
+    if not have_ref(9):
+        pytest.skip("oracle/_ref/go_env9.so not built (needs /root/reference at build time)")
+    seed, G = 0x7261, 4096
+    env, tr, played = _headline_launch(G, 0, False, seed)
+    ref = RefEnv(9, max_step=env.max_step)
+    L = ref.lib
+    plies = tr.shape[0]
+    rnd = mix32(seed, np.arange(G, dtype=np.uint64)[:, None], np.arange(plies + 2, dtype=np.uint64)[None, :])   # [G, step]
+    buf = np.zeros(82, dtype=np.int32)
+    bufp = buf.ctypes.data
+    planes_g = env.encode().cpu().numpy()
+    sc_g, te_g = env.score(want_territory=True)
+    sc_g, te_g = sc_g.cpu().numpy(), te_g.cpu().numpy()
+    enc = np.zeros([10, 9, 9], dtype=np.float32); terr = np.zeros([81], dtype=np.float32)
+    a_blob, b_blob = ref._new(), ref._new()
+    total = 0
+    for g in range(G):
+        L.Reset(a_blob)
+        done = False
+        col = tr[:, g]
+        for t in range(plies):
+            if done:
+                assert col[t] == -3, (g, t)
+                continue
+            k = L.getLegalAction(a_blob, bufp) - 1                 # the C list always ends with PASS (go_env.cc:170)
+            step = t + 1                                           # step_count is 1-based and every ply is accepted
+            want = 81 if k == 0 else int(buf[(int(rnd[g, step]) * k) >> 32])
+            assert col[t] == want, (g, t, want, int(col[t]))
+            done = bool(L.Step(a_blob, b_blob, want))
+            a_blob, b_blob = b_blob, a_blob
+            total += 1
+        if g % 8 == 0:                                             # observables of the final position, every 8th game
+            L.Encode(a_blob, enc.ctypes.data)
+            sc = L.getTerritory(a_blob, terr.ctypes.data)
+            assert np.array_equal(planes_g[g], enc) and sc_g[g] == sc and np.array_equal(te_g[g], terr), g
+    assert total == played

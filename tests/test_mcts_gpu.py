@@ -24,8 +24,9 @@ def cpu_provider(seed, sharp):
     return evaluator
 
 
-def make_oracles(G, n, sims, seed, sharp, game_id0=0, max_step=None, tie="hash", readouts=4):
+def make_oracles(G, n, sims, seed, sharp, game_id0=0, max_step=None, tie="hash", readouts=4, eval_fn=None):
     from oracle import provider
+    eval_fn = eval_fn or (lambda o: provider.synth_eval_batch(o, seed=seed, sharp=sharp))
     from oracle.go_oracle import OracleEnv
     from oracle.mcts_oracle import OracleMCTS, MCTSConfig
     out = []
@@ -39,7 +40,7 @@ def make_oracles(G, n, sims, seed, sharp, game_id0=0, max_step=None, tie="hash",
             i = provider.tie_index(seed, gid, cnt[0], k)
             cnt[0] += 1
             return i
-        out.append(OracleMCTS(OracleEnv(n, max_step=max_step), lambda o: provider.synth_eval_batch(o, seed=seed, sharp=sharp),
+        out.append(OracleMCTS(OracleEnv(n, max_step=max_step), eval_fn,
                               MCTSConfig(board_size=n, num_simulation=sims, parallel_readouts=readouts), tie_fn=tie_fn,
                               noise_fn=lambda m, k, gid=gid: provider.dirichlet(seed, gid, m, k),
                               u_fn=lambda m, gid=gid: provider.uniform(seed, gid, m)))
@@ -317,3 +318,74 @@ def test_continuous_selfplay_restarts_finished_slots(oracle_built):
     assert n <= 6 * out["games"]                                 # max_step 6: at most 6 positions per game
     more = w.play_continuous(min_positions=10, augment=True)     # the unfinished games carry on
     assert more["obs"].shape[0] == 8 * more["positions"] and more["positions"] >= 10
+
+
+# ------------------------------------------------------------------ parity at the BASELINE depths
+def _hash_oracles(G, n, sims, seed, sharp, tie):
+    from oracle import provider
+    return make_oracles(G, n, sims, seed, sharp, tie=tie, eval_fn=lambda o: provider.hash_eval_batch(o, seed=seed, sharp=sharp))
+
+
+@pytest.mark.parametrize("tie,graph", [("hash", True), ("first", False)])
+def test_c3_depth_800_simulations_match_oracle(oracle_built, tie, graph):
+    """BASELINE configs[2] depth: 800 simulations per move (deep trees, re-rooted arenas, 16-bit visit counters in use),
+    3 games x 3 moves against the oracle; the evaluator is the device-side hash provider (bit-identical numpy twin on the
+    oracle side), with the whole wave replayed as a CUDA graph in one of the two variants."""
+    from helpers import torch_hash_provider
+    from transgo_b200.mcts import BatchedMCTS
+    seed, G, sims, sharp = 801, 3, 800, 5
+    eng = BatchedMCTS(torch_hash_provider(seed, 9, sharp), G, num_simulation=sims, tie_mode=tie, tie_seed=seed, graph_waves=graph)
+    compare_batch(eng, _hash_oracles(G, 9, sims, seed, sharp, tie), seed, 3)
+    assert (eng._wave_graph is not None) == graph
+    st = eng.search_stats()
+    assert st["mean_depth"] > 2.0                                  # the trees really are deep
+
+
+def test_c4_depth_19x19_400_simulations_match_oracle(oracle_built):
+    """BASELINE configs[3] depth: 19x19, 400 simulations per move, 2 games x 2 moves, CUDA-graphed waves."""
+    from helpers import torch_hash_provider
+    from transgo_b200.mcts import BatchedMCTS
+    seed, G, sims, sharp = 1904, 2, 400, 5
+    eng = BatchedMCTS(torch_hash_provider(seed, 19, sharp), G, board_size=19, num_simulation=sims, tie_seed=seed, graph_waves=True)
+    compare_batch(eng, _hash_oracles(G, 19, sims, seed, sharp, "hash"), seed, 2)
+
+
+def test_select_action_from_a_mid_game_position_matches_oracle(oracle_built):
+    """WP_MCTS.select_action(state) (self_play.py:689-704): a FRESH search from an arbitrary position, no root noise,
+    temperature 0.12.  The position goes in as the reference-style state blob (set_root_state_blob); visit counts, pi and
+    the root observation must equal the oracle's search from the same position."""
+    from oracle import provider
+    from oracle.go_oracle import OracleEnv
+    from oracle.mcts_oracle import OracleMCTS, MCTSConfig
+    from transgo_b200.environment import GoEnv
+    from transgo_b200.mcts import WP_MCTS
+    from helpers import playout_action
+    seed, sims = 23, 210
+
+    class Model:
+        def main_prediction(self, x):
+            p, v = provider.hash_eval_batch(x.cpu().numpy(), seed=seed, sharp=5)
+            return torch.from_numpy(p).cuda(), torch.from_numpy(v).cuda(), torch.zeros(len(p), 81).cuda()
+
+    class Cfg:
+        board_size, num_simulation, c_puct1, c_puct2, wu_loss, parallel_readouts = 9, sims, 3, 0.05, 2, 4
+    env, oenv = GoEnv(Cfg()), OracleEnv(9)
+    agent = WP_MCTS(Cfg(), env, Model(), None, tie_mode="first")
+    for plies in (37, 90):
+        s, _ = env.reset()
+        so, _ = oenv.reset()
+        for t in range(plies):                                    # a mid-game position with captures and kos behind it
+            pts = [x for x in oenv.legal_c(so) if x != 81]
+            a = playout_action(5, plies, oenv.getStep(so), pts, 81)
+            s, _ = env.step(s, a)
+            so, _ = oenv.step(so, a)
+        act = agent.select_action(s)
+        ora = OracleMCTS(oenv, lambda o: provider.hash_eval_batch(o, seed=seed, sharp=5), MCTSConfig(num_simulation=sims))
+        ora.root = ora._root_expand(so)                           # select_action: root = Node_V(state) + expand (:691-700)
+        oa, opi, oobs = ora.get_action_probs(is_selfplay=False, forced_action=act)
+        b = agent._b
+        assert np.array_equal(b.counts[0].cpu().numpy(), ora.visit_counts()), plies
+        assert int(b.root_n[0].item()) == ora.rootN
+        counts = ora.visit_counts()
+        assert counts[act] == counts.max() or counts[act] >= 2     # temperature 0.12 draw: a heavily visited move
+        assert env.getStep(agent.root.state) == plies + 1 and env.checkAction(s, act if act != 81 else -1)
