@@ -119,6 +119,7 @@ def torch_hash_provider(seed, n, sharp=3, device="cuda"):
     from oracle import provider
     A = n * n + 1
     coef, mul, add = (torch.from_numpy(t).to(device) for t in provider.hash_eval_tables(seed, 10 * n * n, A))
+    den = torch.full([1], 32832.0, dtype=torch.float32, device=device)   # tensor / python-scalar becomes a multiply by 1/x on CUDA
 
     def evaluator(obs):
         B = obs.shape[0]
@@ -132,5 +133,5 @@ def torch_hash_provider(seed, n, sharp=3, device="cuda"):
         total = w.sum(1).to(torch.float32)
         policy = w.to(torch.float32) / total[:, None]
         v = (((h * 2654435761) >> 9) & 0xFFFF) - 32768
-        return policy, v.to(torch.float32) / 32832.0
+        return policy, v.to(torch.float32) / den
     return evaluator

@@ -7,6 +7,7 @@
 #include "tg_board.cuh"
 #include "tg_common.cuh"
 #include "tg_rows.cuh"
+#include "tg_inc.cuh"
 
 namespace tg {
 
@@ -197,6 +198,56 @@ k_playout_wu(uint4* __restrict__ states, long long G, int plies, int max_step, u
     }
 }
 
+// Incremental engine (tg_inc.cuh): dense bit-string boards, the atari set kept in registers across plies.  T lanes per game
+// (T >= 8: 32/T games per warp in lock step, lanes = the <= 5 groups around the new stone; T == 1: one thread per game).
+template <int N, int T, bool NOEYE>
+__global__ void __launch_bounds__(kThreads)
+k_playout_inc(uint4* __restrict__ states, long long G, int plies, int max_step, unsigned long long seed, long long game_id0,
+              int16_t* __restrict__ trace, unsigned long long* __restrict__ plies_done) {
+    using namespace inc;
+    const long long g = (blockIdx.x * (long long)blockDim.x + threadIdx.x) / T;
+    const bool exists = g < G;
+    if (T > 1 ? !__any_sync(0xffffffffu, exists) : !exists) return;
+    const int j = (int)(threadIdx.x & (T - 1));
+    const bool lead = j == 0;
+    // lane roles: j = 0..3 -> the E / W / S / N neighbour of the new stone (an enemy group), j >= 4 -> the stone itself
+    const int sl = j == 0 ? 1 : (j == 2 ? DGeo<N>::STR : 0), sr = j == 1 ? 1 : (j == 3 ? DGeo<N>::STR : 0);
+    const bool enemy_lane = j < 4;
+    Pos<N> p0; pos_reset(p0); p0.terminated = 1;
+    if (exists) pos_load<N>(p0, states, g, G, 1);
+    Game<N> s;
+    const bool first_black = p0.player == kBlack;
+    s.a = to_dense<N>(bb_select(first_black, p0.stones[0], p0.stones[1]));
+    s.b = to_dense<N>(bb_select(first_black, p0.stones[1], p0.stones[0]));
+    s.last1 = p0.last1; s.last2 = p0.last2; s.ko_loc = p0.ko_loc; s.ko_age = p0.ko_age; s.step = p0.step; s.player = p0.player;
+    s.ko_color = p0.ko_color; s.terminated = p0.terminated;
+    s.l1 = atari_from_scratch<N, T>(s.a, s.b);
+    const unsigned long long gid = (unsigned long long)(game_id0 + g);
+    int played = 0;
+    for (int t = 0; t < plies; t += 2) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            if (t + h < plies) {                                   // kernel-uniform
+                int action = kInvalid;
+                if (vany<T>(!s.terminated)) {
+                    action = h == 0 ? ply<N, T, NOEYE>(s, s.a, s.b, max_step, seed, gid, sl, sr, enemy_lane)
+                                    : ply<N, T, NOEYE>(s, s.b, s.a, max_step, seed, gid, sl, sr, enemy_lane);
+                    played += action != kInvalid;
+                }
+                if (trace && exists && lead) trace[(long long)(t + h) * G + g] = (int16_t)action;
+            }
+        }
+    }
+    if (exists && lead) {
+        p0.stones[0] = from_dense<N>(dsel<N>(first_black, s.a, s.b));
+        p0.stones[1] = from_dense<N>(dsel<N>(first_black, s.b, s.a));
+        p0.last1 = s.last1; p0.last2 = s.last2; p0.ko_loc = s.ko_loc; p0.ko_age = s.ko_age; p0.step = s.step; p0.player = s.player;
+        p0.ko_color = s.ko_color; p0.terminated = s.terminated;
+        pos_store<N>(p0, states, g, G, 1);
+        if (plies_done && played) atomicAdd(plies_done, (unsigned long long)played);
+    }
+}
+
 // Row-per-lane playout (tg_rows.cuh): 31 / (N+1) games per warp, one board row per lane.  Same move rule, same results.
 template <int N>
 __global__ void __launch_bounds__(kThreads)
@@ -355,6 +406,17 @@ template <int N, int TC> void launch_playout(cudaStream_t st, uint4* states, lon
         k_playout<N, T><<<blocks_for(G, T), kThreads, 0, st>>>(states, G, plies, max_step, seed, game_id0, no_eye, trace, plies_done);
 }
 
+template <int N, int T> int launch_playout_inc(cudaStream_t st, uint4* states, long long G, int plies, int max_step, unsigned long long seed,
+                                                long long game_id0, int no_eye, int16_t* trace, unsigned long long* plies_done) {
+    // a playout CTA lives for the whole game: with few warps per SM one-warp CTAs spread them evenly over the 148 SMs
+    const long long warps = (G * T + 31) / 32;
+    const int threads = warps < 148LL * 16 ? 32 : kThreads;
+    const unsigned blocks = (unsigned)((G * T + threads - 1) / threads);
+    if (no_eye) k_playout_inc<N, T, true><<<blocks, threads, 0, st>>>(states, G, plies, max_step, seed, game_id0, trace, plies_done);
+    else k_playout_inc<N, T, false><<<blocks, threads, 0, st>>>(states, G, plies, max_step, seed, game_id0, trace, plies_done);
+    return 0;
+}
+
 }  // namespace tg
 
 using namespace tg;
@@ -411,9 +473,16 @@ int tg_env_score(int n, const void* states, int64_t G, float komi, float* score,
     return set_err((int)cudaGetLastError(), "tg_env_score");
 }
 
-/* the layout tg_env_playout runs for (n, G, tile): TG_TILE_ROWS or lanes per game */
+/* the layout tg_env_playout runs for (n, G, tile): TG_TILE_ROWS or lanes per game (| TG_TILE_UNIFORM | TG_TILE_INC) */
 int tg_env_playout_tile(int n, int64_t G, int tile) {
-    if (tile == 0) return (n == 19) ? TG_TILE_ROWS : (G < 12288 ? (8 | TG_TILE_UNIFORM) : 1);
+    if (tile == 0) {
+        if (n == 19) return TG_TILE_ROWS;
+        return G < 24576 ? (8 | TG_TILE_INC) : (1 | TG_TILE_INC);
+    }
+    if (tile > 0 && (tile & TG_TILE_INC)) {
+        const int t = tile & (TG_TILE_UNIFORM - 1);
+        return (t == 32 || t == 16 || t == 8 || t == 1) ? (t | TG_TILE_INC) : tg_env_playout_tile(n, G, 0);
+    }
     if (tile > 0 && (tile & TG_TILE_UNIFORM)) {
         const int t = tile & (TG_TILE_UNIFORM - 1);
         return (t == 16 || t == 8 || t == 4) ? tile : pick_tile(0, G);
@@ -432,6 +501,15 @@ int tg_env_playout(int n, void* states, int64_t G, int plies, int max_step, uint
         if (n == 9) launch_playout_rows<9>(st, (uint4*)states, G, plies, max_step, seed, game_id0, no_eye, trace_actions, plies_done);
         else if (n == 19) launch_playout_rows<19>(st, (uint4*)states, G, plies, max_step, seed, game_id0, no_eye, trace_actions, plies_done);
         else return set_err(-1, "board size must be 9 or 19");
+        return set_err((int)cudaGetLastError(), "tg_env_playout");
+    }
+    if (tile & TG_TILE_INC) {
+        const int t = tile & (TG_TILE_UNIFORM - 1);
+#define TG_INC_CASE(NN, TT) launch_playout_inc<NN, TT>(st, (uint4*)states, G, plies, max_step, seed, game_id0, no_eye, trace_actions, plies_done)
+        if (n == 9) { if (t == 32) TG_INC_CASE(9, 32); else if (t == 16) TG_INC_CASE(9, 16); else if (t == 8) TG_INC_CASE(9, 8); else TG_INC_CASE(9, 1); }
+        else if (n == 19) { if (t == 32) TG_INC_CASE(19, 32); else if (t == 16) TG_INC_CASE(19, 16); else if (t == 8) TG_INC_CASE(19, 8); else TG_INC_CASE(19, 1); }
+        else return set_err(-1, "board size must be 9 or 19");
+#undef TG_INC_CASE
         return set_err((int)cudaGetLastError(), "tg_env_playout");
     }
     if (n == 9) { TG_DISPATCH_T6(9, tile, launch_playout, st, (uint4*)states, G, plies, max_step, seed, game_id0, no_eye, trace_actions, plies_done) }

@@ -1,0 +1,330 @@
+// tg_inc.cuh -- incremental playout engine: dense bit-string boards + a persistent atari set.
+//
+// Third formulation of the rules engine behind the C2 loop (Step + getLegalAction of GoEnv/cpp_src/board.cc:437-489,
+// 546-661), written for the playout kernel only.  Two ideas (VERDICT r1 "What's weak" #3: 321 warp instructions per
+// game-ply, ALU pipe bound):
+//
+//  * Dense layout.  A board is ONE bit string of N rows x (N+1) bits (the extra bit of a row is an always-zero guard),
+//    bit b = y*(N+1) + x, cut into 32-bit words: 96 bits / 3 words at 9x9, 380 bits / 12 words at 19x19.  The four
+//    neighbour directions are multi-word shifts by 1 and N+1, i.e. one funnel shift (SHF) per word and direction, and the
+//    eastward flood fill is one multi-word add (the carry ripples along a run of stones and dies in the guard bit).
+//
+//  * Incremental atari set.  The rules never need liberty COUNTS, only "this group has exactly one liberty"
+//    (suicide / capture tests, board.cc:130-158, 606-630).  tg_board.cuh re-derives that set for the whole board on every
+//    ply that has an enclosed empty point (most of the middle game).  Here the set `l1` (stones of groups in atari, both
+//    colours) lives in registers across plies and is repaired after each move: a stone placed at p changes the liberty
+//    count of (a) the group p joins, (b) the enemy groups next to p, (c) groups next to captured stones -- nothing else.
+//    (b) and (a) are at most five group floods, done by five lanes of the tile side by side with an early exit once two
+//    liberties are seen; (c) can only take own groups OUT of atari (they gain a liberty) and is a flood inside `l1`.
+//    With `l1` at hand the legal mask of the next ply is pure bit arithmetic:
+//        legal = empty & nbrs(empty | own-not-in-atari | enemy-in-atari)  minus the ko point.
+//
+// Lanes: T = 8 lanes per game, 32/T games per warp in lock step (warp-uniform control flow, like k_playout_wu), or T = 1
+// (one thread per game, floods one after the other) for batches large enough to fill the GPU with independent threads.
+// Every observable equals tg_board.cuh / tg_rows.cuh / go_env.so bit for bit (tests/test_env_gpu.py replays every game).
+#pragma once
+#include "tg_board.cuh"
+
+namespace tg {
+namespace inc {
+
+constexpr unsigned kFullMask = 0xffffffffu;
+
+template <int N>
+struct DGeo {
+    static constexpr int P = N * N;
+    static constexpr int STR = N + 1;                 // bits per row (guard bit included)
+    static constexpr int NB = N * STR;                // bits in use
+    static constexpr int NW = (NB + 31) / 32;         // 32-bit words
+    __host__ __device__ static constexpr uint32_t mask(int i) {          // on-board bits of word i
+        uint32_t m = 0;
+        for (int k = 0; k < 32; ++k) { const int b = i * 32 + k; if (b < NB && (b % STR) != N) m |= 1u << k; }
+        return m;
+    }
+    __host__ __device__ static constexpr uint32_t edge(int i) {          // points with an off-board diagonal
+        uint32_t m = 0;
+        for (int k = 0; k < 32; ++k) {
+            const int b = i * 32 + k;
+            if (b >= NB || (b % STR) == N) continue;
+            const int y = b / STR, x = b % STR;
+            if (y == 0 || y == N - 1 || x == 0 || x == N - 1) m |= 1u << k;
+        }
+        return m;
+    }
+};
+
+template <int N> struct DS { uint32_t w[DGeo<N>::NW]; };      // a point set in the dense layout
+
+#define TG_DW _Pragma("unroll") for (int i = 0; i < DGeo<N>::NW; ++i)
+
+template <int N> __device__ __forceinline__ DS<N> dzero() { DS<N> r; TG_DW r.w[i] = 0; return r; }
+template <int N> __device__ __forceinline__ bool dany(const DS<N>& a) { uint32_t o = 0; TG_DW o |= a.w[i]; return o != 0; }
+template <int N> __device__ __forceinline__ int dcount(const DS<N>& a) { int c = 0; TG_DW c += __popc(a.w[i]); return c; }
+template <int N> __device__ __forceinline__ DS<N> operator&(const DS<N>& a, const DS<N>& b) { DS<N> r; TG_DW r.w[i] = a.w[i] & b.w[i]; return r; }
+template <int N> __device__ __forceinline__ DS<N> operator|(const DS<N>& a, const DS<N>& b) { DS<N> r; TG_DW r.w[i] = a.w[i] | b.w[i]; return r; }
+template <int N> __device__ __forceinline__ DS<N> dandn(const DS<N>& a, const DS<N>& b) { DS<N> r; TG_DW r.w[i] = a.w[i] & ~b.w[i]; return r; }
+template <int N> __device__ __forceinline__ DS<N> dsel(bool p, const DS<N>& a, const DS<N>& b) { DS<N> r; TG_DW r.w[i] = p ? a.w[i] : b.w[i]; return r; }
+// a has a bit outside b
+template <int N> __device__ __forceinline__ bool dnot_within(const DS<N>& a, const DS<N>& b) { uint32_t o = 0; TG_DW o |= a.w[i] & ~b.w[i]; return o != 0; }
+
+// multi-word shifts by a (possibly per-lane) amount 0 <= k < 32; bits leaving the string are lost, guard bits are NOT cleared
+template <int N> __device__ __forceinline__ DS<N> dshl(const DS<N>& a, int k) {
+    DS<N> r;
+    TG_DW r.w[i] = (i == 0) ? (a.w[0] << k) : __funnelshift_l(a.w[i - 1], a.w[i], k);
+    return r;
+}
+template <int N> __device__ __forceinline__ DS<N> dshr(const DS<N>& a, int k) {
+    constexpr int NW = DGeo<N>::NW;
+    DS<N> r;
+    TG_DW r.w[i] = (i == NW - 1) ? (a.w[NW - 1] >> k) : __funnelshift_r(a.w[i], a.w[i + 1], k);
+    return r;
+}
+template <int N> __device__ __forceinline__ DS<N> dmask(const DS<N>& a) { DS<N> r; TG_DW r.w[i] = a.w[i] & DGeo<N>::mask(i); return r; }
+
+// 4-neighbourhood (go_comm.h:43-44): E/W = shifts by 1, S/N = shifts by N+1; whatever lands on a guard bit or beyond
+// the last row is masked away
+template <int N> __device__ __forceinline__ DS<N> dnbrs(const DS<N>& a) {
+    constexpr int S = DGeo<N>::STR;
+    const DS<N> e = dshl<N>(a, 1), w = dshr<N>(a, 1), s = dshl<N>(a, S), n = dshr<N>(a, S);
+    DS<N> r;
+    TG_DW r.w[i] = (e.w[i] | w.w[i] | s.w[i] | n.w[i]) & DGeo<N>::mask(i);
+    return r;
+}
+
+// eastward fill of the seeds g (a subset of mk) to the end of their runs in mk: one multi-word add, the carry ripples up
+// each run of ones and is absorbed by the first zero (at the latest the row's guard bit)
+template <int N> __device__ __forceinline__ DS<N> defill(const DS<N>& g, const DS<N>& mk) {
+    DS<N> r;
+    uint32_t carry = 0;
+    TG_DW {
+        const uint64_t t = (uint64_t)mk.w[i] + g.w[i] + carry;      // ptxas folds this into IADD3 / IADD3.X
+        carry = (uint32_t)(t >> 32);
+        r.w[i] = (((uint32_t)t ^ mk.w[i]) & mk.w[i]) | g.w[i];
+    }
+    return r;
+}
+
+// true eyes of `own` against `opp` (board.cc:665-714): empty, every on-board neighbour own; fake when an edge point sees
+// one enemy diagonal or an interior point two
+template <int N> __device__ __forceinline__ DS<N> dtrue_eyes(const DS<N>& own, const DS<N>& opp) {
+    constexpr int S = DGeo<N>::STR;
+    DS<N> notown, empty;
+    TG_DW { notown.w[i] = ~own.w[i] & DGeo<N>::mask(i); empty.w[i] = ~(own.w[i] | opp.w[i]) & DGeo<N>::mask(i); }
+    const DS<N> eye = dandn<N>(empty, dnbrs<N>(notown));
+    const DS<N> d1 = dmask<N>(dshl<N>(opp, S + 1)), d2 = dmask<N>(dshl<N>(opp, S - 1));
+    const DS<N> d3 = dmask<N>(dshr<N>(opp, S + 1)), d4 = dmask<N>(dshr<N>(opp, S - 1));
+    DS<N> r;
+    TG_DW {
+        const uint32_t anyd = d1.w[i] | d2.w[i] | d3.w[i] | d4.w[i];
+        const uint32_t twod = (d1.w[i] & d2.w[i]) | ((d1.w[i] | d2.w[i]) & d3.w[i]) | ((d1.w[i] | d2.w[i] | d3.w[i]) & d4.w[i]);
+        const uint32_t fake = (DGeo<N>::edge(i) & anyd) | (~DGeo<N>::edge(i) & twod);
+        r.w[i] = eye.w[i] & ~fake;
+    }
+    return r;
+}
+
+// dense bit index <-> action index
+template <int N> __device__ __forceinline__ int bit_to_action(int b) { return b - b / DGeo<N>::STR; }
+template <int N> __device__ __forceinline__ int action_to_bit(int a) { return a + a / N; }
+template <int N> __device__ __forceinline__ DS<N> dpoint(int b) { DS<N> r; TG_DW r.w[i] = (i == (b >> 5)) ? (1u << (b & 31)) : 0u; return r; }
+template <int N> __device__ __forceinline__ int dlowest(const DS<N>& a) {       // lowest bit index; a must be non-empty
+    int b = -1;
+#pragma unroll
+    for (int i = DGeo<N>::NW - 1; i >= 0; --i) if (a.w[i]) b = i * 32 + __ffs((int)a.w[i]) - 1;
+    return b;
+}
+
+// conversions from / to the stored layout (tg_board.cuh: Pos<N>), once per launch
+template <int N> __device__ __forceinline__ DS<N> to_dense(const BB<N>& a) {
+    using G = Geo<N>; using D = DGeo<N>;
+    DS<N> r = dzero<N>();
+#pragma unroll
+    for (int y = 0; y < N; ++y) {
+        const uint32_t row = (uint32_t)((a.w[y / G::RPW] >> ((y % G::RPW) * G::STRIDE)) & G::row());
+        const int off = y * D::STR, wi = off >> 5, sh = off & 31;
+        r.w[wi] |= row << sh;
+        if (sh + N > 32) r.w[wi + 1] |= row >> (32 - sh);
+    }
+    return r;
+}
+template <int N> __device__ __forceinline__ BB<N> from_dense(const DS<N>& a) {
+    using G = Geo<N>; using D = DGeo<N>; using word_t = typename G::word_t;
+    BB<N> r = bb_zero<N>();
+#pragma unroll
+    for (int y = 0; y < N; ++y) {
+        const int off = y * D::STR, wi = off >> 5, sh = off & 31;
+        uint32_t row = a.w[wi] >> sh;
+        if (sh + N > 32) row |= a.w[wi + 1] << (32 - sh);
+        row &= (uint32_t)G::row();
+        r.w[y / G::RPW] |= word_t(row) << ((y % G::RPW) * G::STRIDE);
+    }
+    return r;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// lane cooperation.  T lanes per game; T > 1 runs warp-uniform: every vote spans the warp, every shuffle uses the full mask
+template <int T> __device__ __forceinline__ bool vany(bool p) { return T == 1 ? p : __any_sync(kFullMask, p); }
+template <int N, int T> __device__ __forceinline__ DS<N> tile_or(DS<N> a) {
+    if constexpr (T > 1) {
+#pragma unroll
+        for (int s = T / 2; s >= 1; s >>= 1)
+            TG_DW a.w[i] |= __shfl_xor_sync(kFullMask, a.w[i], s);
+    }
+    return a;
+}
+
+// flood g through mk to the fixed point (no liberty bookkeeping): captured groups, groups leaving atari
+template <int N, int T> __device__ __forceinline__ DS<N> dflood(DS<N> g, const DS<N>& mk) {
+    bool ch = dany<N>(g);
+    while (vany<T>(ch)) {
+        const DS<N> n1 = defill<N>((g | dnbrs<N>(g)) & mk, mk);
+        ch = dnot_within<N>(n1, g);
+        g = n1;
+    }
+    return g;
+}
+
+// Flood the group of the seed g inside `col`, counting its liberties, until it is complete or `lim` liberties are known.
+// On return: complete -> g is the whole group and libs exact; otherwise libs >= lim.  (tg_board.cuh: flood_group)
+template <int N, int T> __device__ __forceinline__ void dflood_group(DS<N>& g, const DS<N>& col, const DS<N>& empty, int lim, int& libs, bool& complete) {
+    while (true) {
+        const DS<N> nb = dnbrs<N>(g);
+        const DS<N> n1 = defill<N>((g | nb) & col, col);
+        libs = dcount<N>(nb & empty);
+        const bool ch = dnot_within<N>(n1, g);
+        g = n1;
+        complete = !ch;
+        if (!vany<T>(ch && libs < lim)) break;
+    }
+}
+
+// The atari set of a whole position, from scratch (once per launch; an empty board costs nothing).  All lanes of a tile
+// run the same loop: lowest unvisited stone -> its group -> liberties.
+template <int N, int T> __device__ __forceinline__ DS<N> atari_from_scratch(const DS<N>& a, const DS<N>& b) {
+    DS<N> empty; TG_DW empty.w[i] = ~(a.w[i] | b.w[i]) & DGeo<N>::mask(i);
+    DS<N> rest = a | b, l1 = dzero<N>();
+    while (vany<T>(dany<N>(rest))) {
+        DS<N> g; bool taken = false;
+        TG_DW { g.w[i] = taken ? 0u : (rest.w[i] & (0u - rest.w[i])); taken = taken || rest.w[i] != 0; }
+        const DS<N> col = dsel<N>(dany<N>(g & a), a, b);
+        int libs; bool complete;
+        dflood_group<N, T>(g, col, empty, 1 << 20, libs, complete);
+        if (libs == 1) l1 = l1 | g;
+        rest = dandn<N>(rest, g);
+    }
+    return l1;
+}
+
+// One game in registers.  me / op are ROLES (the side to move at even plies of the launch / the other side), swapped by the
+// caller every ply, so the colour of `me` never has to be looked up.
+template <int N>
+struct Game {
+    DS<N> a, b;            // stones of the side to move at ply 0 of the launch, of the other side
+    DS<N> l1;              // stones of groups with exactly one liberty, both colours
+    int last1, last2, ko_loc, ko_age, step, player, ko_color, terminated;
+};
+
+// k-th (0-based) set bit of the string; caller guarantees 0 <= k < count.  Returns the dense bit index.
+template <int N> __device__ __forceinline__ int dselect(const DS<N>& a, int k) {
+    uint32_t sel = 0; int kk = 0, base = 0; bool found = false;
+    TG_DW {
+        const int c = __popc(a.w[i]);
+        const bool here = !found && k < c;
+        sel = here ? a.w[i] : sel; kk = here ? k : kk; base = here ? i * 32 : base;
+        found = found || here;
+        k -= c;
+    }
+    return base + nth_bit(sel, kk);
+}
+
+// One ply of the C2 loop for the side `me`: legal mask -> hashed k-th legal point (PASS iff none) -> place / capture / ko ->
+// repair the atari set.  Returns the action played (P = pass) or kInvalid when this game is over.
+//   role lanes (T >= 8): lane j of a tile, j < 4: the enemy group touching the new stone in direction j; j >= 4: the group
+//   the new stone joins.  sl / sr = this lane's shift (left or right amount, the other 0).
+template <int N, int T, bool NOEYE>
+__device__ __forceinline__ int ply(Game<N>& s, DS<N>& me, DS<N>& op, int max_step, unsigned long long seed, unsigned long long gid,
+                                   int sl, int sr, bool enemy_lane) {
+    using D = DGeo<N>;
+    const bool active = !s.terminated;
+    DS<N> empty; TG_DW empty.w[i] = ~(me.w[i] | op.w[i]) & D::mask(i);
+    // legal = empty & nbrs(empty | own groups with >1 liberty | enemy groups in atari)    (board.cc:130-158, 437-464)
+    DS<N> src; TG_DW src.w[i] = empty.w[i] | (me.w[i] & ~s.l1.w[i]) | (op.w[i] & s.l1.w[i]);
+    DS<N> lg = empty & dnbrs<N>(src);
+    const bool kocond = active && s.ko_age == 0 && s.ko_color == s.player && s.ko_loc >= 0 && s.ko_loc < D::P;   // board.cc:198-200
+    if (vany<T>(kocond)) { if (kocond) lg = dandn<N>(lg, dpoint<N>(action_to_bit<N>(s.ko_loc))); }
+    if (NOEYE) lg = dandn<N>(lg, dtrue_eyes<N>(me, op));                                       // board.cc:510-512
+    const int nl = dcount<N>(lg);
+    const bool placing = active && nl > 0;
+    const uint32_t r = mix32(seed, gid, (unsigned long long)s.step);
+    const int bit = dselect<N>(lg, placing ? (int)(((unsigned long long)r * (unsigned)nl) >> 32) : 0);
+    const int act = bit_to_action<N>(bit);
+    DS<N> pb; TG_DW pb.w[i] = (placing && i == (bit >> 5)) ? (1u << (bit & 31)) : 0u;
+    const DS<N> around = dnbrs<N>(pb);
+    DS<N> hit; TG_DW hit.w[i] = around.w[i] & op.w[i] & s.l1.w[i];                             // enemy neighbours in atari: they die
+    DS<N> mrg; TG_DW mrg.w[i] = around.w[i] & me.w[i] & s.l1.w[i];
+    const bool merge = dany<N>(mrg);                       // the stone joins an own group that was in atari: re-derive it in full
+    bool ko = false;
+    if (vany<T>(dany<N>(hit))) {
+        // simple ko, decided before the capture (board.cc:163-194, 561-570): no empty and no own neighbour, exactly one
+        // captured neighbour block and that block a single stone
+        DS<N> free_or_own; TG_DW free_or_own.w[i] = around.w[i] & (empty.w[i] | me.w[i]);
+        if (dany<N>(hit) && !dany<N>(free_or_own)) {
+            const DS<N> cand = dandn<N>(hit, dnbrs<N>(op));
+            ko = dcount<N>(cand) == 1;
+            if (ko) { s.ko_loc = bit_to_action<N>(dlowest<N>(cand)); s.ko_color = 3 - s.player; s.ko_age = 0; }
+        }
+        const DS<N> l1op = op & s.l1;
+        const DS<N> dead = dflood<N, T>(hit, l1op);          // distinct atari groups never touch: exactly the hit groups (board.cc:606-630)
+        op = dandn<N>(op, dead);
+        s.l1 = dandn<N>(s.l1, dead);
+        // own groups next to the captured stones gain a liberty; the ones that were in atari leave the set (a group that
+        // also touches the new stone is re-derived below)
+        const DS<N> l1me = me & s.l1;
+        const DS<N> freed = dflood<N, T>(dnbrs<N>(dead) & l1me, l1me);
+        s.l1 = dandn<N>(s.l1, freed);
+    }
+    int action = kInvalid;
+    if (placing) {
+        if (!ko) s.ko_age += 1;
+        TG_DW me.w[i] |= pb.w[i];
+        s.player = 3 - s.player; s.last2 = s.last1; s.last1 = act; s.step += 1;
+        if (s.step > max_step) s.terminated = 1;                                             // go_env.cc:67-73
+        action = act;
+    } else if (active) {                                                                     // board.cc:536-542, 554-558, 656-661
+        s.player = 3 - s.player; s.last2 = s.last1; s.last1 = kPass; s.step += 1;
+        if ((s.step > 1 && s.last2 == kPass) || s.step > max_step) s.terminated = 1;
+        action = D::P;
+    }
+    // repair the atari set around the new stone
+    DS<N> empty2; TG_DW empty2.w[i] = ~(me.w[i] | op.w[i]) & D::mask(i);
+    if constexpr (T == 1) {
+        DS<N> seen = dzero<N>();
+#pragma unroll 1
+        for (int j = 0; j < 5; ++j) {
+            const bool enemy = j < 4;
+            const DS<N> sh = j == 0 ? dshl<N>(pb, 1) : j == 1 ? dshr<N>(pb, 1) : j == 2 ? dshl<N>(pb, D::STR) : j == 3 ? dshr<N>(pb, D::STR) : pb;
+            const DS<N> col = dsel<N>(enemy, op, me);
+            DS<N> g = dandn<N>(sh & col, seen);
+            if (!dany<N>(g)) continue;
+            int libs; bool complete;
+            dflood_group<N, 1>(g, col, empty2, (!enemy && merge) ? (1 << 20) : 2, libs, complete);
+            if (!enemy && merge) s.l1 = dandn<N>(s.l1, g);
+            if (complete && libs == 1) s.l1 = s.l1 | g;
+            seen = seen | g;
+        }
+    } else {
+        const DS<N> sh = dsel<N>(sr != 0, dshr<N>(pb, sr), dshl<N>(pb, sl));
+        const DS<N> col = dsel<N>(enemy_lane, op, me);
+        DS<N> g = sh & col;
+        const bool whole = !enemy_lane && merge;
+        int libs; bool complete;
+        dflood_group<N, T>(g, col, empty2, whole ? (1 << 20) : 2, libs, complete);
+        const bool is1 = complete && libs == 1 && dany<N>(g);
+        if (vany<T>(merge)) s.l1 = dandn<N>(s.l1, tile_or<N, T>(dsel<N>(whole, g, dzero<N>())));
+        if (vany<T>(is1)) s.l1 = s.l1 | tile_or<N, T>(dsel<N>(is1, g, dzero<N>()));
+    }
+    return action;
+}
+
+}  // namespace inc
+}  // namespace tg
