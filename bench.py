@@ -367,6 +367,8 @@ def playout_kernel_name(env):
     t = env.lib.tg_env_playout_tile(env.n, env.G, env.tile)
     if t < 0:
         return "tg::k_playout_rows<%d>" % env.n
+    if t & 128:
+        return "tg::k_playout_inc<%d,%d,false>" % (env.n, t & 63)
     return ("tg::k_playout_wu<%d,%d>" if t & 64 else "tg::k_playout<%d,%d>") % (env.n, t & 63)
 
 

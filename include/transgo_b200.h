@@ -158,7 +158,8 @@ typedef struct TgMctsConfig {
 #define TG_MCTS_ERR_EDGES    32u    /* arena overflow: raise edge_cap */
 #define TG_MCTS_ERR_DEPTH    64u    /* path longer than max_depth */
 #define TG_MCTS_ERR_COUNT   128u    /* visit count above 65535 */
-#define TG_MCTS_ERR_ANY     (16u | 32u | 64u | 128u)
+#define TG_MCTS_ERR_NAN     512u    /* a node without a finite selectable score: the evaluator returned NaN (256 = bad action, see tg_mcts_advance) */
+#define TG_MCTS_ERR_ANY     (16u | 32u | 64u | 128u | 512u)
 
 int64_t tg_mcts_workspace_bytes(const TgMctsConfig* cfg);
 /* every game: empty board, empty tree, ACTIVE | NEED_EXPAND (WP_MCTS.reset_root before the net call, :595-597) */

@@ -1,6 +1,6 @@
 """Playout launch time vs batch size for each layout: flat = bound by the 120-ply dependency chain, linear = by throughput."""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 from transgo_b200.environment import BatchedGoEnv
 

@@ -1,7 +1,7 @@
 """Developer probe: per-ply loop statistics of k_playout_rows.  Needs a stats build of the library:
    nvcc ... -DTG_ROWS_STATS -c transgo_b200/csrc/tg_env.cu ; link it with the other objects into gpurun_out/rows_stats.so"""
 import sys, os, ctypes
-sys.path.insert(0, __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__))))
+sys.path.insert(0, __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__)))))
 import torch
 from transgo_b200 import _lib
 _lib.LIB_PATH = "/root/repo/gpurun_out/rows_stats.so"

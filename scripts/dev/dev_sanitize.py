@@ -1,7 +1,7 @@
 """Small run of every kernel family for compute-sanitizer (memcheck / racecheck / initcheck):
     compute-sanitizer --tool memcheck python scripts/dev_sanitize.py"""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 from transgo_b200 import _lib
 from transgo_b200.environment import BatchedGoEnv

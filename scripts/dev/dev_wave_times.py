@@ -1,6 +1,6 @@
 """Per-kernel device time of one MCTS wave (CUDA events around each C-ABI call, eager launches, 1024 games x 4 leaves)."""
 import os, sys, ctypes
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 from transgo_b200 import _lib
 from transgo_b200.mcts import BatchedMCTS, _declare

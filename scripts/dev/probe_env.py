@@ -1,6 +1,6 @@
 """Quick device-time probe of the board kernels (not the bench contract; see bench.py)."""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 from transgo_b200.environment import BatchedGoEnv
 

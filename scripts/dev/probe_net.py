@@ -1,6 +1,6 @@
 """Net forward timing at the MCTS wave batch (4096 positions) in several inference modes."""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 from transgo_b200.net import TransGoNetwork
 

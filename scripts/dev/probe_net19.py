@@ -1,6 +1,6 @@
 """Where does the fused forward spend its time at 19x19 (2048 positions = 512 games x 4 leaves)?"""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 from torch.profiler import profile, ProfilerActivity
 from transgo_b200.net import TransGoNetwork

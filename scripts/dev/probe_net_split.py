@@ -1,7 +1,7 @@
 """Does splitting the wave batch help the fused forward?  (a) one batch, (b) k sequential chunks (activations fit L2),
 (c) k chunks on k streams (tensor-bound convolutions of one chunk overlap the memory-bound glue of another)."""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 from transgo_b200.net import TransGoNetwork
 from transgo_b200.fused_net import FusedTransGoInference

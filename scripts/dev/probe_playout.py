@@ -1,6 +1,6 @@
 """Tile-width sweep of the playout kernel (device time, CUDA events; not the bench contract)."""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 from transgo_b200.environment import BatchedGoEnv
 

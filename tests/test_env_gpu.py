@@ -87,7 +87,9 @@ def _replay_trace_with_oracle(n, trace, game_ids, seed, max_step, no_eye=False):
 @pytest.mark.parametrize("n,G,tile,no_eye", [(9, 4096, 32, False), (9, 4096, 8, False), (9, 4096, 1, False),
                                              (9, 1024, 32, True), (19, 256, 32, False), (19, 256, 1, False),
                                              (9, 4096, 16, False), (9, 4099, 16 | 64, False), (9, 1001, 8 | 64, True), (19, 67, 4 | 64, False), (19, 200, 8 | 64, False), (9, 4096, -1, False), (9, 1000, -1, True), (9, 1, -1, False),
-                                             (19, 256, -1, False), (19, 37, -1, True)])
+                                             (19, 256, -1, False), (19, 37, -1, True),
+                                             (9, 4096, 8 | 128, False), (9, 999, 16 | 128, True), (9, 3000, 1 | 128, True), (19, 300, 32 | 128, False),
+                                             (19, 70, 8 | 128, True), (19, 33, 1 | 128, False)])
 def test_playout_matches_oracle(oracle_built, n, G, tile, no_eye):
     """G concurrent random playouts in one launch; a sample of games is replayed on the CPU."""
     from transgo_b200.environment import BatchedGoEnv
@@ -181,12 +183,12 @@ def test_step_kernel_per_ply_against_oracle(oracle_built, n, G, tile):
 
 def test_tiles_agree_bit_for_bit_at_full_size():
     """Size-independent property at the BASELINE C2 size and beyond: the tile widths (32, 8, 1 lanes per game), the lock-step variant
-    (8 | 64) and the row-per-lane layout (-1, a different formulation of the rules) are different programs and must produce identical final
-    states, scores and planes."""
+    (8 | 64), the row-per-lane layout (-1, a different formulation of the rules) and the incremental engine (n | 128, a third
+    formulation: dense boards + persistent atari set) are different programs and must produce identical final states, scores and planes."""
     from transgo_b200.environment import BatchedGoEnv
     G = 65536
     ref = None
-    for tile in (32, 8, 1, -1, 8 | 64):
+    for tile in (32, 8, 1, -1, 8 | 64, 8 | 128, 1 | 128, 0):
         env = BatchedGoEnv(G, board_size=9, tile=tile)
         env.playout(122, seed=99)
         out = (env.states.clone(), env.score(), env.encode(), env.legal_mask().clone())
@@ -212,8 +214,11 @@ def test_playout_is_resumable_and_deterministic():
     b = BatchedGoEnv(2048, tile=32); b.playout(50, seed=5); b.playout(72, seed=5)
     c = BatchedGoEnv(1024, tile=32); c.playout(122, seed=5, game_id0=1024)
     d = BatchedGoEnv(2048, tile=-1); d.playout(31, seed=5); d.playout(91, seed=5)
+    e = BatchedGoEnv(2048, tile=8 | 128); e.playout(45, seed=5); e.playout(1, seed=5); e.playout(76, seed=5)   # atari set rebuilt per launch
+    f = BatchedGoEnv(2048, tile=1 | 128); f.playout(77, seed=5); f.playout(45, seed=5)
     torch.cuda.synchronize()
     assert torch.equal(a.states, b.states) and torch.equal(a.states, d.states)
+    assert torch.equal(a.states, e.states) and torch.equal(a.states, f.states)
     assert torch.equal(a.states[:, 1024:], c.states)      # sharding by game id gives the same games (multi-GPU rule)
 
 

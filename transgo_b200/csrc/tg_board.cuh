@@ -719,5 +719,14 @@ __host__ __device__ __forceinline__ uint32_t mix32(uint64_t seed, uint64_t a, ui
     z ^= z >> 31;
     return (uint32_t)(z >> 32);
 }
+// the same draw with the (seed, a) part hoisted out of a loop: mix32(seed, a, b) == mix32_tail(mix32_head(seed, a), b)
+__host__ __device__ __forceinline__ uint64_t mix32_head(uint64_t seed, uint64_t a) { return seed + a * 0x9E3779B97F4A7C15ull; }
+__host__ __device__ __forceinline__ uint32_t mix32_tail(uint64_t head, uint64_t b) {
+    uint64_t z = head + b * 0xBF58476D1CE4E5B9ull;
+    z ^= z >> 30; z *= 0xBF58476D1CE4E5B9ull;
+    z ^= z >> 27; z *= 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    return (uint32_t)(z >> 32);
+}
 
 }  // namespace tg

@@ -222,7 +222,7 @@ k_playout_inc(uint4* __restrict__ states, long long G, int plies, int max_step, 
     s.last1 = p0.last1; s.last2 = p0.last2; s.ko_loc = p0.ko_loc; s.ko_age = p0.ko_age; s.step = p0.step; s.player = p0.player;
     s.ko_color = p0.ko_color; s.terminated = p0.terminated;
     s.l1 = atari_from_scratch<N, T>(s.a, s.b);
-    const unsigned long long gid = (unsigned long long)(game_id0 + g);
+    const unsigned long long hash_head = mix32_head(seed, (unsigned long long)(game_id0 + g));
     int played = 0;
     for (int t = 0; t < plies; t += 2) {
 #pragma unroll
@@ -230,8 +230,8 @@ k_playout_inc(uint4* __restrict__ states, long long G, int plies, int max_step, 
             if (t + h < plies) {                                   // kernel-uniform
                 int action = kInvalid;
                 if (vany<T>(!s.terminated)) {
-                    action = h == 0 ? ply<N, T, NOEYE>(s, s.a, s.b, max_step, seed, gid, sl, sr, enemy_lane)
-                                    : ply<N, T, NOEYE>(s, s.b, s.a, max_step, seed, gid, sl, sr, enemy_lane);
+                    action = h == 0 ? ply<N, T, NOEYE>(s, s.a, s.b, max_step, hash_head, sl, sr, enemy_lane)
+                                    : ply<N, T, NOEYE>(s, s.b, s.a, max_step, hash_head, sl, sr, enemy_lane);
                     played += action != kInvalid;
                 }
                 if (trace && exists && lead) trace[(long long)(t + h) * G + g] = (int16_t)action;
@@ -476,8 +476,10 @@ int tg_env_score(int n, const void* states, int64_t G, float komi, float* score,
 /* the layout tg_env_playout runs for (n, G, tile): TG_TILE_ROWS or lanes per game (| TG_TILE_UNIFORM | TG_TILE_INC) */
 int tg_env_playout_tile(int n, int64_t G, int tile) {
     if (tile == 0) {
-        if (n == 19) return TG_TILE_ROWS;
-        return G < 24576 ? (8 | TG_TILE_INC) : (1 | TG_TILE_INC);
+        // measured on B200 (profiles/r02_playout_layouts.txt): the incremental engine wins at every size; lanes per game shrink
+        // as the batch grows (9x9: 8 lanes -> 1 thread at ~12 k games; 19x19: 32 -> 16 -> 8 lanes -> 1 thread)
+        if (n == 19) return (G < 768 ? 32 : G < 1536 ? 16 : G < 8192 ? 8 : 1) | TG_TILE_INC;
+        return (G < 12288 ? 8 : 1) | TG_TILE_INC;
     }
     if (tile > 0 && (tile & TG_TILE_INC)) {
         const int t = tile & (TG_TILE_UNIFORM - 1);

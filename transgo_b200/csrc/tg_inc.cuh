@@ -242,7 +242,7 @@ template <int N> __device__ __forceinline__ int dselect(const DS<N>& a, int k) {
 //   role lanes (T >= 8): lane j of a tile, j < 4: the enemy group touching the new stone in direction j; j >= 4: the group
 //   the new stone joins.  sl / sr = this lane's shift (left or right amount, the other 0).
 template <int N, int T, bool NOEYE>
-__device__ __forceinline__ int ply(Game<N>& s, DS<N>& me, DS<N>& op, int max_step, unsigned long long seed, unsigned long long gid,
+__device__ __forceinline__ int ply(Game<N>& s, DS<N>& me, DS<N>& op, int max_step, unsigned long long hash_head,
                                    int sl, int sr, bool enemy_lane) {
     using D = DGeo<N>;
     const bool active = !s.terminated;
@@ -255,7 +255,7 @@ __device__ __forceinline__ int ply(Game<N>& s, DS<N>& me, DS<N>& op, int max_ste
     if (NOEYE) lg = dandn<N>(lg, dtrue_eyes<N>(me, op));                                       // board.cc:510-512
     const int nl = dcount<N>(lg);
     const bool placing = active && nl > 0;
-    const uint32_t r = mix32(seed, gid, (unsigned long long)s.step);
+    const uint32_t r = mix32_tail(hash_head, (unsigned long long)s.step);
     const int bit = dselect<N>(lg, placing ? (int)(((unsigned long long)r * (unsigned)nl) >> 32) : 0);
     const int act = bit_to_action<N>(bit);
     DS<N> pb; TG_DW pb.w[i] = (placing && i == (bit >> 5)) ? (1u << (bit & 31)) : 0u;

@@ -139,6 +139,13 @@ __device__ __forceinline__ void add_ons(int* h, uint4* hot, const int* path, int
 }
 
 // ---------------------------------------------------------------------------------------------- selection
+// order-preserving map double -> u64 (finite values and infinities; a NaN maps above everything and is caught by the
+// equality test afterwards), so that the warp arg-max is two REDUX.MAX instead of a five-step shuffle butterfly
+__device__ __forceinline__ unsigned long long ordered_bits(double x) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(x);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+
 template <int N>
 __global__ void __launch_bounds__(kThreads) k_select(View v) {
     using GG = Geo<N>;
@@ -156,7 +163,11 @@ __global__ void __launch_bounds__(kThreads) k_select(View v) {
     uint2* cold = cold_of<N>(v, buf, g);
     const uint32_t* kid = kid_of<N>(v, buf, g);
     const uint4* nodes = nodes_of<N>(v, buf, g);
-    const uint32_t root_kid = pack_kid((int)nodes[GG::SQ].x, (int)nodes[GG::SQ].y);     // the root's edges: read once per wave
+    const uint4 root_info = nodes[GG::SQ];                            // the root's edges: read once per wave
+    const uint4 root_meta = nodes[GG::SQ - 1];                        // last1 | last2, ko, step | player | ko_color, terminated
+    const uint32_t root_kid = pack_kid((int)root_info.x, (int)root_info.y);
+    const bool root_after_pass = (int16_t)(root_meta.x & 0xffffu) == (int16_t)kPass;
+    const int root_step = (int)(root_meta.z & 0xffffu);
     const double* p64 = v.root_prior64 + (size_t)g * GG::A;
     const bool noisy = (flags & TG_MCTS_NOISY) != 0;
     const float c1f = (float)v.c1, c2f = (float)v.c2;
@@ -168,44 +179,64 @@ __global__ void __launch_bounds__(kThreads) k_select(View v) {
         int node = 0, depth = 0;
         int Np = h[H_ROOTN], onsp = h[H_ROOTONS];
         uint32_t pk_sel = 0, kid_cur = root_kid;
+        bool after_pass = root_after_pass;                            // the move that led to `node` was a pass
         while (true) {                                                                // :623-627
             // where the node's edges live came with the edge that led here: no dependent load of the node record
             const int eb = (int)(kid_cur & 0x3fffffu), K = (int)(kid_cur >> 22);
             st_fan += K;
+            // every load of the scan is issued before the first use (no branch in between): one memory round trip per node
+            uint4 q[MAXR]; uint32_t ch[MAXR], kd[MAXR]; double pr64[MAXR];
+            const bool noisy_root = noisy && node == 0;
+#pragma unroll
+            for (int r = 0; r < MAXR; ++r) {
+                if (N == 9 || 32 * r < K) {                           // 19x19: skip whole rounds beyond K (warp-uniform)
+                    const int k = lane + 32 * r;
+                    const int kk = k < K ? k : K - 1;
+                    q[r] = hot[eb + kk];
+                    ch[r] = cold[eb + kk].y;                          // child node of the edge (cold record), so that the descent
+                    kd[r] = kid[eb + kk];                             // needs no second trip; kd: where the child's edges live
+                    pr64[r] = noisy_root ? p64[kk] : 0.0;
+                } else { q[r] = make_uint4(0, 0, 0, 0); ch[r] = 0xffffffffu; kd[r] = 0; pr64[r] = 0.0; }
+            }
             const double sq = __dsqrt_rn((double)(Np + onsp));
-            double sc[MAXR]; uint32_t pk[MAXR], ch[MAXR], kd[MAXR];            // ch: child node of each scanned edge (cold record), loaded
-            double best = -1.0e300;                                  // with the hot record so that the descent needs no second trip
+            unsigned long long ob[MAXR];
+            unsigned hi_max = 0;
 #pragma unroll
             for (int r = 0; r < MAXR; ++r) {
                 const int k = lane + 32 * r;
-                sc[r] = -1.0e300; pk[r] = 0; ch[r] = 0xffffffffu; kd[r] = 0;
-                if (k < K) {
-                    const uint4 q = hot[eb + k];
-                    ch[r] = cold[eb + k].y;
-                    kd[r] = kid[eb + k];
-                    const float prior = __uint_as_float(q.x), W = __uint_as_float(q.y), var = __uint_as_float(q.z);
-                    const int nc = pk_n(q.w), oc = pk_ons(q.w);
-                    // prior_score = c1 * prior * sqrt(Np + ons_p) / (Nc + ons_c + 1)          (:718-719)
-                    double ps = (noisy && node == 0) ? __dmul_rn(v.c1, p64[k]) : (double)__fmul_rn(c1f, prior);
-                    ps = __ddiv_rn(__dmul_rn(ps, sq), (double)(nc + oc + 1));
-                    // var_score = c2 * sqrt(1 + clip(var, 0, 3)); float64 for a never-visited child      (:721-722)
-                    double vs;
-                    if (nc == 0) vs = v.c2;
-                    else {
-                        const float cv = var < 0.0f ? 0.0f : (var > 3.0f ? 3.0f : var);
-                        vs = (double)__fmul_rn(c2f, __fsqrt_rn(__fadd_rn(1.0f, cv)));
-                    }
-                    const double qv = (double)(-__fdiv_rn(W, (float)(nc + 1)));                 // -child.value() (:724, :67-68)
-                    sc[r] = __dadd_rn(__dadd_rn(ps, vs), qv);
-                    pk[r] = q.w;
-                }
-                best = sc[r] > best ? sc[r] : best;
+                const float prior = __uint_as_float(q[r].x), W = __uint_as_float(q[r].y), var = __uint_as_float(q[r].z);
+                const int nc = pk_n(q[r].w), oc = pk_ons(q[r].w);
+                // prior_score = c1 * prior * sqrt(Np + ons_p) / (Nc + ons_c + 1)          (:718-719)
+                double ps = noisy_root ? __dmul_rn(v.c1, pr64[r]) : (double)__fmul_rn(c1f, prior);
+                ps = __ddiv_rn(__dmul_rn(ps, sq), (double)(nc + oc + 1));
+                // var_score = c2 * sqrt(1 + clip(var, 0, 3)); float64 for a never-visited child      (:721-722)
+                const float cv = var < 0.0f ? 0.0f : (var > 3.0f ? 3.0f : var);
+                const double vsf = (double)__fmul_rn(c2f, __fsqrt_rn(__fadd_rn(1.0f, cv)));
+                const double vs = nc == 0 ? v.c2 : vsf;
+                const double qv = (double)(-__fdiv_rn(W, (float)(nc + 1)));                 // -child.value() (:724, :67-68)
+                const double sc = __dadd_rn(__dadd_rn(ps, vs), qv);
+                ob[r] = k < K ? ordered_bits(sc) : 0ull;
+                const unsigned hi = (unsigned)(ob[r] >> 32);
+                hi_max = hi > hi_max ? hi : hi_max;
             }
-            best = warp_max(best);
-            // exact ties, ascending action order (:708-713)
+            hi_max = __reduce_max_sync(0xffffffffu, hi_max);
+            unsigned lo_max = 0;
+#pragma unroll
+            for (int r = 0; r < MAXR; ++r) {
+                const unsigned lo = (unsigned)(ob[r] >> 32) == hi_max ? (unsigned)ob[r] : 0u;
+                lo_max = lo > lo_max ? lo : lo_max;
+            }
+            lo_max = __reduce_max_sync(0xffffffffu, lo_max);
+            const unsigned long long best = ((unsigned long long)hi_max << 32) | lo_max;
+            // exact ties, ascending action order (:708-713).  A NaN score (ordered above +inf, never equal to a real one) or
+            // an all-NaN node leaves no candidate: fail loudly instead of walking a bogus edge.
             unsigned bal[MAXR]; int total = 0;
 #pragma unroll
-            for (int r = 0; r < MAXR; ++r) { bal[r] = __ballot_sync(0xffffffffu, sc[r] == best); total += __popc(bal[r]); }
+            for (int r = 0; r < MAXR; ++r) {
+                const bool is_best = ob[r] == best && ob[r] > 0x000fffffffffffffull && ob[r] < 0xfff0000000000000ull;   // finite
+                bal[r] = __ballot_sync(0xffffffffu, is_best); total += __popc(bal[r]);
+            }
+            if (total == 0) { err |= TG_MCTS_ERR_NAN; break; }
             int j = 0;
             if (total > 1) {
                 if (v.tie_mode == 1) j = (int)(((unsigned long long)mix32(v.tie_seed, (unsigned long long)(v.game_id0 + g), (unsigned long long)tie) * (unsigned)total) >> 32);
@@ -219,7 +250,7 @@ __global__ void __launch_bounds__(kThreads) k_select(View v) {
                 if (ksel < 0 && j < c) {
                     const int src = nth_bit(bal[r], j);
                     ksel = src + 32 * r;
-                    pk_sel = __shfl_sync(0xffffffffu, pk[r], src);
+                    pk_sel = __shfl_sync(0xffffffffu, q[r].w, src);
                     ch_sel = __shfl_sync(0xffffffffu, ch[r], src);
                     kd_sel = __shfl_sync(0xffffffffu, kd[r], src);
                 } else if (ksel < 0) j -= c;
@@ -230,18 +261,20 @@ __global__ void __launch_bounds__(kThreads) k_select(View v) {
             depth += 1;
             const int child = (int)ch_sel;
             if (child < 0) break;
+            after_pass = pk_act(pk_sel) == GG::P;
             Np = pk_n(pk_sel); onsp = pk_ons(pk_sel); node = child; kid_cur = kd_sel;
         }
         if (err) break;
         st_desc += 1; st_depth += depth;
         __syncwarp();
-        // the leaf: step from its parent's state (:629).  `done` follows from the parent's meta alone.
+        // the leaf: step from its parent's state (:629).  `done` follows from what the descent already knows: every move
+        // (a pass too) advances step_count by one, and the parent's last move is the edge that led to it.
         const int action = pk_act(pk_sel);
-        Pos<N> s; pos_load<N>(s, nodes + (size_t)node * (GG::SQ + 1), 0, 1, 0);
-        const int step2 = s.step + 1;
+        const int step2 = root_step + depth;
         const bool is_pass = action == GG::P;
-        const bool done = (is_pass && s.last1 == kPass && step2 > 1) || step2 > v.max_step;
+        const bool done = (is_pass && after_pass && step2 > 1) || step2 > v.max_step;
         if (done) {                                                                   // :638-642
+            Pos<N> s; pos_load<N>(s, nodes + (size_t)node * (GG::SQ + 1), 0, 1, 0);
             Groups<N> gr;
             if (!is_pass) analyse_groups<N, 32, false>(s.stones[0], s.stones[1], s.player, gr);
             else { gr.l1[0] = gr.l1[1] = gr.l2[0] = gr.l2[1] = gr.lives = bb_zero<N>(); }

@@ -120,8 +120,10 @@ class BatchedGoEnv:
 
     ``tile`` = lanes cooperating on one game: 0 lets the library choose from (board, G) by measurement (see
     ``playout_layout``); 32 / 16 / 8 / 4 / 2 / 1 force a bitboard tile; ``n | 64`` (n in 16, 8, 4) runs the tiles that share
-    a warp in lock step; -1 is the row-per-lane layout.  The last two only exist for ``playout``; the other kernels then
-    fall back to the library's choice.  Every layout produces identical results (tests/test_env_gpu.py).
+    a warp in lock step; ``n | 128`` (n in 32, 16, 8, 1) is the incremental engine (dense bit-string boards, atari set kept
+    across plies: csrc/tg_inc.cuh -- what the library picks); -1 is the row-per-lane layout.  The last three only exist for
+    ``playout``; the other kernels then fall back to the library's choice.  Every layout produces identical results
+    (tests/test_env_gpu.py).
     """
 
     def __init__(self, num_games, board_size=9, max_step=None, komi=7.5, device="cuda", tile=0):
@@ -196,7 +198,12 @@ class BatchedGoEnv:
     def playout_layout(self):
         """Name of the kernel ``playout`` launches for this batch: lanes per game, or 'rows' (one board row per lane)."""
         t = self.lib.tg_env_playout_tile(self.n, self.G, self.tile)
-        return "rows" if t < 0 else ("%d lanes per game, %d games per warp in lock step" % (t & 63, 32 // (t & 63)) if t & 64 else str(t))
+        if t < 0:
+            return "rows"
+        if t & 128:
+            w = t & 63
+            return "incremental, " + ("one thread per game" if w == 1 else "%d lanes per game, %d games per warp in lock step" % (w, 32 // w))
+        return "%d lanes per game, %d games per warp in lock step" % (t & 63, 32 // (t & 63)) if t & 64 else str(t)
 
     # ---- helpers (format conversion only)
     def unpack_legal(self, legal=None):

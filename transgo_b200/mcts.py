@@ -19,7 +19,8 @@ from .environment import DEFAULT_MAX_STEP, GoState
 ACTIVE, NEED_EXPAND, NOISY = 1, 2, 4
 ERR_BITS = {16: "node arena overflow (raise node_cap)", 32: "edge arena overflow (raise edge_cap)",
             64: "search path deeper than max_depth", 128: "visit count above 65535",
-            256: "update_with_action: action is not a child of the root"}
+            256: "update_with_action: action is not a child of the root",
+            512: "no finite selection score at a node: the evaluator returned NaN / inf policy or value"}
 
 
 class TgMctsConfig(ctypes.Structure):
@@ -144,7 +145,7 @@ class BatchedMCTS:
         _lib.check(self.lib.tg_mcts_status(self._cfg, self._w(), _lib.ptr(self.status), _lib.ptr(self.sims), self._s()),
                    "tg_mcts_status")
         st = self.status.cpu().numpy()
-        bad = st & (16 | 32 | 64 | 128 | 256)
+        bad = st & (16 | 32 | 64 | 128 | 256 | 512)
         if bad.any():
             g = int(np.nonzero(bad)[0][0])
             msgs = [m for b, m in ERR_BITS.items() if bad[g] & b]
