@@ -52,6 +52,11 @@ def main():
         a.record()
         worker.search.total_sims()
         st = selfplay_round(worker, model, ring, pacing, src=0, dst=0, max_moves=args.max_moves, refresh=ev.refresh)
+        if rank == 0:
+            # the throttle of self_play.py:970-980 / trainer.py:94-105: self-play waits while the trainer is behind the
+            # train/play ratio; here the "trainer" is the stand-in above, so it just catches up
+            while pacing.selfplay_should_wait():
+                pacing.now_train_steps += 1
         sims = worker.search.total_sims()
         b.record()
         torch.cuda.synchronize()

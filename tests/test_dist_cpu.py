@@ -29,7 +29,9 @@ def _worker(rank, world, port, q):
     z = torch.full([n], 1.0 - 2 * rank); own = torch.full([n, 81], float(-rank))
     got = gather_trajectories(obs, pi, z, own, dst=0)
     empty = gather_trajectories(obs[:0], pi[:0], z[:0], own[:0], dst=0) if True else None
-    res = dict(rank=rank, digest=digest, shard=(g0, cnt))
+    # uneven shards: the row-count exchange also carries each rank's game count (selfplay_round sums them for the pacing counters)
+    got2, extras = gather_trajectories(obs, pi, z, own, dst=1, extra=[cnt, 7 + rank])
+    res = dict(rank=rank, digest=digest, shard=(g0, cnt), extras=extras.tolist(), got2=None if got2 is None else tuple(got2[0].shape))
     if rank == 0:
         o, p, zz, w = got
         res.update(shapes=(tuple(o.shape), tuple(p.shape), tuple(zz.shape), tuple(w.shape)),
@@ -54,6 +56,8 @@ def test_broadcast_and_gather_world2():
     assert res[0]["shapes"] == ((8, 10, 9, 9), (8, 82), (8,), (8, 81))
     assert res[0]["ranks_seen"] == [0.0, 1.0] and res[0]["z"] == [1.0] * 3 + [-1.0] * 5
     assert res[0]["empty"] == (0, 10, 9, 9)
+    assert res[0]["extras"] == res[1]["extras"] == [[513, 7], [512, 8]]     # every rank sees every rank's counts
+    assert res[0]["got2"] is None and res[1]["got2"] == (8, 10, 9, 9)        # any rank can be the replay owner
 
 
 def test_augment8_matches_the_reference_loop():

@@ -389,3 +389,53 @@ def test_select_action_from_a_mid_game_position_matches_oracle(oracle_built):
         counts = ora.visit_counts()
         assert counts[act] == counts.max() or counts[act] >= 2     # temperature 0.12 draw: a heavily visited move
         assert env.getStep(agent.root.state) == plies + 1 and env.checkAction(s, act if act != 81 else -1)
+
+
+# ------------------------------------------------------------------ robustness
+def test_capacity_limits_and_nan_fail_loudly(oracle_built):
+    """edge_cap above the 22-bit edge-base field is refused (library and host side), a NaN from the evaluator raises a
+    per-game error instead of walking a bogus edge, and max_depth defaults to the moves a game can still have."""
+    from transgo_b200 import _lib
+    from transgo_b200.mcts import BatchedMCTS
+    ev = cpu_provider(1, 4)
+    with pytest.raises(ValueError):
+        BatchedMCTS(ev, 1, num_simulation=8, edge_cap=(1 << 22) + 1)
+    eng = BatchedMCTS(ev, 1, num_simulation=8, edge_cap=1 << 22, node_cap=64)       # the boundary itself is fine
+    assert eng.cfg.max_depth == 121 and eng.cfg.edge_cap == 1 << 22
+    eng.cfg.edge_cap = (1 << 22) + 1
+    assert eng.lib.tg_mcts_workspace_bytes(eng._cfg) < 0 and b"edge_cap" in eng.lib.tg_last_error()
+    assert BatchedMCTS(ev, 1, board_size=19, num_simulation=2500).cfg.edge_cap <= 1 << 22      # the default caps clamp
+    calls = [0]
+
+    def nan_net(obs):
+        p, v = ev(obs)
+        calls[0] += 1
+        if calls[0] >= 3:
+            v = torch.full_like(v, float("nan"))
+        return p, v
+    bad = BatchedMCTS(nan_net, 2, num_simulation=40, tie_seed=3)
+    with pytest.raises(_lib.TransgoLibraryError, match="NaN"):
+        for _ in range(30):
+            bad.run_wave()
+        bad.check_status()
+
+
+def test_continuous_selfplay_is_throttled_by_the_pacing_counters(oracle_built):
+    """self_play.py:970-980: after a finished game the actor waits while now_train_steps / now_play_steps is below the
+    train/play ratio.  play_continuous calls wait_fn (the trainer catching up) until the predicate clears, and returns
+    early (throttled=True) when there is nobody to wait for."""
+    from transgo_b200.replay import Pacing
+    from transgo_b200.selfplay import SelfPlayWorker
+    w = SelfPlayWorker(cpu_provider(7, 6), 4, num_simulation=12, max_step=6, tie_seed=1)
+    pacing = Pacing()
+    waits = [0]
+
+    def trainer_catches_up():
+        waits[0] += 1
+        pacing.now_train_steps += 1
+    out = w.play_continuous(min_positions=30, augment=False, pacing=pacing, wait_fn=trainer_catches_up)
+    assert out["games"] == pacing.now_play_games >= 5 and pacing.now_play_steps == out["positions"]
+    assert waits[0] >= 1 and not pacing.selfplay_should_wait() and out["throttled"] is False
+    pacing.now_train_steps = 0
+    out2 = w.play_continuous(min_positions=1000, augment=False, pacing=pacing)      # no trainer: hand control back
+    assert out2["throttled"] is True and out2["positions"] < 1000

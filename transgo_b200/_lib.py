@@ -88,7 +88,18 @@ def ptr(t):
     return None if t is None else ctypes.c_void_p(t.data_ptr())
 
 
-def stream_ptr(stream=None):
+def stream_ptr(stream=None, device=None):
+    """cudaStream_t of torch's current stream.  The C library launches on the CURRENT CUDA device (it never calls
+    cudaSetDevice), so an object whose tensors live on `device` must be driven with that device current: anything else
+    would run kernels on one GPU against another GPU's pointers.  Fail loudly instead."""
     import torch
-    s = torch.cuda.current_stream() if stream is None else stream
+    if device is not None:
+        dev = torch.device(device)
+        idx = torch.cuda.current_device() if dev.index is None else dev.index
+        if idx != torch.cuda.current_device():
+            raise TransgoLibraryError("tensors live on cuda:%d but the current device is cuda:%d: wrap the call in "
+                                      "`with torch.cuda.device(%d)` (or torch.cuda.set_device)" % (idx, torch.cuda.current_device(), idx))
+        s = torch.cuda.current_stream(idx) if stream is None else stream
+    else:
+        s = torch.cuda.current_stream() if stream is None else stream
     return ctypes.c_void_p(s.cuda_stream)

@@ -376,10 +376,11 @@ template <int N, int T> void launch_legal(cudaStream_t st, const uint4* states, 
 template <int N, int T> void launch_encode(cudaStream_t st, const uint4* states, long long G, float* planes) {
     constexpr int GPC = kThreads / T;
     const size_t smem = planes_smem_bytes<N>(GPC);
-    static bool attr_done = false;
-    if (!attr_done && smem > 48 * 1024) {
+    static unsigned long long attr_done = 0;                 // one bit per device: the attribute is per device, not per process
+    int dev = 0; cudaGetDevice(&dev);
+    if (smem > 48 * 1024 && !((attr_done >> (dev & 63)) & 1ull)) {
         cudaFuncSetAttribute(k_encode<N, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr_done = true;
+        attr_done |= 1ull << (dev & 63);
     }
     k_encode<N, T><<<(unsigned)((G + GPC - 1) / GPC), kThreads, smem, st>>>(states, G, planes);
 }

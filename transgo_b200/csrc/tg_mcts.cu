@@ -712,6 +712,9 @@ static int check_cfg(const TgMctsConfig* c) {
     if (c->num_games <= 0 || c->readouts < 1 || c->readouts > kMaxReadouts) return set_err(-1, "tg_mcts: bad num_games / readouts");
     if (c->wu_loss < 0 || c->wu_loss * c->readouts > 127) return set_err(-1, "tg_mcts: wu_loss * readouts must be <= 127");
     if (c->node_cap < 1 || c->edge_cap < c->n * c->n + 1 || c->max_depth < 2) return set_err(-1, "tg_mcts: capacities too small");
+    // per-edge child info packs (edge base : 22 | edge count : 10) into one word (pack_kid): larger arenas would alias
+    if (c->edge_cap > (1 << 22)) return set_err(-1, "tg_mcts: edge_cap must be <= 4194304 (edge base is a 22-bit field)");
+    if (c->n * c->n + 1 > 1023) return set_err(-1, "tg_mcts: more than 1023 actions per node");
     return 0;
 }
 static inline unsigned warp_blocks(long long warps) { return (unsigned)((warps * 32 + kThreads - 1) / kThreads); }

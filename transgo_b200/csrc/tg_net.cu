@@ -466,10 +466,11 @@ extern "C" int tg_net_attention(const void* qkv, const void* x, float gamma, con
         k_attention<<<(unsigned)B, kAttWarps * 32, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)qkv, (const __nv_bfloat16*)x, gamma, scale,
                                                                                shift, (__nv_bfloat16*)out, P);
     } else {
-        static bool attr_done = false;
-        if (!attr_done) {
+        static unsigned long long attr_done = 0;             // one bit per device: the attribute is per device, not per process
+        int dev = 0; cudaGetDevice(&dev);
+        if (!((attr_done >> (dev & 63)) & 1ull)) {
             cudaFuncSetAttribute(k_attention_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBigSmem);
-            attr_done = true;
+            attr_done |= 1ull << (dev & 63);
         }
         k_attention_big<<<(unsigned)B, kBigWarps * 32, kBigSmem, (cudaStream_t)stream>>>((const __nv_bfloat16*)qkv, (const __nv_bfloat16*)x, gamma,
                                                                                           scale, shift, (__nv_bfloat16*)out, P);

@@ -152,7 +152,7 @@ class BatchedGoEnv:
         self.reset()
 
     def _s(self):
-        return _lib.stream_ptr()
+        return _lib.stream_ptr(device=self.device)
 
     def reset(self):
         _lib.check(self.lib.tg_env_reset(self.n, _lib.ptr(self.states), self.G, self._s()), "tg_env_reset")

@@ -129,7 +129,7 @@ class FusedTransGoInference:
         s_out = torch.empty_like(x) if want_sum else None
         a_out = torch.empty_like(x) if want_act else None
         _lib.check(self.lib.tg_net_add_bn_relu(_lib.ptr(x), _lib.ptr(y), float(alpha), _lib.ptr(ybias), _lib.ptr(scale), _lib.ptr(shift),
-                                               _lib.ptr(s_out), _lib.ptr(a_out), rows, C, _lib.stream_ptr()),
+                                               _lib.ptr(s_out), _lib.ptr(a_out), rows, C, _lib.stream_ptr(device=x.device)),
                    "tg_net_add_bn_relu")
         return s_out, a_out
 
@@ -143,7 +143,7 @@ class FusedTransGoInference:
             # scores, softmax, att^T . v and the junction in ONE hand-written kernel (csrc/tg_net.cu: k_attention)
             act = torch.empty_like(x)
             _lib.check(self.lib.tg_net_attention(_lib.ptr(qkv), _lib.ptr(x), p["gamma"], _lib.ptr(p["s"]), _lib.ptr(p["t"]),
-                                                 _lib.ptr(act), B, self.P, dq, C, _lib.stream_ptr()), "tg_net_attention")
+                                                 _lib.ptr(act), B, self.P, dq, C, _lib.stream_ptr(device=x.device)), "tg_net_attention")
             return act
         q, k, v = qkv[..., :dq], qkv[..., dq:2 * dq], qkv[..., 2 * dq:]
         att = torch.softmax(torch.bmm(q, k.transpose(1, 2)), dim=-1)           # [B, P, P], rows = query position

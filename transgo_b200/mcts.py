@@ -70,7 +70,7 @@ class BatchedMCTS:
 
     def __init__(self, evaluator, num_games, board_size=9, num_simulation=210, c_puct1=3, c_puct2=0.05, wu_loss=2,
                  parallel_readouts=4, max_step=None, komi=7.5, tie_mode="hash", tie_seed=0, game_id0=0,
-                 node_cap=None, edge_cap=None, max_depth=64, device="cuda", check_every=4, graph_waves=False):
+                 node_cap=None, edge_cap=None, max_depth=None, device="cuda", check_every=4, graph_waves=False):
         import torch
         self.torch = torch
         if not torch.cuda.is_available():
@@ -94,7 +94,12 @@ class BatchedMCTS:
         max_step = DEFAULT_MAX_STEP.get(self.n, 2 * self.P) if max_step is None else int(max_step)
         # every net-evaluated simulation adds one node; the kept subtree can carry several moves' worth of visits
         node_cap = node_cap or (6 * self.num_simulation + 64)
-        edge_cap = edge_cap or max(self.A, int(node_cap * self.A * 0.85))
+        # the per-edge child info is (edge base : 22 | count : 10): an arena holds at most 2^22 edges (the library checks too)
+        edge_cap = edge_cap or min(1 << 22, max(self.A, int(node_cap * self.A * 0.85)))
+        if edge_cap > (1 << 22):
+            raise ValueError("edge_cap %d exceeds 4194304 (22-bit edge base in the per-edge child record)" % edge_cap)
+        # the reference has no depth limit; a path can be as long as the moves left in the game
+        max_depth = int(max_depth) if max_depth else max_step + 1
         self.cfg = TgMctsConfig(self.n, self.G, self.R, self.num_simulation, int(wu_loss), max_step, node_cap, edge_cap,
                                 max_depth, 1 if tie_mode == "hash" else 0, float(c_puct1), float(c_puct2), float(komi), 0,
                                 int(tie_seed), int(game_id0))
@@ -121,7 +126,7 @@ class BatchedMCTS:
 
     # ---------------------------------------------------------------- plumbing
     def _s(self):
-        return _lib.stream_ptr()
+        return _lib.stream_ptr(device=self.device)
 
     def _w(self):
         return _lib.ptr(self.ws)

@@ -54,12 +54,26 @@ class ReplayRing:
 
     # ---- reference pickle layout (replay_buffer.py:49-87, transgo.py:225-250)
     def save(self, path=None):
+        """The dict ReplayMemory_Random.save() returns for capacity <= 1.5 M (replay_buffer.py:51-56).  `data` is what
+        `np.array([blank_trans] * capacity, dtype=object)` (replay_buffer.py:27) makes of a list of 4-tuples: an object array
+        of shape [capacity, 4] whose row i holds (obs float64 [C,n,n], pi float64 [A], z float, own float64 [P]); unwritten
+        rows keep the reference's blank transition.  Built column by column from whole-array host copies (no per-row device
+        traffic, no Python-level row loop)."""
         n = len(self)
-        data = np.empty(self.capacity, dtype=object)
-        o, p, z, w = (t.cpu().numpy() for t in (self.obs.float(), self.pi, self.z, self.own))
-        blank = (np.zeros((self.channels, self.n, self.n)), np.zeros(self.n * self.n + 1), 0.0, np.zeros(self.n * self.n))
-        for i in range(self.capacity):
-            data[i] = (o[i], p[i], float(z[i]), w[i]) if i < n or self.full else blank
+        o, p, z, w = (t[:n].detach().cpu().numpy() for t in (self.obs.float(), self.pi, self.z, self.own))
+        o, p, w = o.astype(np.float64), p.astype(np.float64), w.astype(np.float64)
+        data = np.empty((self.capacity, 4), dtype=object)
+        if n:
+            data[:n, 0] = np.fromiter(iter(o), dtype=object, count=n)      # row views of one host array
+            data[:n, 1] = np.fromiter(iter(p), dtype=object, count=n)
+            data[:n, 2] = z.astype(np.float64).tolist()
+            data[:n, 3] = np.fromiter(iter(w), dtype=object, count=n)
+        if n < self.capacity:
+            blank = (np.zeros((self.channels, self.n, self.n)), np.zeros(self.n * self.n + 1), 0.0, np.zeros(self.n * self.n))
+            for c in range(4):
+                col = np.empty(self.capacity - n, dtype=object)
+                col.fill(blank[c])
+                data[n:, c] = col
         out = {"buffer_capacity": self.capacity, "index": self.index, "full": self.full, "data": data, "save_len": self.capacity}
         if path:
             with open(path, "wb") as f:
@@ -67,19 +81,30 @@ class ReplayRing:
         return out
 
     def load(self, info):
+        """replay_buffer.py:72-87 for either writer's file.  A whole-capacity file (the <= 1.5 M branch, ours or the
+        reference's) restores index / full exactly; a partial file (the reference's > 1.5 M branch: the last save_len rows)
+        is appended at the current write position like the reference's load_index."""
         if isinstance(info, str):
             with open(info, "rb") as f:
                 info = pickle.load(f)
-        rows = info["data"][:info["save_len"]]
-        n_valid = info["save_len"] if info.get("full", False) else info.get("index", info["save_len"])
-        rows = rows[:n_valid] if n_valid else rows
+        save_len = int(info["save_len"])
+        rows = info["data"][:save_len]
+        whole = "full" in info and save_len == int(info["buffer_capacity"])
+        if whole:
+            n_valid = save_len if info["full"] else int(info["index"])
+            rows = rows[:n_valid]
         if len(rows) == 0:
             return self.full
         obs = torch.from_numpy(np.stack([r[0] for r in rows]).astype(np.float32)).to(self.device)
         pi = torch.from_numpy(np.stack([r[1] for r in rows]).astype(np.float32)).to(self.device)
         z = torch.tensor([float(r[2]) for r in rows], dtype=torch.float32, device=self.device)
         own = torch.from_numpy(np.stack([r[3] for r in rows]).astype(np.float32)).to(self.device)
-        self.append(obs, pi, z, own)
+        if whole and save_len == self.capacity:
+            k = obs.shape[0]
+            self.obs[:k] = obs.to(self.obs.dtype); self.pi[:k] = pi; self.z[:k] = z; self.own[:k] = own
+            self.index, self.full = int(info["index"]), bool(info["full"])
+        else:
+            self.append(obs, pi, z, own)
         return self.full
 
 
@@ -105,8 +130,54 @@ class Pacing:
             if self.adjust_lr and (g + 1) % 1500 == 0 and g < 3100 and self.learn_rate > 0.5 * 0.5 * 6.5e-5:     # configure.py:88-91
                 self.learn_rate *= 0.5
 
-    def selfplay_should_wait(self):                            # self_play.py:970-980
+    def selfplay_should_wait(self, game_total_num=None):       # self_play.py:970-980
+        """True while self-play is ahead of the trainer: train/play ratio below target, ratio adjustment on, and (when
+        given) fewer games played than game_total_num -- the three conjuncts of the reference's wait loop."""
+        if not self.adjust_ratio:
+            return False
+        if game_total_num is not None and self.now_play_games >= game_total_num:
+            return False
         return self.now_train_steps / max(1, self.now_play_steps) < self.train_play_ratio
+
+    def finish_game(self, positions):
+        """Counter updates of ONE finished game in the reference's order: now_play_steps once per position as it is played
+        (self_play.py:921), then now_play_games (self_play.py:967)."""
+        self.add_play_steps(positions)
+        self.add_play_games(1)
+
+    def state_dict(self):
+        return dict(now_play_steps=self.now_play_steps, now_play_games=self.now_play_games, now_train_steps=self.now_train_steps,
+                    train_play_ratio=self.train_play_ratio, learn_rate=self.learn_rate)
+
+    def load_state_dict(self, d):
+        for k, v in d.items():
+            setattr(self, k, v)
 
     def trainer_should_wait(self):                             # trainer.py:94-105
         return self.now_train_steps / max(1, self.now_play_steps) > self.train_play_ratio
+
+
+# ---- checkpoint pickle (transgo.py:171-184 writes it, transgo.py:70-76 reads it): {"weights", "evaluate_weights"}, each a
+# CPU state_dict as model.get_weights() returns it (model.py:23-38)
+def save_checkpoint(path, model, evaluate_model=None):
+    """Writes current_policy.model / best_policy_*.model in the reference's layout; loadable by transgo.py unchanged."""
+    weights = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    ev = weights if evaluate_model is None else {k: v.detach().cpu() for k, v in evaluate_model.state_dict().items()}
+    out = {"weights": weights, "evaluate_weights": ev}
+    with open(path, "wb") as f:
+        pickle.dump(out, f)
+    return out
+
+
+def load_checkpoint(path, model=None, evaluate_model=None):
+    """Reads a reference (or our) checkpoint pickle; optionally loads "weights" into model and "evaluate_weights" into
+    evaluate_model via set_weights / load_state_dict.  Returns the dict."""
+    with open(path, "rb") as f:
+        ck = pickle.load(f)
+    if not isinstance(ck, dict) or "weights" not in ck or "evaluate_weights" not in ck:
+        raise ValueError("%s is not a Transgo checkpoint: expected a dict with 'weights' and 'evaluate_weights'" % path)
+    if model is not None:
+        model.load_state_dict(ck["weights"])
+    if evaluate_model is not None:
+        evaluate_model.load_state_dict(ck["evaluate_weights"])
+    return ck

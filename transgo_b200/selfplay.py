@@ -56,14 +56,19 @@ class SelfPlayWorker:
         if augment:
             obs, pi, z, own = augment8(obs, pi, z, own, n)
         return dict(obs=obs, pi=pi, z=z, own=own, winner=winner, score=score, moves=moves,
-                    positions=int(valid.sum().item()))
+                    positions=int(valid.sum().item()), positions_per_game=valid.sum(1))
 
 
-def _play_continuous(self, min_positions, augment=True, max_moves=None):
+def _play_continuous(self, min_positions, augment=True, max_moves=None, pacing=None, wait_fn=None, game_total_num=None):
     """continuous_self_play (self_play.py:902-968) for a batch: every slot plays game after game; a slot whose game ends is
     labelled (winner z and ownership from the mover's view), handed out and restarted at once, so the search batch stays
     full while games end at different plies.  Returns at least `min_positions` labelled positions (x8 when `augment`) of
-    FINISHED games; unfinished games stay in their slots for the next call."""
+    FINISHED games; unfinished games stay in their slots for the next call.
+
+    `pacing` (replay.Pacing) gets the reference's counter updates per finished game and throttles the loop like
+    self_play.py:970-980: while the train/play ratio is below target, `wait_fn()` is called (it lets the trainer catch up:
+    a train step, a counter refresh from the trainer rank, or a sleep); without a `wait_fn` the call returns early with
+    throttled=True so that the caller can train."""
     s = self.search
     G, n, A = s.G, self.n, s.A
     T = int(s.cfg.max_step) + 1
@@ -79,6 +84,7 @@ def _play_continuous(self, min_positions, augment=True, max_moves=None):
     cols = torch.arange(T, device=dev)
     out = dict(obs=[], pi=[], z=[], own=[])
     positions = games = moves = 0
+    throttled = False
     while positions < min_positions and (max_moves is None or moves < max_moves):
         actions, pi, obs = s.get_action_probs(is_selfplay=True)
         t = h["length"].clamp_max(T - 1)
@@ -98,8 +104,17 @@ def _play_continuous(self, min_positions, augment=True, max_moves=None):
             out["own"].append(torch.where((pl == 1)[:, None], terr[gidx], -terr[gidx]))
             positions += int(valid.sum().item())
             games += int(fin.sum().item())
+            if pacing is not None:
+                for npos in h["length"][fin].tolist():
+                    pacing.finish_game(int(npos))
             h["length"][fin] = 0
             s.reset_games(fin)
+            if pacing is not None and pacing.selfplay_should_wait(game_total_num):
+                if wait_fn is None:
+                    throttled = True
+                    break
+                while pacing.selfplay_should_wait(game_total_num):
+                    wait_fn()
     if out["obs"]:
         obs, pi, z, own = (torch.cat(out[k]) for k in ("obs", "pi", "z", "own"))
     else:
@@ -107,13 +122,36 @@ def _play_continuous(self, min_positions, augment=True, max_moves=None):
         z, own = torch.zeros([0], device=dev), torch.zeros([0, n * n], device=dev)
     if augment and obs.shape[0]:
         obs, pi, z, own = augment8(obs, pi, z, own, n)
-    return dict(obs=obs, pi=pi, z=z, own=own, positions=positions, games=games, moves=moves)
+    return dict(obs=obs, pi=pi, z=z, own=own, positions=positions, games=games, moves=moves, throttled=throttled)
 
 
 SelfPlayWorker.play_continuous = _play_continuous
 
 
-def selfplay_round(worker, model, ring=None, pacing=None, src=0, dst=0, augment=True, max_moves=None, refresh=None):
+class _Stopwatch:
+    """Phase timer for selfplay_round: CUDA events on the current stream when a GPU is in use, wall clock otherwise."""
+
+    def __init__(self, cuda):
+        self.cuda, self.marks = cuda, []
+
+    def mark(self, name):
+        if self.cuda:
+            e = torch.cuda.Event(enable_timing=True); e.record()
+        else:
+            import time
+            e = time.perf_counter()
+        self.marks.append((name, e))
+
+    def phases(self):
+        if self.cuda:
+            torch.cuda.synchronize()
+        out = {}
+        for (_, a), (name, b) in zip(self.marks, self.marks[1:]):
+            out[name + "_ms"] = a.elapsed_time(b) if self.cuda else (b - a) * 1e3
+        return out
+
+
+def selfplay_round(worker, model, ring=None, pacing=None, src=0, dst=0, augment=True, max_moves=None, refresh=None, timing=False):
     """One round of BASELINE configs[4] on every rank of the process group (or a single process without one):
 
         weights  trainer rank `src` -> all ranks            (replaces shared_storage.get_info("weights"), self_play.py:913)
@@ -123,31 +161,57 @@ def selfplay_round(worker, model, ring=None, pacing=None, src=0, dst=0, augment=
         append   into the replay ring on `dst`, bump the play counters (shared_storage.py:21-43)
 
     `refresh` re-folds inference copies of the weights (e.g. make_fused_evaluator(...).refresh).  Returns the play
-    statistics of this rank plus, on `dst`, the number of rows appended."""
+    statistics of this rank plus, on `dst`, the number of rows appended; with `timing`, also broadcast_ms / play_ms /
+    gather_ms / append_ms of this rank (device time) and the bytes each collective moved."""
     import torch.distributed as dist
     from .dist import broadcast_weights, gather_trajectories
     multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+    sw = _Stopwatch(next(model.parameters()).is_cuda) if timing else None
+    if sw: sw.mark("start")
     if multi:
         broadcast_weights(model, src=src)
     if refresh is not None:
         refresh()
+    if sw: sw.mark("broadcast")
     out = worker.play_games(augment=False, max_moves=max_moves)
     rows = (out["obs"], out["pi"], out["z"], out["own"])
+    games_here = int(out["winner"].numel())
+    per_game = out["positions_per_game"]                       # int64 [G] on the device: positions of each game of this rank
+    if sw: sw.mark("play")
     if multi:
-        rows = gather_trajectories(*rows, dst=dst)
+        # the row-count exchange also carries every rank's game count and per-game position counts: shards are uneven when
+        # the total is not divisible by the world size, and the pacing schedules count games one by one
+        rows, extras = gather_trajectories(*rows, dst=dst, extra=[games_here])
+        games_all = [int(x) for x in extras[:, 0].tolist()]
+    else:
+        games_all = [games_here]
+    if sw: sw.mark("gather")
     rank = dist.get_rank() if multi else dst
     if augment and rank == dst and rows is not None:
         rows = augment8(*rows, worker.n)
-    stats = dict(moves=out["moves"], positions=out["positions"], games=int(out["winner"].numel()),
+    stats = dict(moves=out["moves"], positions=out["positions"], games=games_here, games_all_ranks=int(sum(games_all)),
                  black_wins=int((out["winner"] == 1).sum().item()), appended=0)
     if rank == dst and rows is not None:
         if ring is not None:
             ring.append(*rows)
         stats["appended"] = int(rows[0].shape[0])
         if pacing is not None:
+            # counters advance game by game in the reference's order (positions of a game, then the game itself:
+            # self_play.py:921, :967); only the totals of the other ranks are known here, spread evenly over their games
             total_pos = stats["appended"] // (8 if augment else 1)
-            pacing.add_play_steps(total_pos)
-            pacing.add_play_games(stats["games"] * (dist.get_world_size() if multi else 1))
+            total_games = int(sum(games_all))
+            local = per_game.tolist() if not multi else None
+            for i in range(total_games):
+                if local is not None:
+                    pacing.finish_game(int(local[i]))
+                else:
+                    pacing.finish_game(total_pos // total_games + (1 if i < total_pos % total_games else 0))
+    if sw:
+        sw.mark("append")
+        stats.update(sw.phases())
+        row_bytes = 4 * (out["obs"][0].numel() + out["pi"].shape[1] + 1 + out["own"].shape[1]) if out["positions"] else 0
+        stats["gather_bytes_sent"] = 0 if (not multi or rank == dst) else out["positions"] * row_bytes
+        stats["broadcast_bytes"] = sum(v.numel() * v.element_size() for v in model.state_dict().values()) if multi else 0
     return stats
 
 
