@@ -74,13 +74,49 @@ def cpu_playout_baseline(seconds_per_core=1.5, cores=None):
                        % (sum(r[1] for r in res), plies, cores, seconds_per_core)), (plies, sum(r[1] for r in res), wall)
 
 
+def _mcts_kind():
+    """What the CPU MCTS arm runs: the reference's own WP_MCTS + GoEnv + go_env.so (needs /root/reference: build container
+    only), else the pinned port of the search (oracle/mcts_oracle.py) over the UNMODIFIED reference engine
+    (oracle/_ref/go_env9.so travels to the GPU box), else the port over the C restatement."""
+    from oracle import ref_mcts_harness
+    from oracle.go_oracle import have_ref
+    if ref_mcts_harness.available():
+        return "reference"
+    return "port-search+reference-engine" if have_ref(9) else "port"
+
+
 def _cpu_mcts_worker(args):
     wid, sims = args[0], args[1]
     net_device = args[2] if len(args) > 2 else "cpu"
     import torch
     torch.set_num_threads(1)
     import numpy as np
-    from oracle.go_oracle import OracleEnv
+    kind = _mcts_kind()
+    devnull = os.open(os.devnull, os.O_WRONLY)
+    os.dup2(devnull, 1)
+    if kind == "reference":
+        # self_play.py:575-875 + GoEnv/environment.py:32-198 + model.py, imported where they lie; ray is stubbed (not installed)
+        from oracle import ref_mcts_harness as H
+        self_play, configure = H._import_reference()
+        import model as ref_model
+        cfg = configure.Config()
+        cfg.device = torch.device(net_device)
+        cfg.num_simulation = sims
+        cwd = os.getcwd()
+        os.chdir(H.REFERENCE)                                  # environment.py:42 loads ./GoEnv/go_env.so relative to the CWD
+        try:
+            env = self_play.GoEnv(cfg)
+        finally:
+            os.chdir(cwd)
+        torch.manual_seed(0)
+        net = ref_model.TransGoNetwork(cfg).to(cfg.device).eval()
+        with torch.no_grad():
+            m = self_play.WP_MCTS(cfg, env, net, None)         # constructor expands the root (one net call)
+            t0 = time.perf_counter()
+            m.get_action_probs(True)
+            dt = time.perf_counter() - t0
+        return m.root.total_visit_count, dt, kind
+    from oracle.go_oracle import OracleEnv, RefEnv
     from oracle.mcts_oracle import OracleMCTS, MCTSConfig
     from oracle import provider
     from transgo_b200.net import TransGoNetwork
@@ -98,18 +134,19 @@ def _cpu_mcts_worker(args):
     def tie(n):
         i = provider.tie_index(1, wid, cnt[0], n); cnt[0] += 1
         return i
-    t0 = time.perf_counter()
-    m = OracleMCTS(OracleEnv(9), ev, MCTSConfig(num_simulation=sims), tie_fn=tie,
+    env = RefEnv(9) if kind == "port-search+reference-engine" else OracleEnv(9)
+    m = OracleMCTS(env, ev, MCTSConfig(num_simulation=sims), tie_fn=tie,
                    noise_fn=lambda mv, k: provider.dirichlet(1, wid, mv, k), u_fn=lambda mv: provider.uniform(1, wid, mv))
+    t0 = time.perf_counter()
     m.get_action_probs()
-    return m.sims, time.perf_counter() - t0
+    return m.sims, time.perf_counter() - t0, kind
 
 
-def cpu_mcts_baseline(cores=None, sims=64, net_device="cpu"):
-    """self_play.py WP_MCTS restated (oracle/mcts_oracle.py, pinned bit-exact to the reference) + the TransGo net, one game per
-    process as the reference's actors do (transgo.py:92-96).  net_device "cpu": one CPU thread per process; "cuda:0": the
-    reference as shipped (configure.py:66) -- `cores` actor processes (reference default 6, configure.py:25) share the GPU for
-    their batch-of-4 forwards."""
+def cpu_mcts_baseline(cores=None, sims=210, net_device="cpu"):
+    """BASELINE configs[0] on the host: ONE game per process at the reference defaults (configure.py:25-33: 210 simulations,
+    4 leaves per net call), one move after the root expansion, `cores` processes like the reference's actors
+    (transgo.py:92-96).  kind "reference" = self_play.py's WP_MCTS itself; elsewhere the pinned port of the search over the
+    reference engine.  net_device "cpu": one CPU thread per process; "cuda:0": the reference as shipped (configure.py:66)."""
     import multiprocessing as mp
     cores = cores or os.cpu_count() or 1
     ctx = mp.get_context("fork")
@@ -118,8 +155,11 @@ def cpu_mcts_baseline(cores=None, sims=64, net_device="cpu"):
     total = sum(r[0] for r in res)
     wall = max(r[1] for r in res)
     where = "net on 1 CPU thread each" if net_device == "cpu" else "python tree search on the host, net forward on %s as the reference ships" % net_device
-    return dict(value=total / wall, unit="MCTS sims/s", cores=cores, kind="port",
-                sample="%d processes x one move of %d simulations (4 leaves per net call, %s)" % (cores, sims, where))
+    what = {"reference": "the reference's WP_MCTS + GoEnv + go_env.so + model.py (imported from /root/reference)",
+            "port-search+reference-engine": "oracle/mcts_oracle.py (pinned bit-exact to WP_MCTS) over the unmodified reference engine oracle/_ref/go_env9.so",
+            "port": "oracle/mcts_oracle.py over oracle/go_rules.c"}[res[0][2]]
+    return dict(value=total / wall, unit="MCTS sims/s", cores=cores, kind=res[0][2],
+                sample="%d processes x one move of %d simulations (4 leaves per net call, %s); %s" % (cores, sims, where, what))
 
 
 # ------------------------------------------------------------------------------------------------ clocks
@@ -185,7 +225,7 @@ def run_ours(args):
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu, _ = cpu_playout_baseline()                        # before CUDA is initialised (fork-safe)
         if not args.no_mcts:
-            cpu_mcts = cpu_mcts_baseline()
+            cpu_mcts = cpu_mcts_baseline(sims=64 if args.quick else 210)
             try:                                               # children create their own CUDA contexts; the parent has none yet
                 cpu_mcts_gpu_net = cpu_mcts_baseline(cores=6, sims=210, net_device="cuda:%d" % local)
             except Exception as e:  # pragma: no cover
@@ -308,6 +348,9 @@ def run_ours(args):
     c4 = None
     if rank == 0 and not args.quick and not args.no_sweep and not args.no_mcts:
         c4 = c4_bench(torch, dev, BatchedGoEnv)
+    c5 = None
+    if not args.no_mcts and not args.tree_only:
+        c5 = c5_bench(torch, dist, dev, rank, world, args)
     sampler.stop()
 
     peaks = {}
@@ -321,7 +364,7 @@ def run_ours(args):
     achieved = plies_per_launch * BYTES_PER_PLY / (launch_ms * 1e-3) / 1e9
     traffic = ncu_static = None
     try:
-        prof = json.load(open(os.path.join(ROOT, "profiles", "r01_playout_traffic.json")))
+        prof = json.load(open(os.path.join(ROOT, "profiles", "r02_playout_traffic.json")))
         traffic, ncu_static = prof.get("dram_bytes_per_launch"), prof.get("ncu")
     except Exception:
         pass
@@ -346,7 +389,8 @@ def run_ours(args):
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
                          "ncu": ncu_static,
                          "note": "integer bit-manipulation kernel: state stays in registers for ~120 plies, so it is bound by the ALU "
-                                 "pipe / the dependency chain of a game, not by HBM; 'ncu' = the static capture under profiles/"},
+                                 "pipe (IADD3/LOP3/SHF issue every other cycle per scheduler: 50 % issue slots is that pipe's ceiling) and "
+                                 "the dependency chain of a game, not by HBM; 'ncu' = the static capture under profiles/"},
             "cpu_baseline": cpu,
         }
         line.update(extras)
@@ -358,9 +402,18 @@ def run_ours(args):
             line["mcts"] = mcts
         if c4 is not None:
             line["c4_19x19"] = c4
+        if c5 is not None:
+            line["c5"] = c5
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def _hbm_peak():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        return 6650.0
 
 
 def playout_kernel_name(env):
@@ -488,6 +541,63 @@ def c4_bench(torch, dev, BatchedGoEnv):
     return out
 
 
+def c5_bench(torch, dist, dev, rank, world, args):
+    """BASELINE configs[4]: the full self-play round on every rank of the job -- NCCL weight broadcast from the trainer rank
+    (replaces the per-game weight fetch, self_play.py:913 / trainer.py:75-79), this rank's shard of games searched with the
+    fused TransGo evaluator (1024 games x 800 simulations per move, a bounded number of moves), labelled positions gathered
+    to the replay owner with one variable-size message per rank (replaces the 8.T appends per game, self_play.py:956-965),
+    x8 augmentation and ring append on the owner.  Phase times are device times, max over ranks."""
+    from transgo_b200.dist import shard_games
+    from transgo_b200.fused_net import make_fused_evaluator
+    from transgo_b200.net import TransGoNetwork
+    from transgo_b200.replay import Pacing, ReplayRing
+    from transgo_b200.selfplay import SelfPlayWorker, selfplay_round
+    G, sims, moves = (MCTS_GAMES, MCTS_SIMS, 3) if not args.quick else (256, 64, 3)
+    torch.manual_seed(1234 + rank)                             # ranks start with DIFFERENT weights: the broadcast must fix that
+    model = TransGoNetwork(board_size=9).to(dev).eval()
+    ev = make_fused_evaluator(model, cuda_graph="roots")
+    game_id0, _ = shard_games(G * world, rank, world)
+    worker = SelfPlayWorker(ev, G, num_simulation=sims, tie_seed=7, game_id0=game_id0, device=dev, graph_waves=True)
+    ring = ReplayRing(1 << 18, device=dev) if rank == 0 else None
+    pacing = Pacing() if rank == 0 else None
+    out = None
+    for rnd in range(2):                                       # round 0 warms up (graph capture, NCCL channels); round 1 is reported
+        if rank == 0:
+            with torch.no_grad():                              # stand-in for train steps: the trainer rank's weights move
+                for p in model.parameters():
+                    p.mul_(1.0 + 1e-3 * (rnd + 1))
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        worker.search.total_sims()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        st = selfplay_round(worker, model, ring, pacing, src=0, dst=0, max_moves=moves, refresh=ev.refresh, timing=True)
+        b.record()
+        torch.cuda.synchronize()
+        n_sims = worker.search.total_sims()
+        t = torch.tensor([a.elapsed_time(b), st["broadcast_ms"], st["play_ms"], st["gather_ms"], st["append_ms"]], dtype=torch.float64, device=dev)
+        c = torch.tensor([n_sims, st["positions"], st["gather_bytes_sent"]], dtype=torch.float64, device=dev)
+        digest = torch.stack([p.detach().double().sum() for p in model.parameters()]).sum().reshape(1)
+        lo, hi = digest.clone(), digest.clone()
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dist.all_reduce(c, op=dist.ReduceOp.SUM)
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+            dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        out = {"config": {"workload": "BASELINE configs[4]: 9x9 self-play round sharded by game batch, %d games x %d simulations/move per GPU, "
+                                      "%d moves per round, fused bf16 TransGo evaluator, NCCL weight broadcast + trajectory gather" % (G, sims, moves),
+                          "games_per_gpu": G, "num_simulation": sims, "moves": moves},
+               "round_ms": float(t[0]), "broadcast_ms": float(t[1]), "play_ms": float(t[2]), "gather_ms": float(t[3]), "append_x8_ms": float(t[4]),
+               "broadcast_bytes": st["broadcast_bytes"], "gather_bytes": float(c[2]), "gather_frac_of_round": float(t[3]) / float(t[0]),
+               "positions": float(c[1]), "positions_per_s": float(c[1]) / (float(t[0]) * 1e-3), "mcts_sims_per_s": float(c[0]) / (float(t[0]) * 1e-3),
+               "weights_identical_on_all_ranks": bool(float(lo[0]) == float(hi[0])),
+               "rows_appended_x8": st["appended"] if rank == 0 else None,
+               "collectives": "dist.broadcast (one flat buffer per dtype), all_gather_into_tensor (row counts), batch_isend_irecv (rows)" if world > 1 else "none (1 GPU)"}
+    del worker, ring
+    return out
+
+
 def mcts_bench(torch, dist, dev, rank, world, args):
     """BASELINE configs[2]: 1024 games x 800 simulations per move.  (i) tree kernels alone: policy/value come from the
     device-side synthetic provider; (ii) end to end with the random-init TransGo net (PyTorch: bf16 weights + channels_last,
@@ -550,7 +660,12 @@ def mcts_bench(torch, dist, dev, rank, world, args):
                         "provider": "tg_synth_provider (device-side synthetic policy/value, NOT the net); each wave (select, leaves, "
                                     "provider, expand) replayed as one CUDA graph",
                         "mean_depth": d_bar, "mean_fanout": k_bar, "bytes_per_sim": bps,
-                        "gbps_algorithmic": rate * bps / 1e9}
+                        "gbps_algorithmic": rate * bps / 1e9 / world,
+                        "roofline": {"bound": "hbm", "achieved": rate * bps / 1e9 / world, "peak": _hbm_peak(), "unit": "GB/s",
+                                     "frac": rate * bps / 1e9 / world / _hbm_peak(),
+                                     "note": "per GPU; algorithmic bytes per simulation from the measured depth / fan-out (DESIGN.md 4); "
+                                             "the tree kernels are latency bound (one warp per game, dependent loads + float64 score chain), "
+                                             "see profiles/r02_mcts_ncu_summary.txt"}}
     del eng
     if args.tree_only:
         return out
@@ -630,6 +745,12 @@ def run_reference(args):
                              "sample": "%d steps x %d processes x %.2f s: %d games, %d plies" % (K, cores, per, games, int(plies))},
             "e2e": {"value": value, "unit": "board steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
+    if not args.no_mcts:
+        # second half of the metric on the host: BASELINE configs[0] defaults, one game per process on every core
+        m = cpu_mcts_baseline(cores=cores, sims=210)
+        line["mcts"] = {"config": {"workload": "BASELINE configs[0]: 9x9 self-play search, reference defaults (210 simulations/move, 4 leaves "
+                                               "per net call), random-init TransGo net on the CPU, one game per process x %d processes" % cores},
+                        "value": m["value"], "unit": "MCTS sims/s", "cpu_baseline": m}
     print(json.dumps(line), flush=True)
 
 
