@@ -177,6 +177,10 @@ int tg_mcts_begin_move(const TgMctsConfig* cfg, void* ws, const double* noise, v
 /* wave, first half: selection + terminal backups + leaf step/legal/encode.  obs float32 [G*readouts][10][n][n];
  * rows of unused slots are left untouched. */
 int tg_mcts_wave_begin(const TgMctsConfig* cfg, void* ws, float* obs, void* stream);
+/* test hook: 1 = run the selection of every wave with one warp per game in the reference's descent order (the default kernel
+ * pipelines the descents of a wave over one warp each and falls back to that order by itself where needed); returns the old value */
+int tg_mcts_debug_sequential_select(int on);
+
 /* wave, second half: policy float32 [G*readouts][A] (softmaxed, model.py:111), value float32 [G*readouts];
  * pending (may be NULL) receives the number of active games still below N0 + num_simulation */
 int tg_mcts_wave_end(const TgMctsConfig* cfg, void* ws, const float* policy, const float* value, int32_t* pending,

@@ -439,3 +439,43 @@ def test_continuous_selfplay_is_throttled_by_the_pacing_counters(oracle_built):
     pacing.now_train_steps = 0
     out2 = w.play_continuous(min_positions=1000, augment=False, pacing=pacing)      # no trainer: hand control back
     assert out2["throttled"] is True and out2["positions"] < 1000
+
+
+def test_pipelined_selection_equals_the_sequential_kernel():
+    """k_select_par (one warp per descent of the wave, pipelined through shared memory, speculative with a sequential replay
+    for terminal leaves / repeated ties) against k_select (one warp per game, the reference's descent order) at the BASELINE
+    size: identical visit counts, actions, priors and statistics over several moves, including the end of short games."""
+    from transgo_b200 import _lib
+    from transgo_b200.mcts import BatchedMCTS, _declare
+    L = _lib.lib(); _declare(L)
+    for G, sims, max_step, moves in ((256, 200, None, 3), (64, 48, 10, 12)):
+        outs = []
+        for sequential in (1, 0):
+            L.tg_mcts_debug_sequential_select(sequential)
+            try:
+                wave = [0]
+
+                def evaluator(obs):
+                    B = obs.shape[0]
+                    p = torch.empty([B, 82], dtype=torch.float32, device="cuda"); v = torch.empty([B], dtype=torch.float32, device="cuda")
+                    _lib.check(L.tg_synth_provider(9, B, 4242, wave[0], _lib.ptr(p), _lib.ptr(v), _lib.stream_ptr()))
+                    wave[0] += 1
+                    return p, v
+                eng = BatchedMCTS(evaluator, G, num_simulation=sims, tie_seed=5, max_step=max_step)
+                gen = torch.Generator(device="cuda"); gen.manual_seed(9)
+                rec = []
+                for _ in range(moves):
+                    noise = eng.make_noise(generator=gen)
+                    u = torch.rand([G], dtype=torch.float64, device="cuda", generator=gen)
+                    a, pi, _ = eng.get_action_probs(True, noise=noise, u=u)
+                    c, W, var, prior = eng.root_stats(full=True)
+                    rec.append((a.clone(), pi.clone(), c.clone(), W.clone(), var.clone(), eng.root_n.clone()))
+                    eng.update_with_action(a)
+                outs.append((rec, eng.total_sims(), eng.search_stats()))
+            finally:
+                L.tg_mcts_debug_sequential_select(0)
+        (ra, sa, sta), (rb, sb, stb) = outs
+        assert sa == sb and sta == stb
+        for x, y in zip(ra, rb):
+            for p, q in zip(x, y):
+                assert torch.equal(p, q)

@@ -14,6 +14,7 @@ enum { H_BUF = 0, H_NNODES, H_NEDGES, H_ROOTN, H_ROOTONS, H_ROOTW, H_ROOTMEAN, H
        H_NPATHS, H_SIMS, H_STAT_DESC, H_STAT_DEPTH, H_STAT_FAN, H_SPARE1, H_WORDS_USED, H_WORDS = 20 };   // 80 B per game
 constexpr unsigned kErrAction = 256u;
 constexpr int kMaxReadouts = 8;
+constexpr int kParWarps = 4;        // k_select_par: one warp per descent, up to this many (the reference default is 4 readouts)
 
 // hot.w : N[31:16] | ons[15:9] | action[8:0]
 __device__ __forceinline__ int pk_n(uint32_t p) { return (int)(p >> 16); }
@@ -146,18 +147,119 @@ __device__ __forceinline__ unsigned long long ordered_bits(double x) {
     return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
 }
 
+// One node visit of select_child (self_play.py:706-725), split in two so that the loads can be in flight while the warp
+// still waits for something else.  Lane l scans children l, l+32, ...
+template <int N> struct ScanRegs {
+    static constexpr int MAXR = (Geo<N>::A + 31) / 32;
+    uint4 q[MAXR]; uint32_t ch[MAXR], kd[MAXR]; double pr64[MAXR];
+};
+
+// every load of the scan is issued before the first use (no branch in between): one memory round trip per node
 template <int N>
-__global__ void __launch_bounds__(kThreads) k_select(View v) {
+__device__ __forceinline__ void scan_load(ScanRegs<N>& s, const uint4* hot, const uint2* cold, const uint32_t* kid, const double* p64,
+                                          bool noisy_root, int eb, int K, int lane) {
+#pragma unroll
+    for (int r = 0; r < ScanRegs<N>::MAXR; ++r) {
+        if (N == 9 || 32 * r < K) {                           // 19x19: skip whole rounds beyond K (warp-uniform)
+            const int k = lane + 32 * r;
+            const int kk = k < K ? k : K - 1;
+            s.q[r] = hot[eb + kk];
+            s.ch[r] = cold[eb + kk].y;                        // child node of the edge (cold record), so that the descent
+            s.kd[r] = kid[eb + kk];                           // needs no second trip; kd: where the child's edges live
+            s.pr64[r] = noisy_root ? p64[kk] : 0.0;
+        } else { s.q[r] = make_uint4(0, 0, 0, 0); s.ch[r] = 0xffffffffu; s.kd[r] = 0; s.pr64[r] = 0.0; }
+    }
+}
+
+// scores, arg-max, exact-tie rule.  xo[r] = virtual-loss units (multiples of wu_loss are added to the child's ons) that earlier
+// descents of the same wave put on this lane's r-th child and that memory does not hold yet (nullptr: none).
+// Returns false when no child has a finite score (NaN from the evaluator).  tie_events counts exact ties seen.
+template <int N>
+__device__ __forceinline__ bool scan_pick(const View& v, const ScanRegs<N>& s, bool noisy_root, int K, int Np, int onsp, const int* xo,
+                                          int tie_counter, int& tie_events, int g, int lane,
+                                          int& ksel, uint32_t& pk_sel, uint32_t& ch_sel, uint32_t& kd_sel) {
+    constexpr int MAXR = ScanRegs<N>::MAXR;
+    const float c1f = (float)v.c1, c2f = (float)v.c2;
+    const double sq = __dsqrt_rn((double)(Np + onsp));
+    unsigned long long ob[MAXR];
+    unsigned hi_max = 0;
+#pragma unroll
+    for (int r = 0; r < MAXR; ++r) {
+        const int k = lane + 32 * r;
+        const float prior = __uint_as_float(s.q[r].x), W = __uint_as_float(s.q[r].y), var = __uint_as_float(s.q[r].z);
+        const int nc = pk_n(s.q[r].w), oc = pk_ons(s.q[r].w) + (xo ? xo[r] * v.wu : 0);
+        // prior_score = c1 * prior * sqrt(Np + ons_p) / (Nc + ons_c + 1)          (:718-719)
+        double ps = noisy_root ? __dmul_rn(v.c1, s.pr64[r]) : (double)__fmul_rn(c1f, prior);
+        ps = __ddiv_rn(__dmul_rn(ps, sq), (double)(nc + oc + 1));
+        // var_score = c2 * sqrt(1 + clip(var, 0, 3)); float64 for a never-visited child      (:721-722)
+        const float cv = var < 0.0f ? 0.0f : (var > 3.0f ? 3.0f : var);
+        const double vsf = (double)__fmul_rn(c2f, __fsqrt_rn(__fadd_rn(1.0f, cv)));
+        const double vs = nc == 0 ? v.c2 : vsf;
+        const double qv = (double)(-__fdiv_rn(W, (float)(nc + 1)));                 // -child.value() (:724, :67-68)
+        const double sc = __dadd_rn(__dadd_rn(ps, vs), qv);
+        ob[r] = k < K ? ordered_bits(sc) : 0ull;
+        const unsigned hi = (unsigned)(ob[r] >> 32);
+        hi_max = hi > hi_max ? hi : hi_max;
+    }
+    hi_max = __reduce_max_sync(0xffffffffu, hi_max);
+    unsigned lo_max = 0;
+#pragma unroll
+    for (int r = 0; r < MAXR; ++r) {
+        const unsigned lo = (unsigned)(ob[r] >> 32) == hi_max ? (unsigned)ob[r] : 0u;
+        lo_max = lo > lo_max ? lo : lo_max;
+    }
+    lo_max = __reduce_max_sync(0xffffffffu, lo_max);
+    const unsigned long long best = ((unsigned long long)hi_max << 32) | lo_max;
+    // exact ties, ascending action order (:708-713).  A NaN score (ordered above +inf or below -inf, never equal to a real
+    // one) or an all-NaN node leaves no candidate: fail loudly instead of walking a bogus edge.
+    if (best <= 0x000fffffffffffffull || best >= 0xfff0000000000000ull) return false;      // the maximum is not a finite number
+    unsigned bal[MAXR]; int total = 0;
+#pragma unroll
+    for (int r = 0; r < MAXR; ++r) { bal[r] = __ballot_sync(0xffffffffu, ob[r] == best); total += __popc(bal[r]); }
+    int j = 0;
+    if (total > 1) {
+        if (v.tie_mode == 1) j = (int)(((unsigned long long)mix32(v.tie_seed, (unsigned long long)(v.game_id0 + g), (unsigned long long)tie_counter) * (unsigned)total) >> 32);
+        tie_events += 1;
+    }
+    ksel = -1; ch_sel = 0xffffffffu; kd_sel = 0;
+#pragma unroll
+    for (int r = 0; r < MAXR; ++r) {
+        const int c = __popc(bal[r]);
+        if (ksel < 0 && j < c) {
+            const int src = nth_bit(bal[r], j);
+            ksel = src + 32 * r;
+            pk_sel = __shfl_sync(0xffffffffu, s.q[r].w, src);
+            ch_sel = __shfl_sync(0xffffffffu, s.ch[r], src);
+            kd_sel = __shfl_sync(0xffffffffu, s.kd[r], src);
+        } else if (ksel < 0) j -= c;
+    }
+    return true;
+}
+
+// terminal leaf (self_play.py:638-642): step, score, back the result up at once
+template <int N>
+__device__ __forceinline__ void terminal_backup(const View& v, int* h, uint4* hot, uint2* cold, const uint4* nodes, int node, int action,
+                                                const int* path, int depth, unsigned& err) {
     using GG = Geo<N>;
-    constexpr int MAXR = (GG::A + 31) / 32;
-    const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (g >= v.G) return;
+    Pos<N> s; pos_load<N>(s, nodes + (size_t)node * (GG::SQ + 1), 0, 1, 0);
+    Groups<N> gr;
+    if (action != GG::P) analyse_groups<N, 32, false>(s.stones[0], s.stones[1], s.player, gr);
+    else { gr.l1[0] = gr.l1[1] = gr.l2[0] = gr.l2[1] = gr.lives = bb_zero<N>(); }
+    bool acc;
+    apply_move<N, 32>(s, gr, action, v.max_step, acc, true);
+    BB<N> bt, wt;
+    const int raw = area_score<N, 32>(s.stones[0], s.stones[1], bt, wt);
+    const int winner = ((float)raw - v.komi) > 0.0f ? kBlack : kWhite;          // environment.py:118-119
+    const float value = (s.player == winner) ? 1.0f : -1.0f;
+    backup<N>(v, h, hot, cold, path, depth, value, err);
+}
+
+// The wave of one game, one descent after the other, exactly as WP_MCTS.run does it (self_play.py:616-646).  One warp.
+template <int N>
+__device__ __forceinline__ void select_sequential(const View& v, int g, int lane) {
+    using GG = Geo<N>;
     int* h = v.hdr + (size_t)g * H_WORDS;
     const unsigned flags = (unsigned)h[H_FLAGS];
-    const bool run = (flags & TG_MCTS_ACTIVE) && !(flags & (TG_MCTS_NEED_EXPAND | TG_MCTS_ERR_ANY | kErrAction)) &&
-                     h[H_ROOTN] < h[H_N0] + v.num_sim;
-    if (!run) { if (lane == 0) h[H_NPATHS] = 0; return; }
     const int buf = h[H_BUF];
     uint4* hot = hot_of<N>(v, buf, g);
     uint2* cold = cold_of<N>(v, buf, g);
@@ -170,7 +272,6 @@ __global__ void __launch_bounds__(kThreads) k_select(View v) {
     const int root_step = (int)(root_meta.z & 0xffffu);
     const double* p64 = v.root_prior64 + (size_t)g * GG::A;
     const bool noisy = (flags & TG_MCTS_NOISY) != 0;
-    const float c1f = (float)v.c1, c2f = (float)v.c2;
     int npaths = 0, tie = h[H_TIE], sims = 0;
     int st_desc = 0, st_depth = 0, st_fan = 0;                        // descents, edges walked, children scanned (bench: d, K)
     unsigned err = 0;
@@ -184,77 +285,11 @@ __global__ void __launch_bounds__(kThreads) k_select(View v) {
             // where the node's edges live came with the edge that led here: no dependent load of the node record
             const int eb = (int)(kid_cur & 0x3fffffu), K = (int)(kid_cur >> 22);
             st_fan += K;
-            // every load of the scan is issued before the first use (no branch in between): one memory round trip per node
-            uint4 q[MAXR]; uint32_t ch[MAXR], kd[MAXR]; double pr64[MAXR];
-            const bool noisy_root = noisy && node == 0;
-#pragma unroll
-            for (int r = 0; r < MAXR; ++r) {
-                if (N == 9 || 32 * r < K) {                           // 19x19: skip whole rounds beyond K (warp-uniform)
-                    const int k = lane + 32 * r;
-                    const int kk = k < K ? k : K - 1;
-                    q[r] = hot[eb + kk];
-                    ch[r] = cold[eb + kk].y;                          // child node of the edge (cold record), so that the descent
-                    kd[r] = kid[eb + kk];                             // needs no second trip; kd: where the child's edges live
-                    pr64[r] = noisy_root ? p64[kk] : 0.0;
-                } else { q[r] = make_uint4(0, 0, 0, 0); ch[r] = 0xffffffffu; kd[r] = 0; pr64[r] = 0.0; }
-            }
-            const double sq = __dsqrt_rn((double)(Np + onsp));
-            unsigned long long ob[MAXR];
-            unsigned hi_max = 0;
-#pragma unroll
-            for (int r = 0; r < MAXR; ++r) {
-                const int k = lane + 32 * r;
-                const float prior = __uint_as_float(q[r].x), W = __uint_as_float(q[r].y), var = __uint_as_float(q[r].z);
-                const int nc = pk_n(q[r].w), oc = pk_ons(q[r].w);
-                // prior_score = c1 * prior * sqrt(Np + ons_p) / (Nc + ons_c + 1)          (:718-719)
-                double ps = noisy_root ? __dmul_rn(v.c1, pr64[r]) : (double)__fmul_rn(c1f, prior);
-                ps = __ddiv_rn(__dmul_rn(ps, sq), (double)(nc + oc + 1));
-                // var_score = c2 * sqrt(1 + clip(var, 0, 3)); float64 for a never-visited child      (:721-722)
-                const float cv = var < 0.0f ? 0.0f : (var > 3.0f ? 3.0f : var);
-                const double vsf = (double)__fmul_rn(c2f, __fsqrt_rn(__fadd_rn(1.0f, cv)));
-                const double vs = nc == 0 ? v.c2 : vsf;
-                const double qv = (double)(-__fdiv_rn(W, (float)(nc + 1)));                 // -child.value() (:724, :67-68)
-                const double sc = __dadd_rn(__dadd_rn(ps, vs), qv);
-                ob[r] = k < K ? ordered_bits(sc) : 0ull;
-                const unsigned hi = (unsigned)(ob[r] >> 32);
-                hi_max = hi > hi_max ? hi : hi_max;
-            }
-            hi_max = __reduce_max_sync(0xffffffffu, hi_max);
-            unsigned lo_max = 0;
-#pragma unroll
-            for (int r = 0; r < MAXR; ++r) {
-                const unsigned lo = (unsigned)(ob[r] >> 32) == hi_max ? (unsigned)ob[r] : 0u;
-                lo_max = lo > lo_max ? lo : lo_max;
-            }
-            lo_max = __reduce_max_sync(0xffffffffu, lo_max);
-            const unsigned long long best = ((unsigned long long)hi_max << 32) | lo_max;
-            // exact ties, ascending action order (:708-713).  A NaN score (ordered above +inf, never equal to a real one) or
-            // an all-NaN node leaves no candidate: fail loudly instead of walking a bogus edge.
-            unsigned bal[MAXR]; int total = 0;
-#pragma unroll
-            for (int r = 0; r < MAXR; ++r) {
-                const bool is_best = ob[r] == best && ob[r] > 0x000fffffffffffffull && ob[r] < 0xfff0000000000000ull;   // finite
-                bal[r] = __ballot_sync(0xffffffffu, is_best); total += __popc(bal[r]);
-            }
-            if (total == 0) { err |= TG_MCTS_ERR_NAN; break; }
-            int j = 0;
-            if (total > 1) {
-                if (v.tie_mode == 1) j = (int)(((unsigned long long)mix32(v.tie_seed, (unsigned long long)(v.game_id0 + g), (unsigned long long)tie) * (unsigned)total) >> 32);
-                tie += 1;
-            }
-            int ksel = -1;
-            uint32_t ch_sel = 0xffffffffu, kd_sel = 0;
-#pragma unroll
-            for (int r = 0; r < MAXR; ++r) {
-                const int c = __popc(bal[r]);
-                if (ksel < 0 && j < c) {
-                    const int src = nth_bit(bal[r], j);
-                    ksel = src + 32 * r;
-                    pk_sel = __shfl_sync(0xffffffffu, q[r].w, src);
-                    ch_sel = __shfl_sync(0xffffffffu, ch[r], src);
-                    kd_sel = __shfl_sync(0xffffffffu, kd[r], src);
-                } else if (ksel < 0) j -= c;
-            }
+            ScanRegs<N> sr;
+            scan_load<N>(sr, hot, cold, kid, p64, noisy && node == 0, eb, K, lane);
+            int ksel; uint32_t ch_sel, kd_sel; int ties = 0;
+            if (!scan_pick<N>(v, sr, noisy && node == 0, K, Np, onsp, nullptr, tie, ties, g, lane, ksel, pk_sel, ch_sel, kd_sel)) { err |= TG_MCTS_ERR_NAN; break; }
+            tie += ties;
             const int e = eb + ksel;
             if (depth >= v.MAXD) { err |= TG_MCTS_ERR_DEPTH; break; }
             if (lane == 0) path[depth] = e;
@@ -271,20 +306,9 @@ __global__ void __launch_bounds__(kThreads) k_select(View v) {
         // (a pass too) advances step_count by one, and the parent's last move is the edge that led to it.
         const int action = pk_act(pk_sel);
         const int step2 = root_step + depth;
-        const bool is_pass = action == GG::P;
-        const bool done = (is_pass && after_pass && step2 > 1) || step2 > v.max_step;
+        const bool done = (action == GG::P && after_pass && step2 > 1) || step2 > v.max_step;
         if (done) {                                                                   // :638-642
-            Pos<N> s; pos_load<N>(s, nodes + (size_t)node * (GG::SQ + 1), 0, 1, 0);
-            Groups<N> gr;
-            if (!is_pass) analyse_groups<N, 32, false>(s.stones[0], s.stones[1], s.player, gr);
-            else { gr.l1[0] = gr.l1[1] = gr.l2[0] = gr.l2[1] = gr.lives = bb_zero<N>(); }
-            bool acc;
-            apply_move<N, 32>(s, gr, action, v.max_step, acc, true);
-            BB<N> bt, wt;
-            const int raw = area_score<N, 32>(s.stones[0], s.stones[1], bt, wt);
-            const int winner = ((float)raw - v.komi) > 0.0f ? kBlack : kWhite;          // environment.py:118-119
-            const float value = (s.player == winner) ? 1.0f : -1.0f;
-            backup<N>(v, h, hot, cold, path, depth, value, err);
+            terminal_backup<N>(v, h, hot, cold, nodes, node, action, path, depth, err);
             sims += 1;
         } else {
             if (lane == 0) {
@@ -299,6 +323,138 @@ __global__ void __launch_bounds__(kThreads) k_select(View v) {
         h[H_TIE] = tie; h[H_NPATHS] = npaths; h[H_SIMS] += sims;
         h[H_STAT_DESC] += st_desc; h[H_STAT_DEPTH] += st_depth; h[H_STAT_FAN] += st_fan;
         if (err) h[H_FLAGS] = (int)(flags | err);
+    }
+}
+
+// out-of-line copy for the (rare) replay inside k_select_par: keeps that kernel's hot path small
+template <int N> __device__ __noinline__ void select_sequential_cold(const View& v, int g, int lane) { select_sequential<N>(v, g, lane); }
+
+template <int N> __device__ __forceinline__ bool game_runs(const View& v, const int* h) {
+    const unsigned flags = (unsigned)h[H_FLAGS];
+    return (flags & TG_MCTS_ACTIVE) && !(flags & (TG_MCTS_NEED_EXPAND | TG_MCTS_ERR_ANY | kErrAction)) && h[H_ROOTN] < h[H_N0] + v.num_sim;
+}
+
+// one warp per game, descents one after the other (reference order); also the fallback of k_select_par
+template <int N>
+__global__ void __launch_bounds__(kThreads) k_select(View v) {
+    const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (g >= v.G) return;
+    int* h = v.hdr + (size_t)g * H_WORDS;
+    if (!game_runs<N>(v, h)) { if (lane == 0) h[H_NPATHS] = 0; return; }
+    select_sequential<N>(v, g, lane);
+}
+
+// One CTA per game, one WARP PER DESCENT of the wave (R = parallel_readouts warps).  The descents of a wave only interact
+// through the virtual loss (`ons`) earlier descents leave on the nodes they pass (self_play.py:644, :767-769): the choice of
+// descent j at tree level L depends on the choices descents 0..j-1 made AT LEVEL L and nothing deeper.  So the warps run as a
+// pipeline -- warp j handles level L as soon as warp j-1 has published its level-L choice in shared memory -- and the wave
+// costs (depth + R - 1) node visits of latency instead of depth * R, with R times as many loads in flight.  Nothing is written
+// to the tree until all descents are known.  Two cases need the reference order and are replayed by select_sequential:
+// a descent that ends in a terminal leaf (its backup changes W / N before the next descent starts, :638-642), and more than one
+// exact tie in the wave (the tie-break draws are numbered in descent-major order).  Both are rare outside the last moves.
+// Launch bounds: a CTA lives for the whole wave of its game (latency bound), so ALL games must be resident at once or the
+// kernel takes two rounds: 8 CTAs of 4 warps per SM (<= 64 registers) hold 1184 games of 9x9, 4 per SM 592 games of 19x19.
+template <int N>
+__global__ void __launch_bounds__(32 * kParWarps, N == 9 ? 8 : 4) k_select_par(View v) {
+    using GG = Geo<N>;
+    constexpr int MAXR = ScanRegs<N>::MAXR;
+    extern __shared__ int sm_sel[];                                   // [MAXD][R] node, then [MAXD][R] child index
+    __shared__ int progress[kMaxReadouts], plen[kMaxReadouts];
+    __shared__ int s_ties[kMaxReadouts], s_flag[kMaxReadouts], s_fan[kMaxReadouts];
+    const int g = blockIdx.x, R = v.R;
+    const int j = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int* h = v.hdr + (size_t)g * H_WORDS;
+    if (!game_runs<N>(v, h)) { if (threadIdx.x == 0) h[H_NPATHS] = 0; return; }   // CTA-uniform
+    volatile int* sel_node = sm_sel;
+    volatile int* sel_k = sm_sel + v.MAXD * R;
+    volatile int* vprog = progress; volatile int* vlen = plen;
+    if (threadIdx.x < kMaxReadouts) { progress[threadIdx.x] = 0; plen[threadIdx.x] = 1 << 30; }
+    __syncthreads();
+    const unsigned flags = (unsigned)h[H_FLAGS];
+    const int buf = h[H_BUF];
+    uint4* hot = hot_of<N>(v, buf, g);
+    uint2* cold = cold_of<N>(v, buf, g);
+    const uint32_t* kid = kid_of<N>(v, buf, g);
+    const uint4* nodes = nodes_of<N>(v, buf, g);
+    const uint4 root_info = nodes[GG::SQ];
+    const uint4 root_meta = nodes[GG::SQ - 1];
+    const bool root_after_pass = (int16_t)(root_meta.x & 0xffffu) == (int16_t)kPass;
+    const int root_step = (int)(root_meta.z & 0xffffu);
+    const double* p64 = v.root_prior64 + (size_t)g * GG::A;
+    const bool noisy = (flags & TG_MCTS_NOISY) != 0;
+    const int tie0 = h[H_TIE], rootN = h[H_ROOTN], rootons = h[H_ROOTONS];
+    int* path = v.paths + ((size_t)g * R + j) * v.MAXD;
+    // ---- descent j, speculative: registers, shared memory and this descent's private path row only
+    int node = 0, depth = 0, Np = rootN, ons_base = rootons;
+    uint32_t pk_sel = 0, kid_cur = pack_kid((int)root_info.x, (int)root_info.y);
+    bool after_pass = root_after_pass;
+    int ties = 0, fan = 0;
+    int flag = 0;                                                     // 1: needs the sequential replay, 2: depth error, 4: NaN
+    for (int L = 0;; ++L) {
+        const int eb = (int)(kid_cur & 0x3fffffu), K = (int)(kid_cur >> 22);
+        fan += K;
+        ScanRegs<N> sr;
+        scan_load<N>(sr, hot, cold, kid, p64, noisy && node == 0, eb, K, lane);    // in flight while waiting for warp j-1
+        // every earlier descent must have published its level-L choice (or have ended): a short descent j-1 says nothing
+        // about how far a long descent j-2 has come
+        for (int jp = 0; jp < j; ++jp) { while (vprog[jp] <= L) __nanosleep(40); }
+        __syncwarp();
+        // virtual loss of the earlier descents that stand on this node at this level
+        int same = 0, xo[MAXR];
+#pragma unroll
+        for (int r = 0; r < MAXR; ++r) xo[r] = 0;
+        for (int jp = 0; jp < j; ++jp) {
+            if (L < vlen[jp] && sel_node[L * R + jp] == node) {
+                same += 1;
+                const int kx = sel_k[L * R + jp];
+#pragma unroll
+                for (int r = 0; r < MAXR; ++r) xo[r] += (kx == lane + 32 * r) ? 1 : 0;
+            }
+        }
+        int ksel; uint32_t ch_sel, kd_sel;
+        if (!scan_pick<N>(v, sr, noisy && node == 0, K, Np, ons_base + same * v.wu, xo, tie0, ties, g, lane, ksel, pk_sel, ch_sel, kd_sel)) { flag |= 4; break; }
+        if (depth >= v.MAXD) { flag |= 2; break; }
+        if (lane == 0) { path[depth] = eb + ksel; sel_node[L * R + j] = node; sel_k[L * R + j] = ksel; }
+        depth += 1;
+        __syncwarp();
+        __threadfence_block();
+        if (lane == 0) vprog[j] = L + 1;
+        const int child = (int)ch_sel;
+        if (child < 0) break;
+        after_pass = pk_act(pk_sel) == GG::P;
+        Np = pk_n(pk_sel); ons_base = pk_ons(pk_sel); node = child; kid_cur = kd_sel;
+    }
+    const int action = pk_act(pk_sel);
+    const int step2 = root_step + depth;
+    if (!flag && ((action == GG::P && after_pass && step2 > 1) || step2 > v.max_step)) flag |= 1;   // terminal leaf
+    if (lane == 0) {
+        vlen[j] = depth; s_ties[j] = ties; s_flag[j] = flag; s_fan[j] = fan;
+        __threadfence_block();
+        vprog[j] = 1 << 30;
+    }
+    __syncthreads();
+    int any_flag = 0, all_ties = 0;
+    for (int jp = 0; jp < R; ++jp) { any_flag |= s_flag[jp]; all_ties += s_ties[jp]; }
+    if (any_flag || all_ties > 1) {                                   // CTA-uniform: replay in the reference order
+        if (j == 0) select_sequential_cold<N>(v, g, lane);
+        return;
+    }
+    // ---- commit: every descent found a leaf to evaluate
+    __syncwarp();
+    for (int i = lane; i <= depth; i += 32) {                         // incomplete_update (:767-769): +wu on every node of the path
+        if (i == depth) atomicAdd(&h[H_ROOTONS], v.wu);
+        else atomicAdd(&reinterpret_cast<uint32_t*>(hot + path[i])[3], (uint32_t)(v.wu * 512));
+    }
+    if (lane == 0) {
+        const size_t slot = (size_t)g * R + j;
+        v.leaf_parent[slot] = node; v.leaf_action[slot] = action; v.path_len[slot] = depth;
+    }
+    if (threadIdx.x == 0) {
+        int sd = 0, sf = 0;
+        for (int jp = 0; jp < R; ++jp) { sd += plen[jp]; sf += s_fan[jp]; }
+        h[H_TIE] = tie0 + all_ties; h[H_NPATHS] = R;
+        h[H_STAT_DESC] += R; h[H_STAT_DEPTH] += sd; h[H_STAT_FAN] += sf;
     }
 }
 
@@ -402,6 +558,8 @@ __global__ void __launch_bounds__(kThreads) k_expand(View v, const float* __rest
         float scale = 0.0f;                                                           // :739 python sum(): sequential float32
         if (lane == 0) for (int k = 0; k < K; ++k) scale = __fadd_rn(scale, sp[k]);
         scale = __shfl_sync(0xffffffffu, scale, 0);
+        // a NaN / inf from the evaluator would poison W along the whole path and every later selection: fail loudly here
+        if (!isfinite(scale) || !isfinite(val)) { err |= TG_MCTS_ERR_NAN; add_ons(h, hot, path, len, -v.wu); continue; }
         const bool ok = scale > 0.0f;                                                 // :740
         for (int k = lane; k < K; k += 32) {
             const float prior = ok ? __fdiv_rn(sp[k], scale) : 0.0f;                   // :743-744
@@ -427,6 +585,157 @@ __global__ void __launch_bounds__(kThreads) k_expand(View v, const float* __rest
         if (err) { flags |= err; h[H_FLAGS] = (int)flags; }
         if (pending && (flags & TG_MCTS_ACTIVE) && !(flags & (TG_MCTS_ERR_ANY | kErrAction)) && h[H_ROOTN] < h[H_N0] + v.num_sim)
             atomicAdd(pending, 1);
+    }
+}
+
+// One CTA per game, one warp per leaf of the wave (the expansion counterpart of k_select_par).  complete_update
+// (self_play.py:727-755) of the R leaves of a wave is independent work -- legal list, prior renormalisation, R x K new edge
+// records, the node record -- except for three things that follow the reference's leaf order j = 0..R-1 and are resolved
+// between the phases: duplicate leaves (:733-734), arena allocation, and the value backups, whose float32 sums / Welford
+// updates on shared ancestors must be applied in leaf order.
+//   phase A  warp j: loads of leaf j, legal list compaction, sequential float32 prior sum (:739)
+//   phase B  thread 0: the sequential decisions (duplicate / error / node and edge base) for j = 0..R-1
+//   phase C  warp j: writes the node and its edges
+//   phase D  warp 0: all backups and virtual-loss reverts, lane = tree level; each lane loads the <= R records of its level
+//            once, applies the leaves' updates in order with forwarding between leaves that share the edge, stores once
+template <int N>
+__global__ void __launch_bounds__(32 * kParWarps) k_expand_par(View v, const float* __restrict__ policy, const float* __restrict__ value, int* __restrict__ pending) {
+    using GG = Geo<N>;
+    extern __shared__ uint32_t sm_raw[];
+    __shared__ int s_e[kParWarps], s_len[kParWarps], s_K[kParWarps], s_pre[kParWarps], s_bad[kParWarps], s_exp[kParWarps], s_node[kParWarps], s_eb[kParWarps];
+    __shared__ float s_val[kParWarps], s_scale[kParWarps];
+    __shared__ unsigned s_err;
+    __shared__ int s_nn, s_ne;
+    const int g = blockIdx.x, R = v.R;
+    const int j = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* sp = reinterpret_cast<float*>(sm_raw) + j * 2 * GG::A;
+    int* sa = reinterpret_cast<int*>(sp + GG::A);
+    int* h = v.hdr + (size_t)g * H_WORDS;
+    unsigned flags = (unsigned)h[H_FLAGS];
+    const int npaths = h[H_NPATHS];
+    const int buf = h[H_BUF];
+    uint4* hot = hot_of<N>(v, buf, g);
+    uint2* cold = cold_of<N>(v, buf, g);
+    uint32_t* kid = kid_of<N>(v, buf, g);
+    uint4* nodes = nodes_of<N>(v, buf, g);
+    const size_t slot = (size_t)g * R + j;
+    const int* path = v.paths + slot * v.MAXD;
+    // ---- phase A
+    if (j < npaths) {
+        const int len = v.path_len[slot];
+        const int e = path[len - 1];
+        const float val = value[slot];
+        const int pre = (int)cold[e].y >= 0;
+        const int K = compact_legal<N>(v.leaf_legal + slot * GG::DQ * 4, policy + slot * GG::A, sp, sa);
+        float scale = 0.0f;                                                           // :739 python sum(): sequential float32
+        if (lane == 0) for (int k = 0; k < K; ++k) scale = __fadd_rn(scale, sp[k]);
+        if (lane == 0) {
+            s_e[j] = e; s_len[j] = len; s_K[j] = K; s_pre[j] = pre; s_val[j] = val; s_scale[j] = scale;
+            s_bad[j] = (!isfinite(scale) || !isfinite(val)) ? 1 : 0;
+        }
+    }
+    __syncthreads();
+    // ---- phase B: the reference's leaf order
+    if (threadIdx.x == 0) {
+        unsigned err = 0;
+        int nn = h[H_NNODES], ne = h[H_NEDGES];
+        for (int jj = 0; jj < npaths; ++jj) {
+            s_exp[jj] = 0;
+            bool dup = s_pre[jj] != 0;
+            for (int jp = 0; jp < jj; ++jp) dup = dup || (s_exp[jp] && s_e[jp] == s_e[jj]);
+            if (dup || err) continue;                                                 // :653, :733-734 duplicate leaf: no backup
+            if (nn + 1 > v.NC) err |= TG_MCTS_ERR_NODES;
+            if (ne + s_K[jj] > v.EC) err |= TG_MCTS_ERR_EDGES;
+            if (err) continue;
+            if (s_bad[jj]) { err |= TG_MCTS_ERR_NAN; continue; }                      // NaN / inf from the evaluator: fail loudly
+            s_exp[jj] = 1; s_node[jj] = nn; s_eb[jj] = ne;
+            nn += 1; ne += s_K[jj];
+        }
+        s_err = err; s_nn = nn; s_ne = ne;
+    }
+    __syncthreads();
+    // ---- phase C
+    if (j < npaths && s_exp[j]) {
+        const int K = s_K[j], eb = s_eb[j], node = s_node[j], e = s_e[j];
+        const float scale = s_scale[j], val = s_val[j];
+        const bool ok = scale > 0.0f;                                                 // :740
+        for (int k = lane; k < K; k += 32) {
+            const float prior = ok ? __fdiv_rn(sp[k], scale) : 0.0f;                   // :743-744
+            const float w0 = ok ? -val : -0.0f;                                        // :752 / :76
+            hot[eb + k] = make_uint4(__float_as_uint(prior), __float_as_uint(w0), 0u, (uint32_t)sa[k]);
+            cold[eb + k] = make_uint2(0u, 0xffffffffu);
+        }
+        uint4* rec = nodes + (size_t)node * (GG::SQ + 1);
+        if (lane < GG::SQ) rec[lane] = v.leaf_state[(size_t)lane * v.G * R + slot];
+        if (lane == 0) {
+            rec[GG::SQ] = make_uint4((uint32_t)eb, (uint32_t)K, 0u, 0u);
+            cold[e].y = (uint32_t)node;
+            kid[e] = pack_kid(eb, K);
+        }
+    }
+    __syncthreads();
+    // ---- phase D: revert_incomplete_update (:770-774) of every leaf + backpropagate (:758-764) of the expanded ones, leaf order
+    if (j == 0) {
+        unsigned err = s_err;
+        int maxlen = 0;
+        for (int jj = 0; jj < npaths; ++jj) maxlen = s_len[jj] > maxlen ? s_len[jj] : maxlen;
+        for (int i = lane; i < maxlen; i += 32) {
+            int e[kParWarps]; uint4 q[kParWarps]; uint2 c[kParWarps];
+#pragma unroll
+            for (int jj = 0; jj < kParWarps; ++jj) {
+                e[jj] = (jj < npaths && i < s_len[jj]) ? v.paths[((size_t)g * R + jj) * v.MAXD + i] : -1;
+                if (e[jj] >= 0) { q[jj] = hot[e[jj]]; c[jj] = cold[e[jj]]; }
+            }
+#pragma unroll
+            for (int jj = 0; jj < kParWarps; ++jj) {
+                if (e[jj] < 0) continue;
+#pragma unroll
+                for (int jp = 0; jp < jj; ++jp) if (e[jp] == e[jj]) { q[jj] = q[jp]; c[jj] = c[jp]; }    // the latest earlier leaf on this edge
+                q[jj].w = (uint32_t)((int)q[jj].w - v.wu * 512);
+                if (s_exp[jj]) {
+                    const float val = s_val[jj];
+                    const float sv = ((s_len[jj] - 1 - i) & 1) ? -val : val;
+                    const float W = __fadd_rn(__uint_as_float(q[jj].y), sv);
+                    const int n = pk_n(q[jj].w) + 1;
+                    if (n > 65535) err |= TG_MCTS_ERR_COUNT;
+                    const float t = __uint_as_float(c[jj].x);
+                    const float mean = __fdiv_rn(W, (float)(n + 1));
+                    const float var = __fadd_rn(__uint_as_float(q[jj].z), __fmul_rn(__fsub_rn(sv, t), __fsub_rn(sv, mean)));
+                    q[jj].y = __float_as_uint(W); q[jj].z = __float_as_uint(var); q[jj].w += 1u << 16;
+                    c[jj].x = __float_as_uint(mean);
+                }
+            }
+#pragma unroll
+            for (int jj = 0; jj < kParWarps; ++jj) {
+                if (e[jj] < 0) continue;
+                bool last = true;
+#pragma unroll
+                for (int jq = jj + 1; jq < kParWarps; ++jq) last = last && e[jq] != e[jj];
+                if (last) { hot[e[jj]] = q[jj]; cold[e[jj]] = c[jj]; }
+            }
+        }
+        err |= __reduce_or_sync(0xffffffffu, err);
+        if (lane == 0) {                                                               // the root's own statistics, leaf order
+            float W = __int_as_float(h[H_ROOTW]), mean = __int_as_float(h[H_ROOTMEAN]), var = __int_as_float(h[H_ROOTVAR]);
+            int n = h[H_ROOTN], ons = h[H_ROOTONS], sims = 0;
+            for (int jj = 0; jj < npaths; ++jj) {
+                ons -= v.wu;
+                if (!s_exp[jj]) continue;
+                const float val = s_val[jj];
+                const float rv = (s_len[jj] & 1) ? -val : val;
+                W = __fadd_rn(W, rv); n += 1;
+                const float t = mean;
+                mean = __fdiv_rn(W, (float)(n + 1));
+                var = __fadd_rn(var, __fmul_rn(__fsub_rn(rv, t), __fsub_rn(rv, mean)));
+                sims += 1;
+            }
+            h[H_ROOTW] = __float_as_int(W); h[H_ROOTN] = n; h[H_ROOTMEAN] = __float_as_int(mean); h[H_ROOTVAR] = __float_as_int(var);
+            h[H_ROOTONS] = ons;
+            h[H_NPATHS] = 0; h[H_SIMS] += sims; h[H_NNODES] = s_nn; h[H_NEDGES] = s_ne;
+            if (err) { flags |= err; h[H_FLAGS] = (int)flags; }
+            if (pending && (flags & TG_MCTS_ACTIVE) && !(flags & (TG_MCTS_ERR_ANY | kErrAction)) && n < h[H_N0] + v.num_sim)
+                atomicAdd(pending, 1);
+        }
     }
 }
 
@@ -480,6 +789,9 @@ __global__ void __launch_bounds__(kThreads) k_root_expand(View v, const float* _
     unsigned err = 0;
     if (K > v.EC) err |= TG_MCTS_ERR_EDGES;
     if (v.NC < 1) err |= TG_MCTS_ERR_NODES;
+    bool bad = !isfinite(value_root[g]);
+    for (int k = lane; k < K; k += 32) bad = bad || !isfinite(sp[k]);
+    if (__any_sync(0xffffffffu, bad)) err |= TG_MCTS_ERR_NAN;                          // evaluator returned NaN / inf
     if (!err) {
         const float w0 = -value_root[g];                                                // :76, value from :599
         for (int k = lane; k < K; k += 32) {
@@ -706,6 +1018,8 @@ __global__ void k_synth(int A, long long rows, unsigned long long seed, unsigned
 }
 
 // ------------------------------------------------------------------------------------------ host side
+static int g_force_sequential_select = 0;     // tg_mcts_debug_sequential_select: tests compare the two selection kernels
+
 static int check_cfg(const TgMctsConfig* c) {
     if (!c) return set_err(-1, "tg_mcts: null config");
     if (c->n != 9 && c->n != 19) return set_err(-1, "tg_mcts: board size must be 9 or 19");
@@ -776,19 +1090,30 @@ int tg_mcts_wave_begin(const TgMctsConfig* cfg, void* ws, float* obs, void* stre
     if ((reinterpret_cast<uintptr_t>(obs) & 3) != 0) return set_err(-1, "tg_mcts_wave_begin: obs must be 4-byte aligned");
     TG_MCTS_N(cfg, {
         View v = make_view<N>(cfg, ws);
-        k_select<N><<<warp_blocks(v.G), kThreads, 0, (cudaStream_t)stream>>>(v);
+        // one CTA per game with a warp per descent (pipelined through shared memory); the one-warp-per-game kernel remains for
+        // configurations whose pipeline state does not fit the default shared-memory window
+        const size_t sel_smem = (size_t)2 * v.MAXD * v.R * sizeof(int);
+        if (v.R > 1 && v.R <= kParWarps && sel_smem <= 40 * 1024 && !g_force_sequential_select)
+            k_select_par<N><<<(unsigned)v.G, 32 * v.R, sel_smem, (cudaStream_t)stream>>>(v);
+        else
+            k_select<N><<<warp_blocks(v.G), kThreads, 0, (cudaStream_t)stream>>>(v);
         const size_t smem = (size_t)(kThreads / 32) * ((Geo<N>::PLANE_BITS + 31) / 32 + 2) * 4;
         k_leaves<N><<<warp_blocks((long long)v.G * v.R), kThreads, smem, (cudaStream_t)stream>>>(v, obs);
     });
     return set_err((int)cudaGetLastError(), "tg_mcts_wave_begin");
 }
 
+int tg_mcts_debug_sequential_select(int on) { const int old = g_force_sequential_select; g_force_sequential_select = on; return old; }
+
 int tg_mcts_wave_end(const TgMctsConfig* cfg, void* ws, const float* policy, const float* value, int32_t* pending, void* stream) {
     if (check_cfg(cfg) || !ws || !policy || !value) return set_err(-1, "tg_mcts_wave_end");
     TG_MCTS_N(cfg, {
         View v = make_view<N>(cfg, ws);
         const size_t smem = (size_t)(kThreads / 32) * 2 * Geo<N>::A * 4;
-        k_expand<N><<<warp_blocks(v.G), kThreads, smem, (cudaStream_t)stream>>>(v, policy, value, pending);
+        if (v.R > 1 && v.R <= kParWarps && !g_force_sequential_select)
+            k_expand_par<N><<<(unsigned)v.G, 32 * v.R, (size_t)v.R * 2 * Geo<N>::A * 4, (cudaStream_t)stream>>>(v, policy, value, pending);
+        else
+            k_expand<N><<<warp_blocks(v.G), kThreads, smem, (cudaStream_t)stream>>>(v, policy, value, pending);
     });
     return set_err((int)cudaGetLastError(), "tg_mcts_wave_end");
 }

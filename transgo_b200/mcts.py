@@ -52,6 +52,7 @@ def _declare(L):
     L.tg_mcts_begin_move.argtypes = [P, vp, vp, vp]
     L.tg_mcts_wave_begin.argtypes = [P, vp, vp, vp]
     L.tg_mcts_wave_end.argtypes = [P, vp, vp, vp, vp, vp]
+    L.tg_mcts_debug_sequential_select.argtypes = [i32]
     L.tg_mcts_root_stats.argtypes = [P, vp] + [vp] * 7 + [vp]
     L.tg_mcts_advance.argtypes = [P, vp, vp, vp, vp]
     L.tg_mcts_status.argtypes = [P, vp, vp, vp, vp]
