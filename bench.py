@@ -640,7 +640,7 @@ def mcts_bench(torch, dist, dev, rank, world, args):
     pol_r = torch.empty([G, 82], dtype=torch.float32, device=dev)
     val_r = torch.empty([G], dtype=torch.float32, device=dev)
 
-    wave_dev = torch.zeros([1], dtype=torch.int64, device=dev)
+    wave_dev = torch.zeros([2], dtype=torch.int64, device=dev)
 
     def synth(obs):                                            # capturable: the wave index lives on the device
         B = obs.shape[0]
@@ -667,6 +667,42 @@ def mcts_bench(torch, dist, dev, rank, world, args):
                                              "the tree kernels are latency bound (one warp per game, dependent loads + float64 score chain), "
                                              "see profiles/r02_mcts_ncu_summary.txt"}}
     del eng
+    # the same workload with the batch cut into shards whose waves overlap on separate CUDA streams (mcts.ConcurrentMCTS):
+    # every tree kernel is latency bound at 1024 games, so independent shards fill the SMs the single batch leaves idle
+    from transgo_b200.mcts import ConcurrentMCTS
+    best = None
+    for shards in ((2, 4, 8) if not args.quick else (4,)):
+        per = G // shards
+        bufs = [(torch.empty([per * 4, 82], dtype=torch.float32, device=dev), torch.empty([per * 4], dtype=torch.float32, device=dev),
+                 torch.empty([per, 82], dtype=torch.float32, device=dev), torch.empty([per], dtype=torch.float32, device=dev),
+                 torch.zeros([2], dtype=torch.int64, device=dev)) for _ in range(shards)]
+
+        def make_synth(i):
+            pw, vw, pr, vr, wv = bufs[i]
+
+            def synth_i(obs):
+                B = obs.shape[0]
+                p, v = (pw, vw) if B == per * 4 else (pr, vr)
+                _lib.check(L.tg_synth_provider_dev(9, B, 99 + i, _lib.ptr(wv), _lib.ptr(p), _lib.ptr(v), _lib.stream_ptr()))
+                return p, v
+            return synth_i
+        ceng = ConcurrentMCTS([make_synth(i) for i in range(shards)], G, shards=shards, num_simulation=sims, tie_seed=1, game_id0=rank * G,
+                              device=dev, graph_waves=True, waves_per_graph=4)
+        timed_moves(ceng, 1)
+        ceng.search_stats()
+        rate_c, ms_c, n_c, waves_c = timed_moves(ceng, moves)
+        st_c = ceng.search_stats()
+        row = {"value": rate_c, "unit": "MCTS sims/s", "shards": shards, "ms": ms_c, "sims": n_c, "moves": moves, "waves": waves_c,
+               "mean_depth": st_c["mean_depth"], "mean_fanout": st_c["mean_fanout"]}
+        if best is None or rate_c > best["value"]:
+            best = row
+        out.setdefault("tree_only_streams_sweep", []).append({"shards": shards, "value": rate_c, "ms": ms_c})
+        del ceng, bufs
+    bps_c = best["mean_depth"] * (16 * best["mean_fanout"] + 16) + 40 * (best["mean_depth"] + 1) + 24 * best["mean_fanout"] + (4 * 82 + 4) + 16 + 2 * 48 + 3240
+    best.update(bytes_per_sim=bps_c, provider="tg_synth_provider per shard; the shards' waves (one CUDA graph each) are replayed round-robin on "
+                                               "separate streams", roofline={"bound": "hbm", "achieved": best["value"] * bps_c / 1e9 / world, "peak": _hbm_peak(),
+                                                                           "unit": "GB/s", "frac": best["value"] * bps_c / 1e9 / world / _hbm_peak()})
+    out["tree_only_streams"] = best
     if args.tree_only:
         return out
     torch.manual_seed(0)

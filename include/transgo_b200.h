@@ -177,12 +177,15 @@ int tg_mcts_begin_move(const TgMctsConfig* cfg, void* ws, const double* noise, v
 /* wave, first half: selection + terminal backups + leaf step/legal/encode.  obs float32 [G*readouts][10][n][n];
  * rows of unused slots are left untouched. */
 int tg_mcts_wave_begin(const TgMctsConfig* cfg, void* ws, float* obs, void* stream);
+/* number of active games still below N0 + num_simulation (the loop condition of get_action_probs, :660-664) -> out int32[1];
+ * a separate small launch so that the waves themselves carry no counter traffic (ask every few waves) */
+int tg_mcts_pending(const TgMctsConfig* cfg, void* ws, int32_t* out, void* stream);
 /* test hook: 1 = run the selection of every wave with one warp per game in the reference's descent order (the default kernel
  * pipelines the descents of a wave over one warp each and falls back to that order by itself where needed); returns the old value */
 int tg_mcts_debug_sequential_select(int on);
 
 /* wave, second half: policy float32 [G*readouts][A] (softmaxed, model.py:111), value float32 [G*readouts];
- * pending (may be NULL) receives the number of active games still below N0 + num_simulation */
+ * pending (may be NULL; prefer tg_mcts_pending) is INCREMENTED by the number of active games still below N0 + num_simulation */
 int tg_mcts_wave_end(const TgMctsConfig* cfg, void* ws, const float* policy, const float* value, int32_t* pending,
                      void* stream);
 /* root statistics in ACTION order, zero where the action has no edge.  Any pointer may be NULL.
@@ -208,7 +211,8 @@ int tg_mcts_outcome(const TgMctsConfig* cfg, void* ws, uint8_t* winner, float* s
 /* a device-side synthetic policy/value provider for tree-only throughput runs (bench.py): policy[row] = normalised
  * heavy-tailed hash weights of (seed, row, wave), value in (-1, 1).  NOT the reference net. */
 int tg_synth_provider(int n, int64_t rows, uint64_t seed, uint64_t wave, float* policy, float* value, void* stream);
-/* same, with the wave index read from (and then incremented in) device memory, so that the call can sit inside a replayed CUDA graph */
+/* same, with the wave index read from (and then incremented in) device memory, so that the call can sit inside a replayed CUDA
+ * graph.  wave_counter: u64[2], zero-initialised ([0] the wave index, [1] scratch: the block that finishes last advances [0]) */
 int tg_synth_provider_dev(int n, int64_t rows, uint64_t seed, unsigned long long* wave_counter, float* policy, float* value, void* stream);
 
 /* ---------------------------------------------------------------- (4) inference epilogue of the policy/value net

@@ -8,7 +8,7 @@ L = _lib.lib(); _declare(L)
 G = 1024
 pol = torch.empty([G * 4, 82], dtype=torch.float32, device="cuda"); val = torch.empty([G * 4], dtype=torch.float32, device="cuda")
 pol_r = torch.empty([G, 82], dtype=torch.float32, device="cuda"); val_r = torch.empty([G], dtype=torch.float32, device="cuda")
-wave = torch.zeros([1], dtype=torch.int64, device="cuda")
+wave = torch.zeros([2], dtype=torch.int64, device="cuda")
 
 
 def synth(obs):
@@ -31,9 +31,10 @@ for _ in range(n):
     ev[1].record()
     p, v = synth(eng.obs)
     ev[2].record()
-    eng.pending.zero_()
-    L.tg_mcts_wave_end(eng._cfg, eng._w(), _lib.ptr(p), _lib.ptr(v), _lib.ptr(eng.pending), eng._s())
+    L.tg_mcts_wave_end(eng._cfg, eng._w(), _lib.ptr(p), _lib.ptr(v), None, eng._s())
     ev[3].record()
     torch.cuda.synchronize()
     tb += ev[0].elapsed_time(ev[1]); tp += ev[1].elapsed_time(ev[2]); te += ev[2].elapsed_time(ev[3])
 print("wave_begin (select + leaves) %.1f us | provider %.1f us | wave_end (memset + expand) %.1f us" % (tb / n * 1e3, tp / n * 1e3, te / n * 1e3))
+hdr = eng.ws.reshape(-1)[:G * 20].reshape(G, 20)
+print("replays per game: mean %.3f | terminal %.3f | ties>1 %.3f" % (hdr[:, 17].float().mean().item(), hdr[:, 18].float().mean().item(), hdr[:, 19].float().mean().item()))

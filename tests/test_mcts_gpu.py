@@ -273,7 +273,7 @@ def test_graphed_waves_replay_bit_for_bit():
     def make(graph):
         pol = torch.empty([G * 4, 82], dtype=torch.float32, device="cuda"); val = torch.empty([G * 4], dtype=torch.float32, device="cuda")
         pol_r = torch.empty([G, 82], dtype=torch.float32, device="cuda"); val_r = torch.empty([G], dtype=torch.float32, device="cuda")
-        wave = torch.zeros([1], dtype=torch.int64, device="cuda")
+        wave = torch.zeros([2], dtype=torch.int64, device="cuda")
 
         def synth(obs):
             p, v = (pol, val) if obs.shape[0] == G * 4 else (pol_r, val_r)
@@ -479,3 +479,26 @@ def test_pipelined_selection_equals_the_sequential_kernel():
         for x, y in zip(ra, rb):
             for p, q in zip(x, y):
                 assert torch.equal(p, q)
+
+
+def test_concurrent_shards_equal_one_engine(oracle_built):
+    """ConcurrentMCTS (the batch cut into shards whose waves overlap on separate CUDA streams) must play exactly the games
+    one engine plays: game ids -- and with them every hashed tie-break -- are global, games never interact."""
+    from helpers import torch_hash_provider
+    from transgo_b200.mcts import BatchedMCTS, ConcurrentMCTS
+    seed, G, sims = 77, 16, 64
+    one = BatchedMCTS(torch_hash_provider(seed, 9, 5), G, num_simulation=sims, tie_seed=seed, graph_waves=True)
+    many = ConcurrentMCTS(torch_hash_provider(seed, 9, 5), G, shards=4, num_simulation=sims, tie_seed=seed, graph_waves=True)
+    gen = torch.Generator(device="cuda"); gen.manual_seed(3)
+    for move in range(5):
+        noise = one.make_noise(generator=gen)
+        u = torch.rand([G], dtype=torch.float64, device="cuda", generator=gen)
+        a1, p1, o1 = one.get_action_probs(True, noise=noise, u=u)
+        a2, p2, o2 = many.get_action_probs(True, noise=noise, u=u)
+        assert torch.equal(a1, a2) and torch.equal(p1, p2) and torch.equal(o1, o2), move
+        assert torch.equal(one.counts, many.counts) and torch.equal(one.root_n, many.root_n)
+        d1, d2 = one.update_with_action(a1), many.update_with_action(a2)
+        assert torch.equal(d1, d2)
+    assert one.total_sims() == many.total_sims()
+    w1, s1, t1 = one.outcome(); w2, s2, t2 = many.outcome()
+    assert torch.equal(w1, w2) and torch.equal(s1, s2) and torch.equal(t1, t2)

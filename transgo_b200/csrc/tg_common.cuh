@@ -42,6 +42,50 @@ template <int N, int T> __device__ __forceinline__ void planes_to_smem(const BB<
     }
 }
 
+// The same for wide tiles (T >= 8), where the loop above spends most of its instructions on the 10 N lane tests: the tile
+// first parks its (replicated) bitboards in `stage` (10 * W words of word_t as u32 pairs), then lane l assembles whole 32-bit
+// words l, l + T, ... of the game's output string from the <= 32 / N + 2 rows each one overlaps and ORs them into place.
+template <int N> __host__ __device__ constexpr int planes_stage_words() { return 10 * Geo<N>::W * (int)(sizeof(typename Geo<N>::word_t) / 4); }
+
+template <int N, int T> __device__ __forceinline__ void planes_to_smem_staged(const BB<N>* pl, uint32_t* sm, int local, uint32_t* stage) {
+    using G = Geo<N>;
+    constexpr int U = (int)(sizeof(typename G::word_t) / 4);      // u32 per board word
+    constexpr int SW = 10 * G::W * U;
+    const int lane = Tile<T>::lane();
+#pragma unroll
+    for (int i = 0; i < SW; ++i) {
+        if ((i & (T - 1)) == lane) {
+            const typename G::word_t wv = pl[i / (G::W * U)].w[(i / U) % G::W];
+            stage[i] = (uint32_t)(U == 1 ? wv : (wv >> (32 * (i % U))));
+        }
+    }
+    Tile<T>::sync();
+    constexpr int NW = (G::PLANE_BITS + 31) / 32;                  // words of one game's string
+    const int base = local * G::PLANE_BITS;
+    for (int w = lane; w < NW; w += T) {
+        uint32_t out = 0;
+        const int r0 = (32 * w) / N;
+        int r1 = (32 * w + 31) / N;
+        r1 = r1 < 10 * N ? r1 : 10 * N - 1;
+        for (int r = r0; r <= r1; ++r) {
+            const int k = r / N, y = r - k * N;
+            const int wi = y / G::RPW, sh = (y - wi * G::RPW) * G::STRIDE;          // bit offset of the row inside its board word
+            const uint32_t* bw = stage + (k * G::W + wi) * U;
+            uint32_t row;
+            if (U == 1) row = bw[0] >> sh;
+            else row = sh < 32 ? __funnelshift_r(bw[0], bw[1], sh) : (bw[1] >> (sh - 32));
+            row &= (uint32_t)G::row();
+            const int off = r * N - 32 * w;                                         // position of the row's bit 0 in this word
+            out |= off >= 0 ? (row << off) : (row >> (-off));
+        }
+        if (out) {
+            const int bit = base + 32 * w, ds = bit & 31;
+            atomicOr(&sm[bit >> 5], out << ds);
+            if (ds) atomicOr(&sm[(bit >> 5) + 1], out >> (32 - ds));
+        }
+    }
+}
+
 // ngames * PLANE_BITS floats are written by `nthreads` cooperating threads (a CTA or one warp), thread `tid` of them.
 // `out` is 4-byte aligned at least; up to three leading floats are peeled so that the bulk goes out as aligned
 // 128-bit stores.

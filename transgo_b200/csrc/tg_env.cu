@@ -95,7 +95,8 @@ k_encode(const uint4* __restrict__ states, long long G, float* __restrict__ plan
         Pos<N> s; pos_load<N>(s, states, g, G, 1);
         BB<N> pl[10];
         feature_planes<N, T>(s, pl);
-        planes_to_smem<N, T>(pl, sm_bits, local);
+        if constexpr (T >= 8) planes_to_smem_staged<N, T>(pl, sm_bits, local, sm_bits + (planes_smem_bytes<N>(GPC) >> 2) + local * planes_stage_words<N>());
+        else planes_to_smem<N, T>(pl, sm_bits, local);
     }
     __syncthreads();
     const int ng = (int)((G - g0) < GPC ? (G - g0) : GPC);
@@ -375,7 +376,8 @@ template <int N, int T> void launch_legal(cudaStream_t st, const uint4* states, 
 }
 template <int N, int T> void launch_encode(cudaStream_t st, const uint4* states, long long G, float* planes) {
     constexpr int GPC = kThreads / T;
-    const size_t smem = planes_smem_bytes<N>(GPC);
+    // the CTA's bit string, plus (wide tiles) one staging area of the ten bitboards per game (planes_to_smem_staged)
+    const size_t smem = planes_smem_bytes<N>(GPC) + (T >= 8 ? (size_t)GPC * planes_stage_words<N>() * 4 : 0);
     static unsigned long long attr_done = 0;                 // one bit per device: the attribute is per device, not per process
     int dev = 0; cudaGetDevice(&dev);
     if (smem > 48 * 1024 && !((attr_done >> (dev & 63)) & 1ull)) {

@@ -139,6 +139,42 @@ __device__ __forceinline__ void add_ons(int* h, uint4* hot, const int* path, int
     __syncwarp();
 }
 
+// One leaf of a wave, one warp: env.step from the parent (self_play.py:629), getLegalAction (:634, :737) and encode (:798)
+// fused; the planes go straight into the net's input tensor.  sm: this warp's leaf_smem_words<N>() words of shared memory.
+template <int N> __host__ __device__ constexpr int leaf_smem_words() { return (Geo<N>::PLANE_BITS + 31) / 32 + 2 + planes_stage_words<N>(); }
+
+template <int N>
+__device__ __forceinline__ void leaf_work(const View& v, const uint4* nodes, size_t slot, int parent, int action, float* __restrict__ obs,
+                                          uint32_t* sm, int lane) {
+    using GG = Geo<N>;
+    Pos<N> s; pos_load<N>(s, nodes + (size_t)parent * (GG::SQ + 1), 0, 1, 0);
+    // an action the search took from the parent's legal list (trusted): only the groups touching the new stone matter for
+    // captures / ko, so only those are analysed (tg_board.cuh: apply_stone_lazy)
+    if (action == GG::P) apply_pass<N>(s, kPass, v.max_step);
+    else apply_stone_lazy<N, 32>(s, bb_point<N>(action), action, bb_zero<N>(), bb_zero<N>(), bb_zero<N>(), v.max_step);
+    BB<N> pl[10];
+    Groups<N> g2;
+    feature_planes_g<N, 32>(s, pl, g2);
+    const BB<N> lg = legal_points(s, g2);
+    constexpr int WPW = (GG::PLANE_BITS + 31) / 32 + 2;
+    for (int i = lane; i < WPW; i += 32) sm[i] = 0;
+    __syncwarp();
+    planes_to_smem_staged<N, 32>(pl, sm, 0, sm + WPW);
+    __syncwarp();
+    planes_smem_to_global_part<N>(sm, obs + slot * GG::PLANE_BITS, 1, lane, 32);
+    if (lane == 0) {
+        pos_store<N>(s, v.leaf_state, (long long)slot, (long long)v.G * v.R, 1);
+        uint32_t d[GG::DQ * 4];
+#pragma unroll
+        for (int i = 0; i < GG::DQ * 4; ++i) d[i] = 0;
+        bb_to_dense<N>(lg, d);
+        if (!any(lg)) d[GG::P >> 5] |= 1u << (GG::P & 31);
+        uint4* o = reinterpret_cast<uint4*>(v.leaf_legal) + slot * GG::DQ;
+#pragma unroll
+        for (int k = 0; k < GG::DQ; ++k) o[k] = make_uint4(d[4 * k], d[4 * k + 1], d[4 * k + 2], d[4 * k + 3]);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------- selection
 // order-preserving map double -> u64 (finite values and infinities; a NaN maps above everything and is caught by the
 // equality test afterwards), so that the warp arg-max is two REDUX.MAX instead of a five-step shuffle butterfly
@@ -355,8 +391,10 @@ __global__ void __launch_bounds__(kThreads) k_select(View v) {
 // exact tie in the wave (the tie-break draws are numbered in descent-major order).  Both are rare outside the last moves.
 // Launch bounds: a CTA lives for the whole wave of its game (latency bound), so ALL games must be resident at once or the
 // kernel takes two rounds: 8 CTAs of 4 warps per SM (<= 64 registers) hold 1184 games of 9x9, 4 per SM 592 games of 19x19.
-template <int N>
-__global__ void __launch_bounds__(32 * kParWarps, N == 9 ? 8 : 4) k_select_par(View v) {
+// FUSE: the leaves (step + legal mask + feature planes) follow in the same launch.  Off at 19x19, where the leaf code's register
+// needs (ten 7-word bitboards) would spill inside the residency bound above.
+template <int N, bool FUSE>
+__global__ void __launch_bounds__(32 * kParWarps, N == 9 ? 8 : 4) k_select_par(View v, float* __restrict__ obs) {
     using GG = Geo<N>;
     constexpr int MAXR = ScanRegs<N>::MAXR;
     extern __shared__ int sm_sel[];                                   // [MAXD][R] node, then [MAXD][R] child index
@@ -413,7 +451,18 @@ __global__ void __launch_bounds__(32 * kParWarps, N == 9 ? 8 : 4) k_select_par(V
             }
         }
         int ksel; uint32_t ch_sel, kd_sel;
-        if (!scan_pick<N>(v, sr, noisy && node == 0, K, Np, ons_base + same * v.wu, xo, tie0, ties, g, lane, ksel, pk_sel, ch_sel, kd_sel)) { flag |= 4; break; }
+        // exact ties are numbered in the reference's order (all of descent 0's, then descent 1's, ...).  Ties are rare: pick
+        // assuming the earlier descents have none; on a tie wait until they have finished, and pick again if they had any.
+        const int ties_before = ties;
+        if (!scan_pick<N>(v, sr, noisy && node == 0, K, Np, ons_base + same * v.wu, xo, tie0 + ties_before, ties, g, lane, ksel, pk_sel, ch_sel, kd_sel)) { flag |= 4; break; }
+        if (ties != ties_before && j > 0) {
+            int earlier = 0;
+            for (int jp = 0; jp < j; ++jp) { while (vprog[jp] < (1 << 30)) __nanosleep(40); earlier += s_ties[jp]; }
+            if (earlier) {
+                ties = ties_before;
+                scan_pick<N>(v, sr, noisy && node == 0, K, Np, ons_base + same * v.wu, xo, tie0 + earlier + ties_before, ties, g, lane, ksel, pk_sel, ch_sel, kd_sel);
+            }
+        }
         if (depth >= v.MAXD) { flag |= 2; break; }
         if (lane == 0) { path[depth] = eb + ksel; sel_node[L * R + j] = node; sel_k[L * R + j] = ksel; }
         depth += 1;
@@ -436,8 +485,15 @@ __global__ void __launch_bounds__(32 * kParWarps, N == 9 ? 8 : 4) k_select_par(V
     __syncthreads();
     int any_flag = 0, all_ties = 0;
     for (int jp = 0; jp < R; ++jp) { any_flag |= s_flag[jp]; all_ties += s_ties[jp]; }
-    if (any_flag || all_ties > 1) {                                   // CTA-uniform: replay in the reference order
+    uint32_t* sm_planes = reinterpret_cast<uint32_t*>(sm_sel) + j * leaf_smem_words<N>();   // the pipeline state is dead by now
+    if (any_flag) {                                                   // CTA-uniform: replay in the reference order
+        if (threadIdx.x == 0) h[H_SPARE1] += 1;                       // replay counter (diagnostics)
         if (j == 0) select_sequential_cold<N>(v, g, lane);
+        __syncthreads();
+        if (FUSE && j < h[H_NPATHS]) {
+            const size_t slot = (size_t)g * R + j;
+            leaf_work<N>(v, nodes, slot, v.leaf_parent[slot], v.leaf_action[slot], obs, sm_planes, lane);
+        }
         return;
     }
     // ---- commit: every descent found a leaf to evaluate
@@ -446,16 +502,17 @@ __global__ void __launch_bounds__(32 * kParWarps, N == 9 ? 8 : 4) k_select_par(V
         if (i == depth) atomicAdd(&h[H_ROOTONS], v.wu);
         else atomicAdd(&reinterpret_cast<uint32_t*>(hot + path[i])[3], (uint32_t)(v.wu * 512));
     }
-    if (lane == 0) {
-        const size_t slot = (size_t)g * R + j;
-        v.leaf_parent[slot] = node; v.leaf_action[slot] = action; v.path_len[slot] = depth;
-    }
+    const size_t slot = (size_t)g * R + j;
+    if (lane == 0) { v.leaf_parent[slot] = node; v.leaf_action[slot] = action; v.path_len[slot] = depth; }
     if (threadIdx.x == 0) {
         int sd = 0, sf = 0;
         for (int jp = 0; jp < R; ++jp) { sd += plen[jp]; sf += s_fan[jp]; }
         h[H_TIE] = tie0 + all_ties; h[H_NPATHS] = R;
         h[H_STAT_DESC] += R; h[H_STAT_DEPTH] += sd; h[H_STAT_FAN] += sf;
     }
+    // ---- the leaf of this descent: step + legal mask + feature planes, straight into the evaluator's input (k_leaves fused:
+    // a game goes on to its leaves as soon as ITS descents are done instead of waiting for the slowest game of the batch)
+    if (FUSE) leaf_work<N>(v, nodes, slot, node, action, obs, sm_planes, lane);
 }
 
 // ---------------------------------------------------------------------------------------------- leaves
@@ -471,34 +528,7 @@ __global__ void __launch_bounds__(kThreads) k_leaves(View v, float* __restrict__
     const int g = slot / v.R, jj = slot - g * v.R;
     const int* h = v.hdr + (size_t)g * H_WORDS;
     if (jj >= h[H_NPATHS]) return;
-    const uint4* nodes = nodes_of<N>(v, h[H_BUF], g);
-    Pos<N> s; pos_load<N>(s, nodes + (size_t)v.leaf_parent[slot] * (GG::SQ + 1), 0, 1, 0);
-    Groups<N> gr;
-    analyse_groups<N, 32, false>(s.stones[0], s.stones[1], s.player, gr);
-    bool acc;
-    apply_move<N, 32>(s, gr, v.leaf_action[slot], v.max_step, acc, true);
-    BB<N> pl[10];
-    Groups<N> g2;
-    feature_planes_g<N, 32>(s, pl, g2);
-    const BB<N> lg = legal_points(s, g2);
-    constexpr int WPW = (GG::PLANE_BITS + 31) / 32 + 2;       // smem words per warp
-    uint32_t* sm = sm_bits + wib * WPW;
-    for (int i = lane; i < WPW; i += 32) sm[i] = 0;
-    __syncwarp();
-    planes_to_smem<N, 32>(pl, sm, 0);
-    __syncwarp();
-    planes_smem_to_global_part<N>(sm, obs + (size_t)slot * GG::PLANE_BITS, 1, lane, 32);
-    if (lane == 0) {
-        pos_store<N>(s, v.leaf_state, slot, (long long)v.G * v.R, 1);
-        uint32_t d[GG::DQ * 4];
-#pragma unroll
-        for (int i = 0; i < GG::DQ * 4; ++i) d[i] = 0;
-        bb_to_dense<N>(lg, d);
-        if (!any(lg)) d[GG::P >> 5] |= 1u << (GG::P & 31);
-        uint4* o = reinterpret_cast<uint4*>(v.leaf_legal) + (size_t)slot * GG::DQ;
-#pragma unroll
-        for (int k = 0; k < GG::DQ; ++k) o[k] = make_uint4(d[4 * k], d[4 * k + 1], d[4 * k + 2], d[4 * k + 3]);
-    }
+    leaf_work<N>(v, nodes_of<N>(v, h[H_BUF], g), (size_t)slot, v.leaf_parent[slot], v.leaf_action[slot], obs, sm_bits + wib * leaf_smem_words<N>(), lane);
 }
 
 // write one node's edges from a dense legal mask: prior_k = pol[a_k] * (renorm ? 1/scale : raw), W = w0
@@ -992,6 +1022,23 @@ __global__ void k_winner(const float* __restrict__ score, uint8_t* __restrict__ 
 
 __global__ void k_bump(unsigned long long* c) { *c += 1ull; }
 
+// number of games that still need simulations for the current move (the loop condition of self_play.py:660-664); one block
+template <int N>
+__global__ void k_pending(View v, int* __restrict__ out) {
+    __shared__ int total;
+    if (threadIdx.x == 0) total = 0;
+    __syncthreads();
+    int mine = 0;
+    for (int g = threadIdx.x; g < v.G; g += blockDim.x) {
+        const int* h = v.hdr + (size_t)g * H_WORDS;
+        const unsigned flags = (unsigned)h[H_FLAGS];
+        if ((flags & TG_MCTS_ACTIVE) && !(flags & (TG_MCTS_NEED_EXPAND | TG_MCTS_ERR_ANY | kErrAction)) && h[H_ROOTN] < h[H_N0] + v.num_sim) mine += 1;
+    }
+    if (mine) atomicAdd(&total, mine);
+    __syncthreads();
+    if (threadIdx.x == 0) *out = total;
+}
+
 // synthetic provider (bench only): heavy-tailed integer weights -> one f32 division per entry
 __global__ void k_synth(int A, long long rows, unsigned long long seed, unsigned long long wave, const unsigned long long* __restrict__ wave_dev,
                         float* __restrict__ policy, float* __restrict__ value) {
@@ -999,21 +1046,74 @@ __global__ void k_synth(int A, long long rows, unsigned long long seed, unsigned
     const int lane = threadIdx.x & 31;
     if (row >= rows) return;
     if (wave_dev) wave += *wave_dev;            // the wave index lives on the device when the wave is replayed from a CUDA graph
+    // each lane owns actions lane, lane + 32, ...: hash once, keep the weights in registers (A <= 12 * 32)
     unsigned long long sum = 0;
-    for (int a = lane; a < A; a += 32) {
-        const unsigned long long r = mix32(seed + wave * 0x632BE59BD9B4E019ull, (unsigned long long)row, (unsigned long long)a) & 0xFFFFu;
-        sum += 1ull + ((r * r * r) >> 32);
+    unsigned wgt[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) {
+        const int a = lane + 32 * i;
+        wgt[i] = 0;
+        if (a < A) {
+            const unsigned long long r = mix32(seed + wave * 0x632BE59BD9B4E019ull, (unsigned long long)row, (unsigned long long)a) & 0xFFFFu;
+            wgt[i] = (unsigned)(1ull + ((r * r * r) >> 32));
+            sum += wgt[i];
+        }
     }
 #pragma unroll
     for (int s = 16; s >= 1; s >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, s);
     const float total = (float)sum;
-    for (int a = lane; a < A; a += 32) {
-        const unsigned long long r = mix32(seed + wave * 0x632BE59BD9B4E019ull, (unsigned long long)row, (unsigned long long)a) & 0xFFFFu;
-        policy[row * A + a] = __fdiv_rn((float)(1ull + ((r * r * r) >> 32)), total);
+#pragma unroll
+    for (int i = 0; i < 12; ++i) {
+        const int a = lane + 32 * i;
+        if (a < A) policy[row * A + a] = __fdiv_rn((float)wgt[i], total);
     }
     if (lane == 0) {
         const int vv = (int)(mix32(seed ^ 0x5555ull, (unsigned long long)row, wave) & 0xFFFFu) - 32768;
         value[row] = __fdiv_rn((float)vv, 32832.0f);
+    }
+}
+
+// device-side wave counter: every block reads it when it starts; the block that finishes LAST (ticket) advances it, so the
+// increment needs no launch of its own.  ticket lives next to the counter (wave_dev[1]).
+__global__ void k_synth_counted(int A, long long rows, unsigned long long seed, unsigned long long* __restrict__ wave_dev,
+                                float* __restrict__ policy, float* __restrict__ value) {
+    __shared__ unsigned long long s_wave;
+    if (threadIdx.x == 0) s_wave = *reinterpret_cast<volatile unsigned long long*>(wave_dev);
+    __syncthreads();
+    const unsigned long long wave = s_wave;
+    const long long row = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row < rows) {
+        unsigned long long sum = 0;
+        unsigned wgt[12];
+#pragma unroll
+        for (int i = 0; i < 12; ++i) {
+            const int a = lane + 32 * i;
+            wgt[i] = 0;
+            if (a < A) {
+                const unsigned long long r = mix32(seed + wave * 0x632BE59BD9B4E019ull, (unsigned long long)row, (unsigned long long)a) & 0xFFFFu;
+                wgt[i] = (unsigned)(1ull + ((r * r * r) >> 32));
+                sum += wgt[i];
+            }
+        }
+#pragma unroll
+        for (int s = 16; s >= 1; s >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, s);
+        const float total = (float)sum;
+#pragma unroll
+        for (int i = 0; i < 12; ++i) {
+            const int a = lane + 32 * i;
+            if (a < A) policy[row * A + a] = __fdiv_rn((float)wgt[i], total);
+        }
+        if (lane == 0) {
+            const int vv = (int)(mix32(seed ^ 0x5555ull, (unsigned long long)row, wave) & 0xFFFFu) - 32768;
+            value[row] = __fdiv_rn((float)vv, 32832.0f);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned long long t = atomicAdd(&wave_dev[1], 1ull);
+        if (t == (unsigned long long)gridDim.x - 1ull) { wave_dev[1] = 0ull; wave_dev[0] = wave + 1ull; }
     }
 }
 
@@ -1092,15 +1192,29 @@ int tg_mcts_wave_begin(const TgMctsConfig* cfg, void* ws, float* obs, void* stre
         View v = make_view<N>(cfg, ws);
         // one CTA per game with a warp per descent (pipelined through shared memory); the one-warp-per-game kernel remains for
         // configurations whose pipeline state does not fit the default shared-memory window
-        const size_t sel_smem = (size_t)2 * v.MAXD * v.R * sizeof(int);
-        if (v.R > 1 && v.R <= kParWarps && sel_smem <= 40 * 1024 && !g_force_sequential_select)
-            k_select_par<N><<<(unsigned)v.G, 32 * v.R, sel_smem, (cudaStream_t)stream>>>(v);
-        else
+        size_t sel_smem = (size_t)2 * v.MAXD * v.R * sizeof(int);
+        const size_t smem = (size_t)(kThreads / 32) * leaf_smem_words<N>() * 4;
+        if (v.R > 1 && v.R <= kParWarps && sel_smem <= 40 * 1024 && !g_force_sequential_select) {
+            // select + leaves in one launch: a game moves on to its leaves as soon as its own descents are done
+            const size_t planes = (size_t)v.R * leaf_smem_words<N>() * 4;
+            if (planes > sel_smem) sel_smem = planes;
+            if (N == 9) k_select_par<N, true><<<(unsigned)v.G, 32 * v.R, sel_smem, (cudaStream_t)stream>>>(v, obs);
+            else {
+                k_select_par<N, false><<<(unsigned)v.G, 32 * v.R, sel_smem, (cudaStream_t)stream>>>(v, obs);
+                k_leaves<N><<<warp_blocks((long long)v.G * v.R), kThreads, smem, (cudaStream_t)stream>>>(v, obs);
+            }
+        } else {
             k_select<N><<<warp_blocks(v.G), kThreads, 0, (cudaStream_t)stream>>>(v);
-        const size_t smem = (size_t)(kThreads / 32) * ((Geo<N>::PLANE_BITS + 31) / 32 + 2) * 4;
-        k_leaves<N><<<warp_blocks((long long)v.G * v.R), kThreads, smem, (cudaStream_t)stream>>>(v, obs);
+            k_leaves<N><<<warp_blocks((long long)v.G * v.R), kThreads, smem, (cudaStream_t)stream>>>(v, obs);
+        }
     });
     return set_err((int)cudaGetLastError(), "tg_mcts_wave_begin");
+}
+
+int tg_mcts_pending(const TgMctsConfig* cfg, void* ws, int32_t* out, void* stream) {
+    if (check_cfg(cfg) || !ws || !out) return set_err(-1, "tg_mcts_pending");
+    TG_MCTS_N(cfg, { View v = make_view<N>(cfg, ws); k_pending<N><<<1, 256, 0, (cudaStream_t)stream>>>(v, out); });
+    return set_err((int)cudaGetLastError(), "tg_mcts_pending");
 }
 
 int tg_mcts_debug_sequential_select(int on) { const int old = g_force_sequential_select; g_force_sequential_select = on; return old; }
@@ -1159,8 +1273,7 @@ int tg_synth_provider(int n, int64_t rows, uint64_t seed, uint64_t wave, float* 
 
 int tg_synth_provider_dev(int n, int64_t rows, uint64_t seed, unsigned long long* wave_counter, float* policy, float* value, void* stream) {
     if (!policy || !value || !wave_counter || rows <= 0 || (n != 9 && n != 19)) return set_err(-1, "tg_synth_provider_dev");
-    k_synth<<<warp_blocks(rows), kThreads, 0, (cudaStream_t)stream>>>(n * n + 1, rows, seed, 0ull, wave_counter, policy, value);
-    k_bump<<<1, 1, 0, (cudaStream_t)stream>>>(wave_counter);
+    k_synth_counted<<<warp_blocks(rows), kThreads, 0, (cudaStream_t)stream>>>(n * n + 1, rows, seed, wave_counter, policy, value);
     return set_err((int)cudaGetLastError(), "tg_synth_provider_dev");
 }
 

@@ -53,6 +53,7 @@ def _declare(L):
     L.tg_mcts_wave_begin.argtypes = [P, vp, vp, vp]
     L.tg_mcts_wave_end.argtypes = [P, vp, vp, vp, vp, vp]
     L.tg_mcts_debug_sequential_select.argtypes = [i32]
+    L.tg_mcts_pending.argtypes = [P, vp, vp, vp]
     L.tg_mcts_root_stats.argtypes = [P, vp] + [vp] * 7 + [vp]
     L.tg_mcts_advance.argtypes = [P, vp, vp, vp, vp]
     L.tg_mcts_status.argtypes = [P, vp, vp, vp, vp]
@@ -187,9 +188,13 @@ class BatchedMCTS:
     def _wave_body(self):
         _lib.check(self.lib.tg_mcts_wave_begin(self._cfg, self._w(), _lib.ptr(self.obs), self._s()), "tg_mcts_wave_begin")
         policy, value = self._eval(self.obs)
-        self.pending.zero_()
-        _lib.check(self.lib.tg_mcts_wave_end(self._cfg, self._w(), _lib.ptr(policy), _lib.ptr(value), _lib.ptr(self.pending),
-                                             self._s()), "tg_mcts_wave_end")
+        _lib.check(self.lib.tg_mcts_wave_end(self._cfg, self._w(), _lib.ptr(policy), _lib.ptr(value), None, self._s()),
+                   "tg_mcts_wave_end")
+
+    def games_pending(self):
+        """Number of games that still need simulations for this move (one small launch + a host read)."""
+        _lib.check(self.lib.tg_mcts_pending(self._cfg, self._w(), _lib.ptr(self.pending), self._s()), "tg_mcts_pending")
+        return int(self.pending.item())
 
     def run_wave(self):                                     # self_play.py:607-654
         torch = self.torch
@@ -229,13 +234,17 @@ class BatchedMCTS:
                                                _lib.ptr(self.step), self._s()), "tg_mcts_root_stats")
         return self.counts, W, var, prior
 
+    def begin_move(self, noise=None):
+        """Dirichlet mix at the roots (:90-95) and the simulation budget of this move (N0 = inherited visits, :660)."""
+        _lib.check(self.lib.tg_mcts_begin_move(self._cfg, self._w(), _lib.ptr(noise), self._s()), "tg_mcts_begin_move")
+
     def search(self, noise=None):
         """The simulation loop of get_action_probs (:660-664) for all games."""
-        _lib.check(self.lib.tg_mcts_begin_move(self._cfg, self._w(), _lib.ptr(noise), self._s()), "tg_mcts_begin_move")
+        self.begin_move(noise)
         min_waves = -(-self.num_simulation // self.R)
         for _ in range(min_waves):
             self.run_wave()
-        while int(self.pending.item()) > 0:
+        while self.games_pending() > 0:
             for _ in range(self.check_every):
                 self.run_wave()
 
@@ -243,12 +252,20 @@ class BatchedMCTS:
         """Returns (actions int16 [G], pi float64 [G, A], root observations float32 [G, 10, n, n]).
         noise: float64 [G, A] Dirichlet draws in root-edge order (generated on the device when None and is_selfplay);
         u: float64 [G] uniforms for the move draw (torch.rand when None)."""
-        torch = self.torch
-        if is_selfplay and noise is None:
+        noise = self.prepare_noise(is_selfplay, noise)
+        self.search(noise)
+        return self.pick_actions(is_selfplay, u, forced_actions)
+
+    def prepare_noise(self, is_selfplay=True, noise=None):
+        if not is_selfplay:
+            return None
+        if noise is None:
             noise = self.make_noise()
-        if noise is not None:
-            noise = noise.to(torch.float64).contiguous()
-        self.search(noise if is_selfplay else None)
+        return noise.to(self.torch.float64).contiguous()
+
+    def pick_actions(self, is_selfplay=True, u=None, forced_actions=None):
+        """The part of get_action_probs after the simulations (:666-687): pi from the visit counts, temperature draw, root obs."""
+        torch = self.torch
         counts, _, _, _ = self.root_stats()
         c = counts.to(torch.float64)
         c1 = torch.where(counts == 1, torch.zeros_like(c), c)                   # :668
@@ -309,6 +326,186 @@ class BatchedMCTS:
         off = (base - self.ws.data_ptr()) // 4
         view = self.ws.reshape(-1)[off:off + sq * self.G * 4].reshape(sq, self.G, 4)
         view[:, g, :] = torch.from_numpy(arr.copy()).to(self.device)
+
+
+class ConcurrentMCTS:
+    """The same G searches run as `shards` independent BatchedMCTS engines on their own CUDA streams.
+
+    Every tree kernel of a wave is latency bound at the BASELINE batch (one short dependent chain per game, a wave lasts as
+    long as its slowest game), so one batch keeps the SMs mostly idle.  Games never interact: cutting the batch into shards
+    whose waves are issued round-robin on separate streams lets the select of one shard overlap the leaves / evaluator /
+    expand of the others.  Results are those of one engine over all games (game ids, hence every hashed draw, are global).
+
+    `evaluators`: one callable per shard (each sees its own static [G/shards * R, 10, n, n] input tensor), or a single callable
+    used by all shards.  Surface: the BatchedMCTS methods used by the self-play drivers."""
+
+    def __init__(self, evaluators, num_games, shards=4, game_id0=0, device="cuda", graph_waves=False, waves_per_graph=1, **kw):
+        import torch
+        self.torch = torch
+        assert num_games % shards == 0, "num_games must be divisible by shards"
+        self.G, self.S = int(num_games), int(shards)
+        # graph_waves: ONE CUDA graph holds `waves_per_graph` waves of every shard as parallel branches (fork / join inside the
+        # capture), so a replay costs one launch on the host however many shards there are
+        self.graph_waves, self.waves_per_graph = bool(graph_waves), int(waves_per_graph)
+        self._graph, self._eager_rounds = None, 0
+        per = self.G // self.S
+        evs = list(evaluators) if isinstance(evaluators, (list, tuple)) else [evaluators] * self.S
+        self.device = torch.device(device)
+        self.streams = [torch.cuda.Stream(device=self.device) for _ in range(self.S)]
+        self.engines = []
+        for i in range(self.S):
+            with torch.cuda.stream(self.streams[i]):
+                self.engines.append(BatchedMCTS(evs[i], per, game_id0=game_id0 + i * per, device=device, **kw))
+        torch.cuda.synchronize()
+        e0 = self.engines[0]
+        self.n, self.A, self.P, self.R, self.num_simulation, self.cfg = e0.n, e0.A, e0.P, e0.R, e0.num_simulation, e0.cfg
+        self.check_every = e0.check_every
+
+    # -- stream plumbing: shard work is ordered after what the caller already queued, the caller after the shards
+    def _fork(self):
+        ev = self.torch.cuda.Event(); ev.record()
+        for st in self.streams:
+            st.wait_event(ev)
+
+    def _join(self):
+        cur = self.torch.cuda.current_stream()
+        for st in self.streams:
+            ev = self.torch.cuda.Event(); ev.record(st)
+            cur.wait_event(ev)
+
+    def _each(self, fn):
+        self._fork()
+        out = []
+        for i, e in enumerate(self.engines):
+            with self.torch.cuda.stream(self.streams[i]):
+                out.append(fn(i, e))
+        self._join()
+        return out
+
+    def _split(self, t):
+        return [None] * self.S if t is None else list(t.chunk(self.S, 0))
+
+    @property
+    def waves(self):
+        return sum(e.waves for e in self.engines)
+
+    @property
+    def workspace_bytes(self):
+        return sum(e.workspace_bytes for e in self.engines)
+
+    def reset_root(self):
+        self._each(lambda i, e: e.reset_root())
+
+    def reset_games(self, mask):
+        ms = self._split(mask)
+        self._each(lambda i, e: e.reset_games(ms[i]))
+
+    def search(self, noise=None):
+        torch = self.torch
+        ns = self._split(noise)
+        self._fork()
+        for i, e in enumerate(self.engines):
+            with torch.cuda.stream(self.streams[i]):
+                e.begin_move(ns[i])
+        min_waves = -(-self.num_simulation // self.R)
+        if self.graph_waves:
+            self._join()
+            done = 0
+            while done < min_waves or any(e.games_pending() > 0 for e in self.engines):
+                done += self._round()
+            return
+        for _ in range(min_waves):                                    # waves issued round-robin: the shards overlap on the GPU
+            for i, e in enumerate(self.engines):
+                with torch.cuda.stream(self.streams[i]):
+                    e.run_wave()
+        live = list(range(self.S))
+        while live:
+            nxt = []
+            for i in live:
+                with torch.cuda.stream(self.streams[i]):
+                    if self.engines[i].games_pending() > 0:
+                        for _ in range(self.check_every):
+                            self.engines[i].run_wave()
+                        nxt.append(i)
+            live = nxt
+        self._join()
+
+    def _round(self):
+        """`waves_per_graph` waves of every shard; eager the first time (lazy initialisation), then captured once as a graph
+        with one branch per shard and replayed.  Games whose budget is met sit the extra waves out (k_select skips them)."""
+        torch = self.torch
+        if self._graph is not None:
+            self._graph.replay()
+        elif self._eager_rounds >= 1:
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._round_body()
+            self._graph = g
+            g.replay()
+        else:
+            self._round_body()
+            self._eager_rounds += 1
+        for e in self.engines:
+            e.waves += self.waves_per_graph
+        return self.waves_per_graph
+
+    def _round_body(self):
+        torch = self.torch
+        cur = torch.cuda.current_stream()
+        for i, e in enumerate(self.engines):
+            st = self.streams[i]
+            st.wait_stream(cur)
+            with torch.cuda.stream(st):
+                for _ in range(self.waves_per_graph):
+                    e._wave_body()
+        for st in self.streams:
+            cur.wait_stream(st)
+
+    def get_action_probs(self, is_selfplay=True, noise=None, u=None, forced_actions=None):
+        torch = self.torch
+        ns = self._each(lambda i, e: e.prepare_noise(is_selfplay, self._split(noise)[i]))
+        self.search(torch.cat(ns, 0) if is_selfplay else None)
+        us, fs = self._split(u), self._split(forced_actions)
+        outs = self._each(lambda i, e: e.pick_actions(is_selfplay, us[i], fs[i]))
+        return tuple(torch.cat([o[k] for o in outs], 0) for k in range(3))
+
+    def update_with_action(self, actions):
+        acts = self._split(actions)
+        return self.torch.cat(self._each(lambda i, e: e.update_with_action(acts[i])), 0)
+
+    def root_stats(self, full=False):
+        outs = self._each(lambda i, e: e.root_stats(full))
+        return tuple(None if outs[0][k] is None else self.torch.cat([o[k] for o in outs], 0) for k in range(4))
+
+    @property
+    def counts(self):
+        return self.torch.cat([e.counts for e in self.engines], 0)
+
+    @property
+    def root_n(self):
+        return self.torch.cat([e.root_n for e in self.engines], 0)
+
+    @property
+    def step(self):
+        return self.torch.cat([e.step for e in self.engines], 0)
+
+    def outcome(self, want_territory=True):
+        outs = self._each(lambda i, e: e.outcome(want_territory))
+        return tuple(None if outs[0][k] is None else self.torch.cat([o[k] for o in outs], 0) for k in range(3))
+
+    def check_status(self):
+        return np.concatenate(self._each(lambda i, e: e.check_status()))
+
+    def total_sims(self):
+        return sum(self._each(lambda i, e: e.total_sims()))
+
+    def search_stats(self):
+        st = self._each(lambda i, e: e.search_stats())
+        n = sum(x["descents"] for x in st)
+        d = sum(x["descents"] * x["mean_depth"] for x in st)
+        k = sum(x["descents"] * x["mean_depth"] * x["mean_fanout"] for x in st)
+        return dict(descents=n, mean_depth=d / max(1, n), mean_fanout=k / max(1.0, d))
 
 
 class _Root:
