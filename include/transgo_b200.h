@@ -215,6 +215,25 @@ int tg_synth_provider(int n, int64_t rows, uint64_t seed, uint64_t wave, float* 
  * graph.  wave_counter: u64[2], zero-initialised ([0] the wave index, [1] scratch: the block that finishes last advances [0]) */
 int tg_synth_provider_dev(int n, int64_t rows, uint64_t seed, unsigned long long* wave_counter, float* policy, float* value, void* stream);
 
+/* ---------------------------------------------------------------- (3b) trajectory assembly + root noise
+ * self_play.py:931-965 for a batch of games in ONE launch: every recorded position (t < length[g]) of every finished game
+ * (fin[g] != 0; NULL = all) is labelled -- z = +1 iff the mover is the winner, ownership = territory from the mover's view --
+ * expanded with the eight board symmetries in the reference's order (for i in 1..4: rot90 by i, then its fliplr;
+ * symmetries = 1: as played) and written at row (ring_index + r) % capacity of the output tensors, r numbering rows
+ * game-major / position / symmetry.  hist_obs float32 [G][T][C][n][n], hist_pi float32 [G][T][A], hist_player int32 [G][T]
+ * (1 black, 2 white), length int64 [G] (NULL = one position per game), winner uint8 [G], territory float32 [G][P] (tg_mcts_outcome);
+ * out_obs [capacity][C][n][n], out_pi [capacity][A], out_z [capacity], out_own [capacity][P]; rows_out int64[1] (may be NULL)
+ * receives the number of rows written. */
+int tg_traj_assemble(int n, int channels, int64_t G, int64_t T, const float* hist_obs, const float* hist_pi, const int32_t* hist_player,
+                     const int64_t* length, const uint8_t* fin, const uint8_t* winner, const float* territory, float* out_obs,
+                     float* out_pi, float* out_z, float* out_own, int64_t capacity, int64_t ring_index, int symmetries, int64_t* rows_out,
+                     void* stream);
+/* Node_V.dirichlet_prior's noise (self_play.py:90-95) on the device: noise float64 [G][A], row g ~ Dirichlet(alpha) over its
+ * first root_k[g] entries (root-edge order), zeros beyond.  Counter-based (Philox4x32-10 keyed by seed; counter = child, global
+ * game id, move, draw), so a shard of games draws what the full batch would. */
+int tg_dirichlet(double* noise, const int32_t* root_k, int64_t G, int A, double alpha, uint64_t seed, uint32_t move, int64_t game_id0,
+                 void* stream);
+
 /* ---------------------------------------------------------------- (4) inference epilogue of the policy/value net
  * One pass over NHWC bf16 activations [rows][channels] (channels % 8 == 0):
  *     sum = x + alpha * (y + ybias[c])   (y may be NULL: sum = x; ybias may be NULL)   -> sum_out (may be NULL)

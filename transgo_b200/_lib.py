@@ -32,6 +32,8 @@ def _declare(L):
                                  ctypes.c_int, c_vp, c_vp, ctypes.c_int, c_vp]
     L.tg_env_playout_tile.argtypes = [ctypes.c_int, c_i64, ctypes.c_int]
     L.tg_sub_encode.argtypes = [ctypes.c_int, c_vp, c_i64, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_vp, c_vp]
+    L.tg_traj_assemble.argtypes = [ctypes.c_int, ctypes.c_int, c_i64, c_i64] + [c_vp] * 11 + [c_i64, c_i64, ctypes.c_int, c_vp, c_vp]
+    L.tg_dirichlet.argtypes = [c_vp, c_vp, c_i64, ctypes.c_int, ctypes.c_double, ctypes.c_uint64, ctypes.c_uint32, c_i64, c_vp]
     L.tg_net_add_bn_relu.argtypes = [c_vp, c_vp, ctypes.c_float, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, ctypes.c_int, c_vp]
     L.tg_net_attention.argtypes = [c_vp, c_vp, ctypes.c_float, c_vp, c_vp, c_vp, c_i64, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_vp]
     # the reference's 15 symbols (go_env.h:23-71), typed exactly as GoEnv/environment.py:43-90 types them

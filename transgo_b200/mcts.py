@@ -124,6 +124,7 @@ class BatchedMCTS:
         self.status = torch.zeros([G], dtype=torch.int32, device=self.device)
         self.sims = torch.zeros([1], dtype=torch.int64, device=self.device)
         self.waves = 0
+        self._noise_seed, self._noise_calls = int(tie_seed) ^ 0x5DEECE66D, 0
         self.reset_root()
 
     # ---------------------------------------------------------------- plumbing
@@ -212,15 +213,22 @@ class BatchedMCTS:
         self._wave_calls += 1
         self.waves += 1
 
-    def make_noise(self, alpha=0.03, generator=None):
-        """Dirichlet(alpha) over each root's K children, float64 [G, A] in edge order (Node_V.dirichlet_prior :90-95)."""
+    def make_noise(self, alpha=0.03, generator=None, seed=None):
+        """Dirichlet(alpha) over each root's K children, float64 [G, A] in edge order (Node_V.dirichlet_prior :90-95), drawn on
+        the device by tg_dirichlet (Philox counters keyed by seed / global game id / call number: shards draw what the full
+        batch would).  `generator` (a torch.Generator) only supplies the seed."""
         torch = self.torch
         self.root_stats()
-        conc = torch.full([self.G, self.A], alpha, dtype=torch.float64, device=self.device)
-        gam = torch._standard_gamma(conc) if generator is None else torch._standard_gamma(conc, generator=generator)
-        k = torch.arange(self.A, device=self.device)[None, :] < self.root_k[:, None]
-        gam = torch.where(k, gam, torch.zeros_like(gam))
-        return gam / gam.sum(1, keepdim=True).clamp_min(1e-300)
+        if seed is None:
+            if generator is not None:
+                seed = int(torch.randint(0, 2 ** 62, [1], generator=generator, device=generator.device).item())
+            else:
+                seed = self._noise_seed
+        self._noise_calls += 1
+        noise = torch.empty([self.G, self.A], dtype=torch.float64, device=self.device)
+        _lib.check(self.lib.tg_dirichlet(_lib.ptr(noise), _lib.ptr(self.root_k), self.G, self.A, float(alpha), int(seed) & (2 ** 64 - 1),
+                                         self._noise_calls & 0xffffffff, int(self.cfg.game_id0), self._s()), "tg_dirichlet")
+        return noise
 
     def root_stats(self, full=False):
         torch = self.torch

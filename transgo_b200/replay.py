@@ -38,6 +38,17 @@ class ReplayRing:
         self.full = self.full or (self.index + b >= self.capacity)
         self.index = (self.index + b) % self.capacity
 
+    def append_games(self, hist_obs, hist_pi, hist_player, length, winner, terr, fin=None, augment=True):
+        """Finished games -> labelled (x8) rows written by ONE kernel launch straight into the ring's tensors at the write
+        position (csrc/tg_traj.cu; self_play.py:931-965 + replay_buffer.py:30-34).  Returns the number of rows appended."""
+        from .selfplay import assemble_trajectories
+        assert self.obs.dtype == torch.float32, "append_games writes float32 rows"
+        *_, rows = assemble_trajectories(hist_obs, hist_pi, hist_player, length, winner, terr, fin=fin, augment=augment,
+                                         out=(self.obs, self.pi, self.z, self.own), index=self.index)
+        self.full = self.full or (self.index + rows >= self.capacity)
+        self.index = (self.index + rows) % self.capacity
+        return rows
+
     def sample(self, batch_size, generator=None):
         """replay_buffer.py:36-47: without replacement when enough data, with replacement otherwise."""
         n = len(self)

@@ -26,6 +26,58 @@ def augment8(obs, pi, z, own, n):
     return o, p, z.repeat_interleave(8, 0), w
 
 
+def assemble_trajectories(hist_obs, hist_pi, hist_player, length, winner, terr, fin=None, augment=True, out=None, index=0):
+    """self_play.py:931-965 for a batch of games in one kernel launch (csrc/tg_traj.cu): label every recorded position of the
+    finished games (z from the winner, ownership from the mover's view), expand x8 in the reference's symmetry order and write
+    the rows either into fresh tensors (out=None) or straight into a replay ring's tensors at its write position
+    (out=(obs, pi, z, own), index=ring.index; rows wrap modulo the capacity).
+    hist_obs [G,T,C,n,n] f32, hist_pi [G,T,A] f32, hist_player [G,T] i32, length [G] i64, winner [G] u8, terr [G,P] f32,
+    fin [G] bool/u8 or None.  Returns (obs, pi, z, own, rows)."""
+    from . import _lib
+    L = _lib.lib()
+    G, T, C, n = hist_obs.shape[0], hist_obs.shape[1], hist_obs.shape[2], hist_obs.shape[3]
+    A, P = n * n + 1, n * n
+    dev = hist_obs.device
+    sym = 8 if augment else 1
+    length = None if length is None else length.to(torch.int64).contiguous()
+    fin_u8 = None if fin is None else fin.to(torch.uint8).contiguous()
+    if length is None:
+        rows = (G if fin is None else int(fin_u8.sum().item())) * sym
+    else:
+        rows = int((length if fin is None else length * fin_u8.to(torch.int64)).sum().item()) * sym
+    if out is None:
+        cap = max(rows, 1)
+        out = (torch.empty([cap, C, n, n], dtype=torch.float32, device=dev), torch.empty([cap, A], dtype=torch.float32, device=dev),
+               torch.empty([cap], dtype=torch.float32, device=dev), torch.empty([cap, P], dtype=torch.float32, device=dev))
+        index = 0
+    o_obs, o_pi, o_z, o_own = out
+    cap = o_obs.shape[0]
+    assert rows <= cap, "more rows than the output holds: append in smaller batches"
+    assert all(t.is_contiguous() and t.dtype == torch.float32 for t in (hist_obs, hist_pi, terr, o_obs, o_pi, o_z, o_own))
+    _lib.check(L.tg_traj_assemble(n, C, G, T, _lib.ptr(hist_obs), _lib.ptr(hist_pi), _lib.ptr(hist_player.to(torch.int32).contiguous()),
+                                  _lib.ptr(length), _lib.ptr(fin_u8), _lib.ptr(winner.to(torch.uint8).contiguous()), _lib.ptr(terr),
+                                  _lib.ptr(o_obs), _lib.ptr(o_pi), _lib.ptr(o_z), _lib.ptr(o_own), cap, int(index), sym, None,
+                                  _lib.stream_ptr(device=dev)), "tg_traj_assemble")
+    if cap == max(rows, 1) and index == 0:
+        return o_obs[:rows], o_pi[:rows], o_z[:rows], o_own[:rows], rows
+    return o_obs, o_pi, o_z, o_own, rows
+
+
+def augment8_rows(obs, pi, z, own, n, out=None, index=0):
+    """The x8 expansion of ALREADY LABELLED rows (the receiver side of selfplay_round: the wire carries each position once) with
+    the same kernel: every row is a one-position game whose mover is black and whose winner is black iff z > 0, so the kernel's
+    labels reproduce z and own.  Writes into fresh tensors or into a ring's tensors at `index`."""
+    B = obs.shape[0]
+    dev = obs.device
+    if B == 0:
+        return (obs, pi, z, own) if out is None else out
+    player = torch.ones([B, 1], dtype=torch.int32, device=dev)
+    winner = torch.where(z > 0, 1, 2).to(torch.uint8)
+    o, p, zz, w, _ = assemble_trajectories(obs.reshape(B, 1, *obs.shape[1:]).float().contiguous(), pi.reshape(B, 1, -1).float().contiguous(),
+                                           player, None, winner, own.float().contiguous(), augment=True, out=out, index=index)
+    return o, p, zz, w
+
+
 class SelfPlayWorker:
     """One self-play rank: plays `num_games` games to the end and returns the labelled (optionally augmented) positions."""
 
@@ -48,15 +100,12 @@ class SelfPlayWorker:
             alive = alive & (done == 0)
             moves += 1
         winner, score, terr = s.outcome(want_territory=True)          # self_play.py:931-937
-        obs = torch.stack(obs_l, 1); pi = torch.stack(pi_l, 1)         # [G, T, ...]
+        obs = torch.stack(obs_l, 1).contiguous(); pi = torch.stack(pi_l, 1).contiguous()   # [G, T, ...]
         player = torch.stack(player_l, 1); valid = torch.stack(alive_l, 1)
-        z = torch.where(player == winner[:, None].to(player.dtype), 1.0, -1.0)
-        own = torch.where((player == 1)[:, :, None], terr[:, None, :], -terr[:, None, :])
-        obs, pi, z, own = obs[valid], pi[valid], z[valid], own[valid]
-        if augment:
-            obs, pi, z, own = augment8(obs, pi, z, own, n)
+        per_game = valid.sum(1)                                       # games stay alive for a prefix of the moves
+        obs, pi, z, own, rows = assemble_trajectories(obs, pi, player, per_game, winner, terr, augment=augment)
         return dict(obs=obs, pi=pi, z=z, own=own, winner=winner, score=score, moves=moves,
-                    positions=int(valid.sum().item()), positions_per_game=valid.sum(1))
+                    positions=rows // (8 if augment else 1), positions_per_game=per_game)
 
 
 def _play_continuous(self, min_positions, augment=True, max_moves=None, pacing=None, wait_fn=None, game_total_num=None):
@@ -80,29 +129,24 @@ def _play_continuous(self, min_positions, augment=True, max_moves=None, pacing=N
                           player=torch.zeros([G, T], dtype=torch.int32, device=dev),
                           length=torch.zeros([G], dtype=torch.int64, device=dev))
     h = self._hist
-    rows = torch.arange(G, device=dev)
-    cols = torch.arange(T, device=dev)
+    gi = torch.arange(G, device=dev)
     out = dict(obs=[], pi=[], z=[], own=[])
     positions = games = moves = 0
     throttled = False
     while positions < min_positions and (max_moves is None or moves < max_moves):
         actions, pi, obs = s.get_action_probs(is_selfplay=True)
         t = h["length"].clamp_max(T - 1)
-        h["obs"][rows, t] = obs
-        h["pi"][rows, t] = pi.to(torch.float32)
-        h["player"][rows, t] = 1 + ((s.step - 1) % 2)            # black moves on odd step counts (board.cc:15,19,537)
+        h["obs"][gi, t] = obs
+        h["pi"][gi, t] = pi.to(torch.float32)
+        h["player"][gi, t] = (1 + ((s.step - 1) % 2)).to(torch.int32)            # black moves on odd step counts (board.cc:15,19,537)
         h["length"] += 1
         fin = s.update_with_action(actions).bool()
         moves += 1
         if bool(fin.any()):
             winner, _, terr = s.outcome(want_territory=True)       # self_play.py:931-937 (roots of finished games are final)
-            valid = (cols[None, :] < h["length"][:, None]) & fin[:, None]
-            gidx = rows[:, None].expand(G, T)[valid]
-            pl = h["player"][valid]
-            out["obs"].append(h["obs"][valid]); out["pi"].append(h["pi"][valid])
-            out["z"].append(torch.where(pl == winner[gidx].to(pl.dtype), 1.0, -1.0))
-            out["own"].append(torch.where((pl == 1)[:, None], terr[gidx], -terr[gidx]))
-            positions += int(valid.sum().item())
+            o, p, zz, w, rows = assemble_trajectories(h["obs"], h["pi"], h["player"], h["length"], winner, terr, fin=fin, augment=augment)
+            out["obs"].append(o); out["pi"].append(p); out["z"].append(zz); out["own"].append(w)
+            positions += rows // (8 if augment else 1)
             games += int(fin.sum().item())
             if pacing is not None:
                 for npos in h["length"][fin].tolist():
@@ -120,8 +164,6 @@ def _play_continuous(self, min_positions, augment=True, max_moves=None, pacing=N
     else:
         obs, pi = torch.zeros([0, 10, n, n], device=dev), torch.zeros([0, A], device=dev)
         z, own = torch.zeros([0], device=dev), torch.zeros([0, n * n], device=dev)
-    if augment and obs.shape[0]:
-        obs, pi, z, own = augment8(obs, pi, z, own, n)
     return dict(obs=obs, pi=pi, z=z, own=own, positions=positions, games=games, moves=moves, throttled=throttled)
 
 
@@ -188,7 +230,7 @@ def selfplay_round(worker, model, ring=None, pacing=None, src=0, dst=0, augment=
     if sw: sw.mark("gather")
     rank = dist.get_rank() if multi else dst
     if augment and rank == dst and rows is not None:
-        rows = augment8(*rows, worker.n)
+        rows = augment8_rows(*rows, worker.n)
     stats = dict(moves=out["moves"], positions=out["positions"], games=games_here, games_all_ranks=int(sum(games_all)),
                  black_wins=int((out["winner"] == 1).sum().item()), appended=0)
     if rank == dst and rows is not None:
