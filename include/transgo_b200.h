@@ -111,6 +111,13 @@ int tg_env_score(int n, const void* states, int64_t G, float komi, float* score,
 int tg_env_playout(int n, void* states, int64_t G, int plies, int max_step, uint64_t seed, int64_t game_id0,
                    int no_eye, int16_t* trace_actions, unsigned long long* plies_done, int tile, void* stream);
 
+/* The same launch with the two steps that frame a playout folded in (one launch instead of three for "reset, play to the end,
+ * score"): from_reset != 0 starts every game from the empty board (tg_env_reset) without reading `states` first; score_out
+ * (float32[G], may be NULL) receives getScore of the final positions (area(black) - area(white) - komi, go_env.cc:126-130). */
+int tg_env_playout_scored(int n, void* states, int64_t G, int plies, int max_step, uint64_t seed, int64_t game_id0,
+                          int no_eye, int16_t* trace_actions, unsigned long long* plies_done, int from_reset,
+                          float* score_out, float komi, int tile, void* stream);
+
 /* the layout tg_env_playout uses for (n, G, tile): TG_TILE_ROWS or the number of lanes per game (tile = 0: measured choice) */
 int tg_env_playout_tile(int n, int64_t G, int tile);
 

@@ -313,3 +313,30 @@ def test_headline_launch_against_the_reference_engine_itself():
             sc = L.getTerritory(a_blob, terr.ctypes.data)
             assert np.array_equal(planes_g[g], enc) and sc_g[g] == sc and np.array_equal(te_g[g], terr), g
     assert total == played
+
+
+@pytest.mark.parametrize("n,G,tile", [(9, 4096, 0), (9, 20000, 0), (19, 300, 0), (9, 513, 8 | 64), (19, 64, -1)])
+def test_fused_reset_playout_score_equals_three_launches(n, G, tile):
+    """tg_env_playout_scored (reset + playout + final score in ONE launch of the incremental kernel; separate launches behind the
+    same entry point for the other layouts) against reset(), playout(), score()."""
+    from transgo_b200.environment import BatchedGoEnv
+    a = BatchedGoEnv(G, board_size=n, tile=tile)
+    a.playout(30, seed=3)                                             # dirty states: from_reset must ignore them
+    sa = torch.empty([G], dtype=torch.float32, device="cuda")
+    ta = torch.full([a.max_step + 1, G], -9, dtype=torch.int16, device="cuda")
+    a.playout(a.max_step + 1, seed=11, trace=ta, from_reset=True, score_out=sa)
+    b = BatchedGoEnv(G, board_size=n, tile=tile)
+    tb = torch.full([b.max_step + 1, G], -9, dtype=torch.int16, device="cuda")
+    b.reset(); b.playout(b.max_step + 1, seed=11, trace=tb)
+    torch.cuda.synchronize()
+    assert torch.equal(a.states, b.states) and torch.equal(ta, tb) and torch.equal(sa, b.score())
+    # scoring alone, mid-game (not from reset): 40 more plies of a running game + its score
+    c = BatchedGoEnv(G, board_size=n, tile=tile); c.playout(25, seed=5)
+    d = BatchedGoEnv(G, board_size=n, tile=tile); d.playout(25, seed=5)
+    sc = torch.empty([G], dtype=torch.float32, device="cuda")
+    c.playout(40, seed=5, score_out=sc); d.playout(40, seed=5)
+    assert torch.equal(c.states, d.states) and torch.equal(sc, d.score())
+    e = BatchedGoEnv(G, board_size=n, tile=tile)
+    se = torch.empty([G], dtype=torch.float32, device="cuda")
+    e.playout(0, from_reset=True, score_out=se)                        # stone-less boards score -komi (board.cc:932-935)
+    assert bool((se == -7.5).all())

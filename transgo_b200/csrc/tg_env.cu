@@ -204,7 +204,8 @@ k_playout_wu(uint4* __restrict__ states, long long G, int plies, int max_step, u
 template <int N, int T, bool NOEYE>
 __global__ void __launch_bounds__(kThreads)
 k_playout_inc(uint4* __restrict__ states, long long G, int plies, int max_step, unsigned long long seed, long long game_id0,
-              int16_t* __restrict__ trace, unsigned long long* __restrict__ plies_done) {
+              int16_t* __restrict__ trace, unsigned long long* __restrict__ plies_done, int from_reset, float* __restrict__ score_out,
+              float komi) {
     using namespace inc;
     const long long g = (blockIdx.x * (long long)blockDim.x + threadIdx.x) / T;
     const bool exists = g < G;
@@ -214,15 +215,16 @@ k_playout_inc(uint4* __restrict__ states, long long G, int plies, int max_step, 
     // lane roles: j = 0..3 -> the E / W / S / N neighbour of the new stone (an enemy group), j >= 4 -> the stone itself
     const int sl = j == 0 ? 1 : (j == 2 ? DGeo<N>::STR : 0), sr = j == 1 ? 1 : (j == 3 ? DGeo<N>::STR : 0);
     const bool enemy_lane = j < 4;
-    Pos<N> p0; pos_reset(p0); p0.terminated = 1;
-    if (exists) pos_load<N>(p0, states, g, G, 1);
+    // from_reset: the games start from the empty board (Reset, go_env.cc:34-41) without reading the states first
+    Pos<N> p0; pos_reset(p0); p0.terminated = exists && from_reset ? 0 : 1;
+    if (exists && !from_reset) pos_load<N>(p0, states, g, G, 1);
     Game<N> s;
     const bool first_black = p0.player == kBlack;
     s.a = to_dense<N>(bb_select(first_black, p0.stones[0], p0.stones[1]));
     s.b = to_dense<N>(bb_select(first_black, p0.stones[1], p0.stones[0]));
     s.last1 = p0.last1; s.last2 = p0.last2; s.ko_loc = p0.ko_loc; s.ko_age = p0.ko_age; s.step = p0.step; s.player = p0.player;
     s.ko_color = p0.ko_color; s.terminated = p0.terminated;
-    s.l1 = atari_from_scratch<N, T>(s.a, s.b);
+    s.l1 = from_reset ? dzero<N>() : atari_from_scratch<N, T>(s.a, s.b);
     const unsigned long long hash_head = mix32_head(seed, (unsigned long long)(game_id0 + g));
     int played = 0;
     for (int t = 0; t < plies; t += 2) {
@@ -238,6 +240,10 @@ k_playout_inc(uint4* __restrict__ states, long long G, int plies, int max_step, 
                 if (trace && exists && lead) trace[(long long)(t + h) * G + g] = (int16_t)action;
             }
         }
+    }
+    if (score_out) {                                               // kernel-uniform: getScore of the final position (go_env.cc:126-130)
+        const int raw = area_score_dense<N, T>(dsel<N>(first_black, s.a, s.b), dsel<N>(first_black, s.b, s.a));
+        if (exists && lead) score_out[g] = (float)raw - komi;
     }
     if (exists && lead) {
         p0.stones[0] = from_dense<N>(dsel<N>(first_black, s.a, s.b));
@@ -410,13 +416,14 @@ template <int N, int TC> void launch_playout(cudaStream_t st, uint4* states, lon
 }
 
 template <int N, int T> int launch_playout_inc(cudaStream_t st, uint4* states, long long G, int plies, int max_step, unsigned long long seed,
-                                                long long game_id0, int no_eye, int16_t* trace, unsigned long long* plies_done) {
+                                                long long game_id0, int no_eye, int16_t* trace, unsigned long long* plies_done,
+                                                int from_reset = 0, float* score_out = nullptr, float komi = 0.0f) {
     // a playout CTA lives for the whole game: with few warps per SM one-warp CTAs spread them evenly over the 148 SMs
     const long long warps = (G * T + 31) / 32;
     const int threads = warps < 148LL * 16 ? 32 : kThreads;
     const unsigned blocks = (unsigned)((G * T + threads - 1) / threads);
-    if (no_eye) k_playout_inc<N, T, true><<<blocks, threads, 0, st>>>(states, G, plies, max_step, seed, game_id0, trace, plies_done);
-    else k_playout_inc<N, T, false><<<blocks, threads, 0, st>>>(states, G, plies, max_step, seed, game_id0, trace, plies_done);
+    if (no_eye) k_playout_inc<N, T, true><<<blocks, threads, 0, st>>>(states, G, plies, max_step, seed, game_id0, trace, plies_done, from_reset, score_out, komi);
+    else k_playout_inc<N, T, false><<<blocks, threads, 0, st>>>(states, G, plies, max_step, seed, game_id0, trace, plies_done, from_reset, score_out, komi);
     return 0;
 }
 
@@ -495,13 +502,19 @@ int tg_env_playout_tile(int n, int64_t G, int tile) {
     return tile == TG_TILE_ROWS ? tile : pick_tile(tile, G);
 }
 
-int tg_env_playout(int n, void* states, int64_t G, int plies, int max_step, uint64_t seed, int64_t game_id0, int no_eye,
-                   int16_t* trace_actions, unsigned long long* plies_done, int tile, void* stream) {
+static int playout_impl(int n, void* states, int64_t G, int plies, int max_step, uint64_t seed, int64_t game_id0, int no_eye,
+                        int16_t* trace_actions, unsigned long long* plies_done, int tile, void* stream, int from_reset, float* score_out, float komi) {
     if (!states || G <= 0 || plies < 0) return set_err(-1, "tg_env_playout");
     cudaStream_t st = (cudaStream_t)stream;
     // tile == 0, measured on B200 (profiles/r01_playout_layouts.txt): 19x19 -> rows layout at every batch size (up to 3.6x over
     // the bitboard tiles); 9x9 -> four games per warp in lock step while the batch cannot fill the SMs, one thread per game beyond
     tile = tg_env_playout_tile(n, G, tile);
+    if ((from_reset || score_out) && !(tile > 0 && (tile & TG_TILE_INC))) {       // the other layouts: the same result in separate launches
+        if (from_reset) { const int rc = tg_env_reset(n, states, G, stream); if (rc) return rc; }
+        const int rc = playout_impl(n, states, G, plies, max_step, seed, game_id0, no_eye, trace_actions, plies_done, tile, stream, 0, nullptr, 0.0f);
+        if (rc || !score_out) return rc;
+        return tg_env_score(n, states, G, komi, score_out, nullptr, 0, stream);
+    }
     if (tile == TG_TILE_ROWS) {
         if (n == 9) launch_playout_rows<9>(st, (uint4*)states, G, plies, max_step, seed, game_id0, no_eye, trace_actions, plies_done);
         else if (n == 19) launch_playout_rows<19>(st, (uint4*)states, G, plies, max_step, seed, game_id0, no_eye, trace_actions, plies_done);
@@ -510,7 +523,7 @@ int tg_env_playout(int n, void* states, int64_t G, int plies, int max_step, uint
     }
     if (tile & TG_TILE_INC) {
         const int t = tile & (TG_TILE_UNIFORM - 1);
-#define TG_INC_CASE(NN, TT) launch_playout_inc<NN, TT>(st, (uint4*)states, G, plies, max_step, seed, game_id0, no_eye, trace_actions, plies_done)
+#define TG_INC_CASE(NN, TT) launch_playout_inc<NN, TT>(st, (uint4*)states, G, plies, max_step, seed, game_id0, no_eye, trace_actions, plies_done, from_reset, score_out, komi)
         if (n == 9) { if (t == 32) TG_INC_CASE(9, 32); else if (t == 16) TG_INC_CASE(9, 16); else if (t == 8) TG_INC_CASE(9, 8); else TG_INC_CASE(9, 1); }
         else if (n == 19) { if (t == 32) TG_INC_CASE(19, 32); else if (t == 16) TG_INC_CASE(19, 16); else if (t == 8) TG_INC_CASE(19, 8); else TG_INC_CASE(19, 1); }
         else return set_err(-1, "board size must be 9 or 19");
@@ -521,6 +534,17 @@ int tg_env_playout(int n, void* states, int64_t G, int plies, int max_step, uint
     else if (n == 19) { TG_DISPATCH_T6(19, tile, launch_playout, st, (uint4*)states, G, plies, max_step, seed, game_id0, no_eye, trace_actions, plies_done) }
     else return set_err(-1, "board size must be 9 or 19");
     return set_err((int)cudaGetLastError(), "tg_env_playout");
+}
+
+int tg_env_playout(int n, void* states, int64_t G, int plies, int max_step, uint64_t seed, int64_t game_id0, int no_eye,
+                   int16_t* trace_actions, unsigned long long* plies_done, int tile, void* stream) {
+    return playout_impl(n, states, G, plies, max_step, seed, game_id0, no_eye, trace_actions, plies_done, tile, stream, 0, nullptr, 0.0f);
+}
+
+int tg_env_playout_scored(int n, void* states, int64_t G, int plies, int max_step, uint64_t seed, int64_t game_id0, int no_eye,
+                          int16_t* trace_actions, unsigned long long* plies_done, int from_reset, float* score_out, float komi,
+                          int tile, void* stream) {
+    return playout_impl(n, states, G, plies, max_step, seed, game_id0, no_eye, trace_actions, plies_done, tile, stream, from_reset, score_out, komi);
 }
 
 #ifdef TG_ROWS_STATS

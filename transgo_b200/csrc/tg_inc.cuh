@@ -215,6 +215,14 @@ template <int N, int T> __device__ __forceinline__ DS<N> atari_from_scratch(cons
     return l1;
 }
 
+// Tromp-Taylor area (board.cc:822-958) in the dense layout: black - white (no komi); a stone-less board scores 0 (board.cc:932-935)
+template <int N, int T> __device__ __forceinline__ int area_score_dense(const DS<N>& black, const DS<N>& white) {
+    DS<N> empty; TG_DW empty.w[i] = ~(black.w[i] | white.w[i]) & DGeo<N>::mask(i);
+    const DS<N> rb = dflood<N, T>(dnbrs<N>(black) & empty, empty);       // empty points that reach black / white
+    const DS<N> rw = dflood<N, T>(dnbrs<N>(white) & empty, empty);
+    return dcount<N>(black) + dcount<N>(dandn<N>(rb, rw)) - dcount<N>(white) - dcount<N>(dandn<N>(rw, rb));
+}
+
 // One game in registers.  me / op are ROLES (the side to move at even plies of the launch / the other side), swapped by the
 // caller every ply, so the colour of `me` never has to be looked up.
 template <int N>

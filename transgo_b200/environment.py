@@ -189,8 +189,17 @@ class BatchedGoEnv:
                                          self.tile, self._s()), "tg_env_score")
         return (sc, terr) if want_territory else sc
 
-    def playout(self, plies, seed=0x7261, game_id0=0, no_eye=False, trace=None, counter=None):
-        """Every game plays up to ``plies`` moves of the SURVEY 8d C2 rule in one launch."""
+    def playout(self, plies, seed=0x7261, game_id0=0, no_eye=False, trace=None, counter=None, from_reset=False, score_out=None):
+        """Every game plays up to ``plies`` moves of the SURVEY 8d C2 rule in one launch.  ``from_reset`` starts from empty boards
+        (no separate reset launch, the old states are not read); ``score_out`` (float32 [G]) receives the final area scores
+        (no separate score launch)."""
+        if from_reset or score_out is not None:
+            _lib.check(self.lib.tg_env_playout_scored(self.n, _lib.ptr(self.states), self.G, int(plies), self.max_step, int(seed),
+                                                      int(game_id0), int(no_eye), _lib.ptr(trace), _lib.ptr(counter), int(from_reset),
+                                                      _lib.ptr(score_out), self.komi, self.tile, self._s()), "tg_env_playout_scored")
+            if from_reset:
+                self.done.zero_()
+            return
         _lib.check(self.lib.tg_env_playout(self.n, _lib.ptr(self.states), self.G, int(plies), self.max_step, int(seed),
                                            int(game_id0), int(no_eye), _lib.ptr(trace), _lib.ptr(counter), self.tile,
                                            self._s()), "tg_env_playout")
