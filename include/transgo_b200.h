@@ -77,7 +77,7 @@ int         tg_legal_words(int n);              /* u32 words of a dense legal ma
 /* tg_env_playout: OR into a tile width of 4, 8 or 16 to run the tiles that share a warp in lock step (warp-uniform control
  * flow: one warp never executes two games' branches one after the other) */
 #define TG_TILE_UNIFORM 64
-/* tg_env_playout: OR into a tile width of 1, 8, 16 or 32 to run the incremental engine (csrc/tg_inc.cuh): dense bit-string
+/* tg_env_playout: OR into a tile width of 1, 4, 8, 16 or 32 to run the incremental engine (csrc/tg_inc.cuh): dense bit-string
  * boards and an atari set kept in registers across plies; the lanes of a tile take the <= 5 groups around the new stone */
 #define TG_TILE_INC 128
 

@@ -49,13 +49,13 @@ if __name__ == "__main__":
     if what in ("all", "parity"):
         allok = True
         for n, G, tile, ne in ((9, 4096, 8 | 128, False), (9, 4099, 16 | 128, True), (9, 1000, 32 | 128, False), (9, 4096, 1 | 128, False),
-                               (9, 777, 1 | 128, True), (9, 4096, 8 | 128, True), (19, 256, 8 | 128, False), (19, 100, 32 | 128, True),
+                               (9, 777, 1 | 128, True), (9, 4096, 8 | 128, True), (9, 4096, 4 | 128, False), (9, 4101, 4 | 128, True), (19, 130, 4 | 128, False), (19, 256, 8 | 128, False), (19, 100, 32 | 128, True),
                                (19, 256, 1 | 128, False), (9, 4096, 0, False)):
             allok &= parity(n, G, tile, ne)
         print("ALL PARITY", "OK" if allok else "FAILED")
     if what in ("all", "time"):
-        for n, Gs, tiles in ((9, (4096, 16384, 65536, 1 << 20), (8 | 64, 8 | 128, 16 | 128, 32 | 128, 1 | 128, 1)),
-                             (19, (512, 8192), (-1, 8 | 128, 16 | 128, 32 | 128, 1 | 128))):
+        for n, Gs, tiles in ((9, (2048, 4096, 8192, 12288, 16384, 32768, 65536), (4 | 128, 8 | 128, 16 | 128, 1 | 128)),
+                             (19, (512, 1024, 2048, 4096, 8192, 16384), (4 | 128, 8 | 128, 16 | 128, 32 | 128, 1 | 128))):
             for G in Gs:
                 row = []
                 for tile in tiles:

@@ -89,7 +89,7 @@ def _replay_trace_with_oracle(n, trace, game_ids, seed, max_step, no_eye=False):
                                              (9, 4096, 16, False), (9, 4099, 16 | 64, False), (9, 1001, 8 | 64, True), (19, 67, 4 | 64, False), (19, 200, 8 | 64, False), (9, 4096, -1, False), (9, 1000, -1, True), (9, 1, -1, False),
                                              (19, 256, -1, False), (19, 37, -1, True),
                                              (9, 4096, 8 | 128, False), (9, 999, 16 | 128, True), (9, 3000, 1 | 128, True), (19, 300, 32 | 128, False),
-                                             (19, 70, 8 | 128, True), (19, 33, 1 | 128, False)])
+                                             (19, 70, 8 | 128, True), (19, 33, 1 | 128, False), (9, 4096, 4 | 128, False), (9, 1003, 4 | 128, True), (19, 150, 4 | 128, True)])
 def test_playout_matches_oracle(oracle_built, n, G, tile, no_eye):
     """G concurrent random playouts in one launch; a sample of games is replayed on the CPU."""
     from transgo_b200.environment import BatchedGoEnv
@@ -188,7 +188,7 @@ def test_tiles_agree_bit_for_bit_at_full_size():
     from transgo_b200.environment import BatchedGoEnv
     G = 65536
     ref = None
-    for tile in (32, 8, 1, -1, 8 | 64, 8 | 128, 1 | 128, 0):
+    for tile in (32, 8, 1, -1, 8 | 64, 8 | 128, 4 | 128, 1 | 128, 0):
         env = BatchedGoEnv(G, board_size=9, tile=tile)
         env.playout(122, seed=99)
         out = (env.states.clone(), env.score(), env.encode(), env.legal_mask().clone())
@@ -245,7 +245,7 @@ def _headline_launch(G, tile, no_eye, seed, n=9):
     return env, trace.cpu().numpy(), int(counter.item())
 
 
-@pytest.mark.parametrize("G,tile,no_eye", [(4096, 0, False), (4096, 0, True), (16384, 0, False), (4096, 4 | 64, False),
+@pytest.mark.parametrize("G,tile,no_eye", [(4096, 0, False), (4096, 0, True), (32768, 0, False), (4096, 8 | 128, False), (4096, 4 | 64, False),
                                            (4099, 16 | 64, True)])
 def test_headline_launch_replayed_on_every_game(oracle_built, G, tile, no_eye):
     """BASELINE configs[1] exactly as bench.py launches it (BatchedGoEnv(4096, tile=0): the library's own layout choice),

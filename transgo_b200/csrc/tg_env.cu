@@ -214,7 +214,6 @@ k_playout_inc(uint4* __restrict__ states, long long G, int plies, int max_step, 
     const bool lead = j == 0;
     // lane roles: j = 0..3 -> the E / W / S / N neighbour of the new stone (an enemy group), j >= 4 -> the stone itself
     const int sl = j == 0 ? 1 : (j == 2 ? DGeo<N>::STR : 0), sr = j == 1 ? 1 : (j == 3 ? DGeo<N>::STR : 0);
-    const bool enemy_lane = j < 4;
     // from_reset: the games start from the empty board (Reset, go_env.cc:34-41) without reading the states first
     Pos<N> p0; pos_reset(p0); p0.terminated = exists && from_reset ? 0 : 1;
     if (exists && !from_reset) pos_load<N>(p0, states, g, G, 1);
@@ -226,6 +225,7 @@ k_playout_inc(uint4* __restrict__ states, long long G, int plies, int max_step, 
     s.ko_color = p0.ko_color; s.terminated = p0.terminated;
     s.l1 = from_reset ? dzero<N>() : atari_from_scratch<N, T>(s.a, s.b);
     const unsigned long long hash_head = mix32_head(seed, (unsigned long long)(game_id0 + g));
+    s.draw = mix32_tail(hash_head, (unsigned long long)s.step);
     int played = 0;
     for (int t = 0; t < plies; t += 2) {
 #pragma unroll
@@ -233,8 +233,8 @@ k_playout_inc(uint4* __restrict__ states, long long G, int plies, int max_step, 
             if (t + h < plies) {                                   // kernel-uniform
                 int action = kInvalid;
                 if (vany<T>(!s.terminated)) {
-                    action = h == 0 ? ply<N, T, NOEYE>(s, s.a, s.b, max_step, hash_head, sl, sr, enemy_lane)
-                                    : ply<N, T, NOEYE>(s, s.b, s.a, max_step, hash_head, sl, sr, enemy_lane);
+                    action = h == 0 ? ply<N, T, NOEYE>(s, s.a, s.b, max_step, hash_head, sl, sr)
+                                    : ply<N, T, NOEYE>(s, s.b, s.a, max_step, hash_head, sl, sr);
                     played += action != kInvalid;
                 }
                 if (trace && exists && lead) trace[(long long)(t + h) * G + g] = (int16_t)action;
@@ -487,13 +487,14 @@ int tg_env_score(int n, const void* states, int64_t G, float komi, float* score,
 int tg_env_playout_tile(int n, int64_t G, int tile) {
     if (tile == 0) {
         // measured on B200 (profiles/r02_playout_layouts.txt): the incremental engine wins at every size; lanes per game shrink
-        // as the batch grows (9x9: 8 lanes -> 1 thread at ~12 k games; 19x19: 32 -> 16 -> 8 lanes -> 1 thread)
-        if (n == 19) return (G < 768 ? 32 : G < 1536 ? 16 : G < 8192 ? 8 : 1) | TG_TILE_INC;
-        return (G < 12288 ? 8 : 1) | TG_TILE_INC;
+        // as the batch grows.  4 lanes per game = 8 games per warp: at the BASELINE batch (4096 games = 512 warps) every
+        // scheduler holds at most one warp and the launch lasts one warp's 120-ply dependency chain.
+        if (n == 19) return (G < 768 ? 32 : G < 1536 ? 16 : G < 3072 ? 8 : G < 12288 ? 4 : 1) | TG_TILE_INC;
+        return (G < 3072 ? 8 : G < 24576 ? 4 : 1) | TG_TILE_INC;
     }
     if (tile > 0 && (tile & TG_TILE_INC)) {
         const int t = tile & (TG_TILE_UNIFORM - 1);
-        return (t == 32 || t == 16 || t == 8 || t == 1) ? (t | TG_TILE_INC) : tg_env_playout_tile(n, G, 0);
+        return (t == 32 || t == 16 || t == 8 || t == 4 || t == 1) ? (t | TG_TILE_INC) : tg_env_playout_tile(n, G, 0);
     }
     if (tile > 0 && (tile & TG_TILE_UNIFORM)) {
         const int t = tile & (TG_TILE_UNIFORM - 1);
@@ -524,8 +525,8 @@ static int playout_impl(int n, void* states, int64_t G, int plies, int max_step,
     if (tile & TG_TILE_INC) {
         const int t = tile & (TG_TILE_UNIFORM - 1);
 #define TG_INC_CASE(NN, TT) launch_playout_inc<NN, TT>(st, (uint4*)states, G, plies, max_step, seed, game_id0, no_eye, trace_actions, plies_done, from_reset, score_out, komi)
-        if (n == 9) { if (t == 32) TG_INC_CASE(9, 32); else if (t == 16) TG_INC_CASE(9, 16); else if (t == 8) TG_INC_CASE(9, 8); else TG_INC_CASE(9, 1); }
-        else if (n == 19) { if (t == 32) TG_INC_CASE(19, 32); else if (t == 16) TG_INC_CASE(19, 16); else if (t == 8) TG_INC_CASE(19, 8); else TG_INC_CASE(19, 1); }
+        if (n == 9) { if (t == 32) TG_INC_CASE(9, 32); else if (t == 16) TG_INC_CASE(9, 16); else if (t == 8) TG_INC_CASE(9, 8); else if (t == 4) TG_INC_CASE(9, 4); else TG_INC_CASE(9, 1); }
+        else if (n == 19) { if (t == 32) TG_INC_CASE(19, 32); else if (t == 16) TG_INC_CASE(19, 16); else if (t == 8) TG_INC_CASE(19, 8); else if (t == 4) TG_INC_CASE(19, 4); else TG_INC_CASE(19, 1); }
         else return set_err(-1, "board size must be 9 or 19");
 #undef TG_INC_CASE
         return set_err((int)cudaGetLastError(), "tg_env_playout");

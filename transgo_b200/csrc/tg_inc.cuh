@@ -230,6 +230,7 @@ struct Game {
     DS<N> a, b;            // stones of the side to move at ply 0 of the launch, of the other side
     DS<N> l1;              // stones of groups with exactly one liberty, both colours
     int last1, last2, ko_loc, ko_age, step, player, ko_color, terminated;
+    uint32_t draw;         // mix32(seed, game, step): the move draw of the NEXT ply, computed a ply ahead (off the critical path)
 };
 
 // k-th (0-based) set bit of the string; caller guarantees 0 <= k < count.  Returns the dense bit index.
@@ -247,11 +248,11 @@ template <int N> __device__ __forceinline__ int dselect(const DS<N>& a, int k) {
 
 // One ply of the C2 loop for the side `me`: legal mask -> hashed k-th legal point (PASS iff none) -> place / capture / ko ->
 // repair the atari set.  Returns the action played (P = pass) or kInvalid when this game is over.
-//   role lanes (T >= 8): lane j of a tile, j < 4: the enemy group touching the new stone in direction j; j >= 4: the group
-//   the new stone joins.  sl / sr = this lane's shift (left or right amount, the other 0).
+//   role lanes (T >= 4): lane j of a tile, j < 4: the enemy group touching the new stone in direction j if there is one, else
+//   (and for j >= 4) the group the new stone joins.  sl / sr = this lane's shift (left or right amount, the other 0).
 template <int N, int T, bool NOEYE>
 __device__ __forceinline__ int ply(Game<N>& s, DS<N>& me, DS<N>& op, int max_step, unsigned long long hash_head,
-                                   int sl, int sr, bool enemy_lane) {
+                                   int sl, int sr) {
     using D = DGeo<N>;
     const bool active = !s.terminated;
     DS<N> empty; TG_DW empty.w[i] = ~(me.w[i] | op.w[i]) & D::mask(i);
@@ -263,7 +264,7 @@ __device__ __forceinline__ int ply(Game<N>& s, DS<N>& me, DS<N>& op, int max_ste
     if (NOEYE) lg = dandn<N>(lg, dtrue_eyes<N>(me, op));                                       // board.cc:510-512
     const int nl = dcount<N>(lg);
     const bool placing = active && nl > 0;
-    const uint32_t r = mix32_tail(hash_head, (unsigned long long)s.step);
+    const uint32_t r = s.draw;
     const int bit = dselect<N>(lg, placing ? (int)(((unsigned long long)r * (unsigned)nl) >> 32) : 0);
     const int act = bit_to_action<N>(bit);
     DS<N> pb; TG_DW pb.w[i] = (placing && i == (bit >> 5)) ? (1u << (bit & 31)) : 0u;
@@ -303,6 +304,7 @@ __device__ __forceinline__ int ply(Game<N>& s, DS<N>& me, DS<N>& op, int max_ste
         if ((s.step > 1 && s.last2 == kPass) || s.step > max_step) s.terminated = 1;
         action = D::P;
     }
+    s.draw = mix32_tail(hash_head, (unsigned long long)s.step);            // for the next ply; overlaps the floods below
     // repair the atari set around the new stone
     DS<N> empty2; TG_DW empty2.w[i] = ~(me.w[i] | op.w[i]) & D::mask(i);
     if constexpr (T == 1) {
@@ -321,10 +323,15 @@ __device__ __forceinline__ int ply(Game<N>& s, DS<N>& me, DS<N>& op, int max_ste
             seen = seen | g;
         }
     } else {
+        // lane j < 4 looks at the E / W / S / N neighbour of the new stone: an enemy stone there -> flood that enemy group;
+        // anything else (own stone, empty, off board, or a lane j >= 4 whose shift is 0) -> flood the group the stone joined.
+        // A legal move always leaves a lane for the own group: four surviving enemy neighbours would mean no liberty.
         const DS<N> sh = dsel<N>(sr != 0, dshr<N>(pb, sr), dshl<N>(pb, sl));
-        const DS<N> col = dsel<N>(enemy_lane, op, me);
-        DS<N> g = sh & col;
-        const bool whole = !enemy_lane && merge;
+        const DS<N> es = sh & op;
+        const bool enemy = dany<N>(es);
+        const DS<N> col = dsel<N>(enemy, op, me);
+        DS<N> g = dsel<N>(enemy, es, pb);
+        const bool whole = !enemy && merge;
         int libs; bool complete;
         dflood_group<N, T>(g, col, empty2, whole ? (1 << 20) : 2, libs, complete);
         const bool is1 = complete && libs == 1 && dany<N>(g);

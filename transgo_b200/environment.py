@@ -120,7 +120,7 @@ class BatchedGoEnv:
 
     ``tile`` = lanes cooperating on one game: 0 lets the library choose from (board, G) by measurement (see
     ``playout_layout``); 32 / 16 / 8 / 4 / 2 / 1 force a bitboard tile; ``n | 64`` (n in 16, 8, 4) runs the tiles that share
-    a warp in lock step; ``n | 128`` (n in 32, 16, 8, 1) is the incremental engine (dense bit-string boards, atari set kept
+    a warp in lock step; ``n | 128`` (n in 32, 16, 8, 4, 1) is the incremental engine (dense bit-string boards, atari set kept
     across plies: csrc/tg_inc.cuh -- what the library picks); -1 is the row-per-lane layout.  The last three only exist for
     ``playout``; the other kernels then fall back to the library's choice.  Every layout produces identical results
     (tests/test_env_gpu.py).
