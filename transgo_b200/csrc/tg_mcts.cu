@@ -3,6 +3,7 @@
 //
 // Arithmetic contract (SURVEY.md 8a-3 dtype ledger, numpy 2.x semantics of the reference): every float operation is an
 // explicit round-to-nearest intrinsic in the reference's order and width; the file is also built with -fmad=false.
+#include <cmath>
 #include <cstdio>
 #include "../../include/transgo_b200.h"
 #include "tg_board.cuh"
@@ -16,7 +17,14 @@ constexpr unsigned kErrAction = 256u;
 constexpr int kMaxReadouts = 8;
 constexpr int kParWarps = 4;        // k_select_par: one warp per descent, up to this many (the reference default is 4 readouts)
 
-// hot.w : N[31:16] | ons[15:9] | action[8:0]
+// Edge records (round 2 layout: the selection scan reads only what changes its arithmetic per wave)
+//   hot  uint4 {x: cp   = f32(c1 * prior)            -- the first factor of prior_score (self_play.py:718), fixed at expansion
+//               y: negq = -(W / (N + 1)) in f32      -- value_score (:724, :67-68), refreshed by every backup
+//               z: vs   = f32(c2 * sqrtf(1 + clip(var, 0, 3)))  -- var_score of a VISITED child (:721-722), refreshed by every backup
+//               w: N[31:16] | ons[15:9] | action[8:0]}
+//   cold uint4 {x: W f32, y: var f32 (Welford M2), z: prior f32 as expanded, w: 0}   -- read by backups / root statistics only
+//   kid  uint2 {x: child node (0xffffffff: none), y: edge base | edge count << 22 of the child node}
+// The running mean of Node_V.value_mean_var (:84-88) is 0 before the first visit and W / (N + 1) = -negq afterwards.
 __device__ __forceinline__ int pk_n(uint32_t p) { return (int)(p >> 16); }
 __device__ __forceinline__ int pk_ons(uint32_t p) { return (int)((p >> 9) & 127u); }
 __device__ __forceinline__ int pk_act(uint32_t p) { return (int)(p & 511u); }
@@ -33,8 +41,8 @@ struct View {
     uint4* root_state;      // [SQ][G]
     double* root_prior64;   // [G][A]
     uint4* hot;             // [2][G][EC]
-    uint2* cold;            // [2][G][EC]
-    uint32_t* kid;          // [2][G][EC]  edge base | edge count << 22 of the edge's child node (valid when the child exists)
+    uint4* cold;            // [2][G][EC]
+    uint2* kid;             // [2][G][EC]  child node, edge base | edge count << 22 of the child node (valid when the child exists)
     uint4* nodes;           // [2][G][NC][SQ+1]
     int* paths;             // [G][R][MAXD]
     int* path_len;          // [G][R]
@@ -61,8 +69,8 @@ static View make_view(const TgMctsConfig* c, void* ws) {
     v.root_state = (uint4*)take(G * GG::SQ * 16);
     v.root_prior64 = (double*)take(G * GG::A * 8);
     v.hot = (uint4*)take(2 * G * (size_t)v.EC * 16);
-    v.cold = (uint2*)take(2 * G * (size_t)v.EC * 8);
-    v.kid = (uint32_t*)take(2 * G * (size_t)v.EC * 4);
+    v.cold = (uint4*)take(2 * G * (size_t)v.EC * 16);
+    v.kid = (uint2*)take(2 * G * (size_t)v.EC * 8);
     v.nodes = (uint4*)take(2 * G * (size_t)v.NC * (GG::SQ + 1) * 16);
     v.paths = (int*)take(G * R * (size_t)v.MAXD * 4);
     v.path_len = (int*)take(G * R * 4);
@@ -75,8 +83,31 @@ static View make_view(const TgMctsConfig* c, void* ws) {
 }
 
 template <int N> __device__ __forceinline__ uint4* hot_of(const View& v, int buf, int g) { return v.hot + ((size_t)buf * v.G + g) * v.EC; }
-template <int N> __device__ __forceinline__ uint2* cold_of(const View& v, int buf, int g) { return v.cold + ((size_t)buf * v.G + g) * v.EC; }
-template <int N> __device__ __forceinline__ uint32_t* kid_of(const View& v, int buf, int g) { return v.kid + ((size_t)buf * v.G + g) * v.EC; }
+template <int N> __device__ __forceinline__ uint4* cold_of(const View& v, int buf, int g) { return v.cold + ((size_t)buf * v.G + g) * v.EC; }
+template <int N> __device__ __forceinline__ uint2* kid_of(const View& v, int buf, int g) { return v.kid + ((size_t)buf * v.G + g) * v.EC; }
+constexpr uint32_t kNoChild = 0xffffffffu;
+
+// a fresh edge (Node_V.expand :70-77, complete_update :743-752): never visited, value_sum = w0
+__device__ __forceinline__ void write_fresh_edge(uint4* hot, uint4* cold, uint2* kid, int e, float c1f, float prior, float w0, int action) {
+    hot[e] = make_uint4(__float_as_uint(__fmul_rn(c1f, prior)), __float_as_uint(-__fdiv_rn(w0, 1.0f)), 0u, (uint32_t)action);
+    cold[e] = make_uint4(__float_as_uint(w0), 0u, __float_as_uint(prior), 0u);
+    kid[e] = make_uint2(kNoChild, 0u);
+}
+// one backup step on an edge (backpropagate :758-764 + value_mean_var :84-88); q / c are the loaded records
+__device__ __forceinline__ void backup_edge(uint4& q, uint4& c, float sv, float c2f, unsigned& err) {
+    const int n0 = pk_n(q.w);
+    const float W = __fadd_rn(__uint_as_float(c.x), sv);
+    const int n = n0 + 1;
+    if (n > 65535) err |= TG_MCTS_ERR_COUNT;
+    const float t = n0 == 0 ? 0.0f : -__uint_as_float(q.y);          // the running mean before this visit
+    const float mean = __fdiv_rn(W, (float)(n + 1));
+    const float var = __fadd_rn(__uint_as_float(c.y), __fmul_rn(__fsub_rn(sv, t), __fsub_rn(sv, mean)));
+    const float cv = var < 0.0f ? 0.0f : (var > 3.0f ? 3.0f : var);  // np.clip(var, 0, 3)
+    c.x = __float_as_uint(W); c.y = __float_as_uint(var);
+    q.y = __float_as_uint(-mean);
+    q.z = __float_as_uint(__fmul_rn(c2f, __fsqrt_rn(__fadd_rn(1.0f, cv))));
+    q.w += 1u << 16;
+}
 __device__ __forceinline__ uint32_t pack_kid(int eb, int K) { return (uint32_t)eb | ((uint32_t)K << 22); }
 template <int N> __device__ __forceinline__ uint4* nodes_of(const View& v, int buf, int g) { return v.nodes + ((size_t)buf * v.G + g) * v.NC * (Geo<N>::SQ + 1); }
 
@@ -94,9 +125,10 @@ __device__ __forceinline__ double warp_max(double x) {
 // ons_delta (a multiple of wu_loss, usually -wu_loss) is applied to the same nodes in the same pass: revert_incomplete_update
 // (:770-774) and backpropagate touch exactly the same records.
 template <int N>
-__device__ __forceinline__ void backup(const View& v, int* h, uint4* hot, uint2* cold, const int* path, int len, float value, unsigned& err,
+__device__ __forceinline__ void backup(const View& v, int* h, uint4* hot, uint4* cold, const int* path, int len, float value, unsigned& err,
                                        int ons_delta = 0) {
     const int lane = threadIdx.x & 31;
+    const float c2f = (float)v.c2;
     for (int i = lane; i <= len; i += 32) {
         const float sv = ((len - 1 - i) & 1) ? -value : value;       // i == len -> (-1)^(-1) handled below
         if (i == len) {
@@ -111,15 +143,9 @@ __device__ __forceinline__ void backup(const View& v, int* h, uint4* hot, uint2*
         } else {
             const int e = path[i];
             uint4 q = hot[e];
-            uint2 c = cold[e];
-            const float W = __fadd_rn(__uint_as_float(q.y), sv);
-            const int n = pk_n(q.w) + 1;
-            if (n > 65535) err |= TG_MCTS_ERR_COUNT;
-            const float t = __uint_as_float(c.x);
-            const float mean = __fdiv_rn(W, (float)(n + 1));
-            const float var = __fadd_rn(__uint_as_float(q.z), __fmul_rn(__fsub_rn(sv, t), __fsub_rn(sv, mean)));
-            q.y = __float_as_uint(W); q.z = __float_as_uint(var); q.w = (uint32_t)((int)q.w + (1 << 16) + ons_delta * 512);
-            c.x = __float_as_uint(mean);
+            uint4 c = cold[e];
+            backup_edge(q, c, sv, c2f, err);
+            q.w = (uint32_t)((int)q.w + ons_delta * 512);
             hot[e] = q; cold[e] = c;
         }
     }
@@ -183,6 +209,13 @@ __device__ __forceinline__ unsigned long long ordered_bits(double x) {
     return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
 }
 
+// sqrt(N_parent + ons_parent) as numpy computes it (np.sqrt of a Python int: correctly rounded float64): a table for the
+// counts a search meets, filled by the host's correctly rounded sqrt at library start-up; __dsqrt_rn beyond.  The index is
+// warp-uniform, so the constant cache broadcasts it.
+constexpr int kSqrtTab = 4096;
+__constant__ double c_sqrt_tab[kSqrtTab];
+__device__ __forceinline__ double sqrt_of_count(int n) { return n < kSqrtTab ? c_sqrt_tab[n] : __dsqrt_rn((double)n); }
+
 // One node visit of select_child (self_play.py:706-725), split in two so that the loads can be in flight while the warp
 // still waits for something else.  Lane l scans children l, l+32, ...
 template <int N> struct ScanRegs {
@@ -192,7 +225,7 @@ template <int N> struct ScanRegs {
 
 // every load of the scan is issued before the first use (no branch in between): one memory round trip per node
 template <int N>
-__device__ __forceinline__ void scan_load(ScanRegs<N>& s, const uint4* hot, const uint2* cold, const uint32_t* kid, const double* p64,
+__device__ __forceinline__ void scan_load(ScanRegs<N>& s, const uint4* hot, const uint2* kid, const double* p64,
                                           bool noisy_root, int eb, int K, int lane) {
 #pragma unroll
     for (int r = 0; r < ScanRegs<N>::MAXR; ++r) {
@@ -200,8 +233,8 @@ __device__ __forceinline__ void scan_load(ScanRegs<N>& s, const uint4* hot, cons
             const int k = lane + 32 * r;
             const int kk = k < K ? k : K - 1;
             s.q[r] = hot[eb + kk];
-            s.ch[r] = cold[eb + kk].y;                        // child node of the edge (cold record), so that the descent
-            s.kd[r] = kid[eb + kk];                           // needs no second trip; kd: where the child's edges live
+            const uint2 kq = kid[eb + kk];                    // child node of the edge and where the child's edges live: loaded
+            s.ch[r] = kq.x; s.kd[r] = kq.y;                   // with the scan, so that the descent needs no second trip
             s.pr64[r] = noisy_root ? p64[kk] : 0.0;
         } else { s.q[r] = make_uint4(0, 0, 0, 0); s.ch[r] = 0xffffffffu; s.kd[r] = 0; s.pr64[r] = 0.0; }
     }
@@ -215,23 +248,20 @@ __device__ __forceinline__ bool scan_pick(const View& v, const ScanRegs<N>& s, b
                                           int tie_counter, int& tie_events, int g, int lane,
                                           int& ksel, uint32_t& pk_sel, uint32_t& ch_sel, uint32_t& kd_sel) {
     constexpr int MAXR = ScanRegs<N>::MAXR;
-    const float c1f = (float)v.c1, c2f = (float)v.c2;
-    const double sq = __dsqrt_rn((double)(Np + onsp));
+    const double sq = sqrt_of_count(Np + onsp);
     unsigned long long ob[MAXR];
     unsigned hi_max = 0;
 #pragma unroll
     for (int r = 0; r < MAXR; ++r) {
         const int k = lane + 32 * r;
-        const float prior = __uint_as_float(s.q[r].x), W = __uint_as_float(s.q[r].y), var = __uint_as_float(s.q[r].z);
         const int nc = pk_n(s.q[r].w), oc = pk_ons(s.q[r].w) + (xo ? xo[r] * v.wu : 0);
-        // prior_score = c1 * prior * sqrt(Np + ons_p) / (Nc + ons_c + 1)          (:718-719)
-        double ps = noisy_root ? __dmul_rn(v.c1, s.pr64[r]) : (double)__fmul_rn(c1f, prior);
+        // prior_score = c1 * prior * sqrt(Np + ons_p) / (Nc + ons_c + 1)          (:718-719); f32(c1 * prior) comes with the record
+        double ps = noisy_root ? __dmul_rn(v.c1, s.pr64[r]) : (double)__uint_as_float(s.q[r].x);
         ps = __ddiv_rn(__dmul_rn(ps, sq), (double)(nc + oc + 1));
-        // var_score = c2 * sqrt(1 + clip(var, 0, 3)); float64 for a never-visited child      (:721-722)
-        const float cv = var < 0.0f ? 0.0f : (var > 3.0f ? 3.0f : var);
-        const double vsf = (double)__fmul_rn(c2f, __fsqrt_rn(__fadd_rn(1.0f, cv)));
-        const double vs = nc == 0 ? v.c2 : vsf;
-        const double qv = (double)(-__fdiv_rn(W, (float)(nc + 1)));                 // -child.value() (:724, :67-68)
+        // var_score = c2 * sqrt(1 + clip(var, 0, 3)) in f32 for a visited child (kept in the record by every backup), the
+        // float64 constant for a never-visited one (:721-722); value_score = -child.value() in f32 (:724, :67-68), also kept
+        const double vs = nc == 0 ? v.c2 : (double)__uint_as_float(s.q[r].z);
+        const double qv = (double)__uint_as_float(s.q[r].y);
         const double sc = __dadd_rn(__dadd_rn(ps, vs), qv);
         ob[r] = k < K ? ordered_bits(sc) : 0ull;
         const unsigned hi = (unsigned)(ob[r] >> 32);
@@ -274,7 +304,7 @@ __device__ __forceinline__ bool scan_pick(const View& v, const ScanRegs<N>& s, b
 
 // terminal leaf (self_play.py:638-642): step, score, back the result up at once
 template <int N>
-__device__ __forceinline__ void terminal_backup(const View& v, int* h, uint4* hot, uint2* cold, const uint4* nodes, int node, int action,
+__device__ __forceinline__ void terminal_backup(const View& v, int* h, uint4* hot, uint4* cold, const uint4* nodes, int node, int action,
                                                 const int* path, int depth, unsigned& err) {
     using GG = Geo<N>;
     Pos<N> s; pos_load<N>(s, nodes + (size_t)node * (GG::SQ + 1), 0, 1, 0);
@@ -298,8 +328,8 @@ __device__ __forceinline__ void select_sequential(const View& v, int g, int lane
     const unsigned flags = (unsigned)h[H_FLAGS];
     const int buf = h[H_BUF];
     uint4* hot = hot_of<N>(v, buf, g);
-    uint2* cold = cold_of<N>(v, buf, g);
-    const uint32_t* kid = kid_of<N>(v, buf, g);
+    uint4* cold = cold_of<N>(v, buf, g);
+    const uint2* kid = kid_of<N>(v, buf, g);
     const uint4* nodes = nodes_of<N>(v, buf, g);
     const uint4 root_info = nodes[GG::SQ];                            // the root's edges: read once per wave
     const uint4 root_meta = nodes[GG::SQ - 1];                        // last1 | last2, ko, step | player | ko_color, terminated
@@ -322,7 +352,7 @@ __device__ __forceinline__ void select_sequential(const View& v, int g, int lane
             const int eb = (int)(kid_cur & 0x3fffffu), K = (int)(kid_cur >> 22);
             st_fan += K;
             ScanRegs<N> sr;
-            scan_load<N>(sr, hot, cold, kid, p64, noisy && node == 0, eb, K, lane);
+            scan_load<N>(sr, hot, kid, p64, noisy && node == 0, eb, K, lane);
             int ksel; uint32_t ch_sel, kd_sel; int ties = 0;
             if (!scan_pick<N>(v, sr, noisy && node == 0, K, Np, onsp, nullptr, tie, ties, g, lane, ksel, pk_sel, ch_sel, kd_sel)) { err |= TG_MCTS_ERR_NAN; break; }
             tie += ties;
@@ -412,8 +442,8 @@ __global__ void __launch_bounds__(32 * kParWarps, N == 9 ? 8 : 4) k_select_par(V
     const unsigned flags = (unsigned)h[H_FLAGS];
     const int buf = h[H_BUF];
     uint4* hot = hot_of<N>(v, buf, g);
-    uint2* cold = cold_of<N>(v, buf, g);
-    const uint32_t* kid = kid_of<N>(v, buf, g);
+    uint4* cold = cold_of<N>(v, buf, g);
+    const uint2* kid = kid_of<N>(v, buf, g);
     const uint4* nodes = nodes_of<N>(v, buf, g);
     const uint4 root_info = nodes[GG::SQ];
     const uint4 root_meta = nodes[GG::SQ - 1];
@@ -433,7 +463,7 @@ __global__ void __launch_bounds__(32 * kParWarps, N == 9 ? 8 : 4) k_select_par(V
         const int eb = (int)(kid_cur & 0x3fffffu), K = (int)(kid_cur >> 22);
         fan += K;
         ScanRegs<N> sr;
-        scan_load<N>(sr, hot, cold, kid, p64, noisy && node == 0, eb, K, lane);    // in flight while waiting for warp j-1
+        scan_load<N>(sr, hot, kid, p64, noisy && node == 0, eb, K, lane);    // in flight while waiting for warp j-1
         // every earlier descent must have published its level-L choice (or have ended): a short descent j-1 says nothing
         // about how far a long descent j-2 has come
         for (int jp = 0; jp < j; ++jp) { while (vprog[jp] <= L) __nanosleep(40); }
@@ -567,8 +597,8 @@ __global__ void __launch_bounds__(kThreads) k_expand(View v, const float* __rest
     const int npaths = h[H_NPATHS];
     const int buf = h[H_BUF];
     uint4* hot = hot_of<N>(v, buf, g);
-    uint2* cold = cold_of<N>(v, buf, g);
-    uint32_t* kid = kid_of<N>(v, buf, g);
+    uint4* cold = cold_of<N>(v, buf, g);
+    uint2* kid = kid_of<N>(v, buf, g);
     uint4* nodes = nodes_of<N>(v, buf, g);
     unsigned err = 0;
     int sims = 0;
@@ -579,7 +609,7 @@ __global__ void __launch_bounds__(kThreads) k_expand(View v, const float* __rest
         const int len = v.path_len[slot];
         const int e = path[len - 1];
         const float val = value[slot];                                                // (issued with the loads below, used later)
-        if ((int)cold[e].y >= 0 || err) { add_ons(h, hot, path, len, -v.wu); continue; }   // :653, :733-734 duplicate leaf: no backup
+        if (kid[e].x != kNoChild || err) { add_ons(h, hot, path, len, -v.wu); continue; }   // :653, :733-734 duplicate leaf: no backup
         const int K = compact_legal<N>(v.leaf_legal + slot * GG::DQ * 4, policy + slot * GG::A, sp, sa);
         const int node = nn, eb = ne;
         if (node + 1 > v.NC) err |= TG_MCTS_ERR_NODES;
@@ -594,15 +624,13 @@ __global__ void __launch_bounds__(kThreads) k_expand(View v, const float* __rest
         for (int k = lane; k < K; k += 32) {
             const float prior = ok ? __fdiv_rn(sp[k], scale) : 0.0f;                   // :743-744
             const float w0 = ok ? -val : -0.0f;                                        // :752 / :76
-            hot[eb + k] = make_uint4(__float_as_uint(prior), __float_as_uint(w0), 0u, (uint32_t)sa[k]);
-            cold[eb + k] = make_uint2(0u, 0xffffffffu);
+            write_fresh_edge(hot, cold, kid, eb + k, (float)v.c1, prior, w0, sa[k]);
         }
         uint4* rec = nodes + (size_t)node * (GG::SQ + 1);
         if (lane < GG::SQ) rec[lane] = v.leaf_state[(size_t)lane * v.G * v.R + slot];
         if (lane == 0) {
             rec[GG::SQ] = make_uint4((uint32_t)eb, (uint32_t)K, 0u, 0u);
-            cold[e].y = (uint32_t)node;
-            kid[e] = pack_kid(eb, K);
+            kid[e] = make_uint2((uint32_t)node, pack_kid(eb, K));
         }
         nn = node + 1; ne = eb + K;
         __syncwarp();
@@ -645,8 +673,8 @@ __global__ void __launch_bounds__(32 * kParWarps) k_expand_par(View v, const flo
     const int npaths = h[H_NPATHS];
     const int buf = h[H_BUF];
     uint4* hot = hot_of<N>(v, buf, g);
-    uint2* cold = cold_of<N>(v, buf, g);
-    uint32_t* kid = kid_of<N>(v, buf, g);
+    uint4* cold = cold_of<N>(v, buf, g);
+    uint2* kid = kid_of<N>(v, buf, g);
     uint4* nodes = nodes_of<N>(v, buf, g);
     const size_t slot = (size_t)g * R + j;
     const int* path = v.paths + slot * v.MAXD;
@@ -655,7 +683,7 @@ __global__ void __launch_bounds__(32 * kParWarps) k_expand_par(View v, const flo
         const int len = v.path_len[slot];
         const int e = path[len - 1];
         const float val = value[slot];
-        const int pre = (int)cold[e].y >= 0;
+        const int pre = kid[e].x != kNoChild;
         const int K = compact_legal<N>(v.leaf_legal + slot * GG::DQ * 4, policy + slot * GG::A, sp, sa);
         float scale = 0.0f;                                                           // :739 python sum(): sequential float32
         if (lane == 0) for (int k = 0; k < K; ++k) scale = __fadd_rn(scale, sp[k]);
@@ -692,15 +720,13 @@ __global__ void __launch_bounds__(32 * kParWarps) k_expand_par(View v, const flo
         for (int k = lane; k < K; k += 32) {
             const float prior = ok ? __fdiv_rn(sp[k], scale) : 0.0f;                   // :743-744
             const float w0 = ok ? -val : -0.0f;                                        // :752 / :76
-            hot[eb + k] = make_uint4(__float_as_uint(prior), __float_as_uint(w0), 0u, (uint32_t)sa[k]);
-            cold[eb + k] = make_uint2(0u, 0xffffffffu);
+            write_fresh_edge(hot, cold, kid, eb + k, (float)v.c1, prior, w0, sa[k]);
         }
         uint4* rec = nodes + (size_t)node * (GG::SQ + 1);
         if (lane < GG::SQ) rec[lane] = v.leaf_state[(size_t)lane * v.G * R + slot];
         if (lane == 0) {
             rec[GG::SQ] = make_uint4((uint32_t)eb, (uint32_t)K, 0u, 0u);
-            cold[e].y = (uint32_t)node;
-            kid[e] = pack_kid(eb, K);
+            kid[e] = make_uint2((uint32_t)node, pack_kid(eb, K));
         }
     }
     __syncthreads();
@@ -710,7 +736,7 @@ __global__ void __launch_bounds__(32 * kParWarps) k_expand_par(View v, const flo
         int maxlen = 0;
         for (int jj = 0; jj < npaths; ++jj) maxlen = s_len[jj] > maxlen ? s_len[jj] : maxlen;
         for (int i = lane; i < maxlen; i += 32) {
-            int e[kParWarps]; uint4 q[kParWarps]; uint2 c[kParWarps];
+            int e[kParWarps]; uint4 q[kParWarps]; uint4 c[kParWarps];
 #pragma unroll
             for (int jj = 0; jj < kParWarps; ++jj) {
                 e[jj] = (jj < npaths && i < s_len[jj]) ? v.paths[((size_t)g * R + jj) * v.MAXD + i] : -1;
@@ -724,15 +750,7 @@ __global__ void __launch_bounds__(32 * kParWarps) k_expand_par(View v, const flo
                 q[jj].w = (uint32_t)((int)q[jj].w - v.wu * 512);
                 if (s_exp[jj]) {
                     const float val = s_val[jj];
-                    const float sv = ((s_len[jj] - 1 - i) & 1) ? -val : val;
-                    const float W = __fadd_rn(__uint_as_float(q[jj].y), sv);
-                    const int n = pk_n(q[jj].w) + 1;
-                    if (n > 65535) err |= TG_MCTS_ERR_COUNT;
-                    const float t = __uint_as_float(c[jj].x);
-                    const float mean = __fdiv_rn(W, (float)(n + 1));
-                    const float var = __fadd_rn(__uint_as_float(q[jj].z), __fmul_rn(__fsub_rn(sv, t), __fsub_rn(sv, mean)));
-                    q[jj].y = __float_as_uint(W); q[jj].z = __float_as_uint(var); q[jj].w += 1u << 16;
-                    c[jj].x = __float_as_uint(mean);
+                    backup_edge(q[jj], c[jj], ((s_len[jj] - 1 - i) & 1) ? -val : val, (float)v.c2, err);
                 }
             }
 #pragma unroll
@@ -799,7 +817,8 @@ __global__ void __launch_bounds__(kThreads) k_root_expand(View v, const float* _
     __shared__ uint32_t dense[kThreads / 32][GG::DQ * 4];
     const int buf = h[H_BUF];
     uint4* hot = hot_of<N>(v, buf, g);
-    uint2* cold = cold_of<N>(v, buf, g);
+    uint4* cold = cold_of<N>(v, buf, g);
+    uint2* kid = kid_of<N>(v, buf, g);
     uint4* nodes = nodes_of<N>(v, buf, g);
     Pos<N> s; pos_load<N>(s, v.root_state, g, v.G, 1);
     Groups<N> gr;
@@ -824,10 +843,7 @@ __global__ void __launch_bounds__(kThreads) k_root_expand(View v, const float* _
     if (__any_sync(0xffffffffu, bad)) err |= TG_MCTS_ERR_NAN;                          // evaluator returned NaN / inf
     if (!err) {
         const float w0 = -value_root[g];                                                // :76, value from :599
-        for (int k = lane; k < K; k += 32) {
-            hot[k] = make_uint4(__float_as_uint(sp[k]), __float_as_uint(w0), 0u, (uint32_t)sa[k]);   // RAW prior (:602)
-            cold[k] = make_uint2(0u, 0xffffffffu);
-        }
+        for (int k = lane; k < K; k += 32) write_fresh_edge(hot, cold, kid, k, (float)v.c1, sp[k], w0, sa[k]);   // RAW prior (:602)
         uint4* rec = nodes;
         if (lane < GG::SQ) rec[lane] = v.root_state[(size_t)lane * v.G + g];
         if (lane == 0) rec[GG::SQ] = make_uint4(0u, (uint32_t)K, 0u, 0u);
@@ -850,9 +866,9 @@ __global__ void k_begin_move(View v, const double* __restrict__ noise) {
     if (!(flags & TG_MCTS_ACTIVE) || (flags & TG_MCTS_NEED_EXPAND)) return;
     const int K = h[H_NEDGES] > 0 ? (int)nodes_of<N>(v, h[H_BUF], g)[GG::SQ].y : 0;
     if (noise) {                                                                     // Node_V.dirichlet_prior :90-95
-        const uint4* hot = hot_of<N>(v, h[H_BUF], g);
+        const uint4* cold = cold_of<N>(v, h[H_BUF], g);
         for (int k = lane; k < K; k += 32) {
-            const float p = __fmul_rn(__uint_as_float(hot[k].x), 0.75f);
+            const float p = __fmul_rn(__uint_as_float(cold[k].z), 0.75f);
             v.root_prior64[(size_t)g * GG::A + k] = __dadd_rn((double)p, __dmul_rn(noise[(size_t)g * GG::A + k], 0.25));
         }
         flags |= TG_MCTS_NOISY;
@@ -879,13 +895,17 @@ __global__ void k_root_stats(View v, int* __restrict__ counts, float* __restrict
     const bool has = !((unsigned)h[H_FLAGS] & TG_MCTS_NEED_EXPAND) && h[H_NNODES] > 0;
     const int K = has ? (int)nodes_of<N>(v, h[H_BUF], g)[GG::SQ].y : 0;
     const uint4* hot = hot_of<N>(v, h[H_BUF], g);
+    const uint4* cold = cold_of<N>(v, h[H_BUF], g);
     for (int k = lane; k < K; k += 32) {
-        const uint4 q = hot[k];
-        const int a = pk_act(q.w);
-        if (counts) counts[row + a] = pk_n(q.w);
-        if (W) W[row + a] = __uint_as_float(q.y);
-        if (var) var[row + a] = __uint_as_float(q.z);
-        if (prior) prior[row + a] = __uint_as_float(q.x);
+        const uint32_t pk = hot[k].w;
+        const int a = pk_act(pk);
+        if (counts) counts[row + a] = pk_n(pk);
+        if (W || var || prior) {
+            const uint4 c = cold[k];
+            if (W) W[row + a] = __uint_as_float(c.x);
+            if (var) var[row + a] = __uint_as_float(c.y);
+            if (prior) prior[row + a] = __uint_as_float(c.z);
+        }
     }
     if (lane == 0) {
         if (root_n) root_n[g] = h[H_ROOTN];
@@ -911,7 +931,8 @@ __global__ void __launch_bounds__(kThreads) k_advance(View v, const int16_t* __r
     const int action = (int)actions[g];
     const int buf = h[H_BUF];
     const uint4* shot = hot_of<N>(v, buf, g);
-    const uint2* scold = cold_of<N>(v, buf, g);
+    const uint4* scold = cold_of<N>(v, buf, g);
+    const uint2* skid = kid_of<N>(v, buf, g);
     const uint4* snodes = nodes_of<N>(v, buf, g);
     const int K0 = (int)snodes[GG::SQ].y;
     // the root edge of `action`
@@ -931,14 +952,14 @@ __global__ void __launch_bounds__(kThreads) k_advance(View v, const int16_t* __r
     const bool done = apply_move<N, 32>(s, gr, action, v.max_step, acc, true);
     if (lane == 0) pos_store<N>(s, v.root_state, g, v.G, 1);
     const uint4 qe = shot[ksel];
-    const uint2 ce = scold[ksel];
-    const int child = (int)ce.y;
+    const uint4 ce = scold[ksel];
+    const int child = (int)skid[ksel].x;
     int nd = 0, ne = 0;
     if (child >= 0) {
         const int dbuf = 1 - buf;
         uint4* dhot = hot_of<N>(v, dbuf, g);
-        uint2* dcold = cold_of<N>(v, dbuf, g);
-        uint32_t* dkid = kid_of<N>(v, dbuf, g);
+        uint4* dcold = cold_of<N>(v, dbuf, g);
+        uint2* dkid = kid_of<N>(v, dbuf, g);
         uint4* dnodes = nodes_of<N>(v, dbuf, g);
         if (lane == 0) { dnodes[GG::SQ].z = (uint32_t)child; dnodes[GG::SQ].w = 0xffffffffu; }   // .w: the copied edge that leads here
         __syncwarp();
@@ -950,21 +971,21 @@ __global__ void __launch_bounds__(kThreads) k_advance(View v, const int16_t* __r
             const uint4 sinfo = srec[GG::SQ];
             const int seb = (int)sinfo.x, K = (int)sinfo.y;
             const uint32_t pe = drec[GG::SQ].w;                                        // set when this node was enqueued
-            if (lane == 0 && pe != 0xffffffffu) dkid[pe] = pack_kid(ne, K);             // its edges now start at ne
+            if (lane == 0 && pe != 0xffffffffu) dkid[pe].y = pack_kid(ne, K);           // its edges now start at ne
             if (lane < GG::SQ) drec[lane] = srec[lane];
             for (int base = 0; base < K; base += 32) {
                 const int k = base + lane;
-                uint4 q = make_uint4(0, 0, 0, 0); uint2 c = make_uint2(0, 0xffffffffu);
-                if (k < K) { q = shot[seb + k]; c = scold[seb + k]; }
-                const bool has = k < K && (int)c.y >= 0;
+                uint4 q = make_uint4(0, 0, 0, 0), c = make_uint4(0, 0, 0, 0); uint2 kq = make_uint2(kNoChild, 0u);
+                if (k < K) { q = shot[seb + k]; c = scold[seb + k]; kq = skid[seb + k]; }
+                const bool has = k < K && kq.x != kNoChild;
                 const unsigned b = __ballot_sync(0xffffffffu, has);
                 if (has) {
                     const int my = nd + __popc(b & ((1u << lane) - 1u));
-                    dnodes[(size_t)my * (GG::SQ + 1) + GG::SQ].z = c.y;
+                    dnodes[(size_t)my * (GG::SQ + 1) + GG::SQ].z = kq.x;
                     dnodes[(size_t)my * (GG::SQ + 1) + GG::SQ].w = (uint32_t)(ne + k);
-                    c.y = (uint32_t)my;
+                    kq.x = (uint32_t)my;                                               // .y is patched when the child is dequeued
                 }
-                if (k < K) { dhot[ne + k] = q; dcold[ne + k] = c; }
+                if (k < K) { dhot[ne + k] = q; dcold[ne + k] = c; dkid[ne + k] = kq; }
                 nd += __popc(b);
             }
             __syncwarp();
@@ -977,7 +998,9 @@ __global__ void __launch_bounds__(kThreads) k_advance(View v, const int16_t* __r
         h[H_BUF] = child >= 0 ? 1 - buf : buf;
         h[H_NNODES] = nd; h[H_NEDGES] = ne;
         h[H_ROOTN] = pk_n(qe.w); h[H_ROOTONS] = pk_ons(qe.w);
-        h[H_ROOTW] = (int)qe.y; h[H_ROOTMEAN] = (int)ce.x; h[H_ROOTVAR] = (int)qe.z;
+        // the new root's own statistics = those of the edge that led to it (value_mean: 0 before its first visit, else W / (N + 1))
+        h[H_ROOTW] = (int)ce.x; h[H_ROOTVAR] = (int)ce.y;
+        h[H_ROOTMEAN] = pk_n(qe.w) == 0 ? 0 : __float_as_int(-__uint_as_float(qe.y));
         h[H_MOVE] += 1;
         flags &= ~TG_MCTS_NOISY;
         if (child < 0) flags |= TG_MCTS_NEED_EXPAND;                                   // :861-870
@@ -1118,6 +1141,20 @@ __global__ void k_synth_counted(int A, long long rows, unsigned long long seed, 
 }
 
 // ------------------------------------------------------------------------------------------ host side
+// the sqrt table of sqrt_of_count, once per device (std::sqrt of an exactly representable integer is correctly rounded)
+static int ensure_tables() {
+    static unsigned long long done = 0;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+    if ((done >> (dev & 63)) & 1ull) return 0;
+    static double tab[kSqrtTab];
+    for (int i = 0; i < kSqrtTab; ++i) tab[i] = std::sqrt((double)i);
+    const cudaError_t rc = cudaMemcpyToSymbol(c_sqrt_tab, tab, sizeof(tab));
+    if (rc != cudaSuccess) return (int)rc;
+    done |= 1ull << (dev & 63);
+    return 0;
+}
+
 static int g_force_sequential_select = 0;     // tg_mcts_debug_sequential_select: tests compare the two selection kernels
 
 static int check_cfg(const TgMctsConfig* c) {
@@ -1149,6 +1186,7 @@ int64_t tg_mcts_workspace_bytes(const TgMctsConfig* cfg) {
 
 int tg_mcts_init(const TgMctsConfig* cfg, void* ws, void* stream) {
     if (check_cfg(cfg) || !ws) return set_err(-1, "tg_mcts_init");
+    if (ensure_tables()) return set_err(-1, "tg_mcts_init: constant tables");
     TG_MCTS_N(cfg, { View v = make_view<N>(cfg, ws); k_init<N><<<(v.G + 127) / 128, 128, 0, (cudaStream_t)stream>>>(v, nullptr); });
     return set_err((int)cudaGetLastError(), "tg_mcts_init");
 }
