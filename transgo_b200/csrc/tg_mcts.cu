@@ -427,6 +427,7 @@ template <int N, bool FUSE>
 __global__ void __launch_bounds__(32 * kParWarps, N == 9 ? 8 : 4) k_select_par(View v, float* __restrict__ obs) {
     using GG = Geo<N>;
     constexpr int MAXR = ScanRegs<N>::MAXR;
+    cudaGridDependencySynchronize();                                  // launched with programmatic stream serialization (launch_pdl)
     extern __shared__ int sm_sel[];                                   // [MAXD][R] node, then [MAXD][R] child index
     __shared__ int progress[kMaxReadouts], plen[kMaxReadouts];
     __shared__ int s_ties[kMaxReadouts], s_flag[kMaxReadouts], s_fan[kMaxReadouts];
@@ -659,6 +660,7 @@ __global__ void __launch_bounds__(kThreads) k_expand(View v, const float* __rest
 template <int N>
 __global__ void __launch_bounds__(32 * kParWarps) k_expand_par(View v, const float* __restrict__ policy, const float* __restrict__ value, int* __restrict__ pending) {
     using GG = Geo<N>;
+    cudaGridDependencySynchronize();                                  // launched with programmatic stream serialization (launch_pdl)
     extern __shared__ uint32_t sm_raw[];
     __shared__ int s_e[kParWarps], s_len[kParWarps], s_K[kParWarps], s_pre[kParWarps], s_bad[kParWarps], s_exp[kParWarps], s_node[kParWarps], s_eb[kParWarps];
     __shared__ float s_val[kParWarps], s_scale[kParWarps];
@@ -1101,6 +1103,7 @@ __global__ void k_synth(int A, long long rows, unsigned long long seed, unsigned
 __global__ void k_synth_counted(int A, long long rows, unsigned long long seed, unsigned long long* __restrict__ wave_dev,
                                 float* __restrict__ policy, float* __restrict__ value) {
     __shared__ unsigned long long s_wave;
+    cudaGridDependencySynchronize();                                  // launched with programmatic stream serialization (launch_pdl)
     if (threadIdx.x == 0) s_wave = *reinterpret_cast<volatile unsigned long long*>(wave_dev);
     __syncthreads();
     const unsigned long long wave = s_wave;
@@ -1153,6 +1156,20 @@ static int ensure_tables() {
     if (rc != cudaSuccess) return (int)rc;
     done |= 1ull << (dev & 63);
     return 0;
+}
+
+// Launch with programmatic dependent launch allowed: the grid may be scheduled while the previous kernel of the stream is still
+// draining; the kernel itself waits (cudaGridDependencySynchronize) before it touches anything that kernel produced.  Inside a
+// replayed CUDA graph this hides most of the ~3 us kernel-node dispatch gap of the three tree kernels of a wave.
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
 static int g_force_sequential_select = 0;     // tg_mcts_debug_sequential_select: tests compare the two selection kernels
@@ -1236,9 +1253,9 @@ int tg_mcts_wave_begin(const TgMctsConfig* cfg, void* ws, float* obs, void* stre
             // select + leaves in one launch: a game moves on to its leaves as soon as its own descents are done
             const size_t planes = (size_t)v.R * leaf_smem_words<N>() * 4;
             if (planes > sel_smem) sel_smem = planes;
-            if (N == 9) k_select_par<N, true><<<(unsigned)v.G, 32 * v.R, sel_smem, (cudaStream_t)stream>>>(v, obs);
+            if (N == 9) launch_pdl(k_select_par<N, true>, dim3((unsigned)v.G), dim3(32 * v.R), sel_smem, (cudaStream_t)stream, v, obs);
             else {
-                k_select_par<N, false><<<(unsigned)v.G, 32 * v.R, sel_smem, (cudaStream_t)stream>>>(v, obs);
+                launch_pdl(k_select_par<N, false>, dim3((unsigned)v.G), dim3(32 * v.R), sel_smem, (cudaStream_t)stream, v, obs);
                 k_leaves<N><<<warp_blocks((long long)v.G * v.R), kThreads, smem, (cudaStream_t)stream>>>(v, obs);
             }
         } else {
@@ -1263,7 +1280,7 @@ int tg_mcts_wave_end(const TgMctsConfig* cfg, void* ws, const float* policy, con
         View v = make_view<N>(cfg, ws);
         const size_t smem = (size_t)(kThreads / 32) * 2 * Geo<N>::A * 4;
         if (v.R > 1 && v.R <= kParWarps && !g_force_sequential_select)
-            k_expand_par<N><<<(unsigned)v.G, 32 * v.R, (size_t)v.R * 2 * Geo<N>::A * 4, (cudaStream_t)stream>>>(v, policy, value, pending);
+            launch_pdl(k_expand_par<N>, dim3((unsigned)v.G), dim3(32 * v.R), (size_t)v.R * 2 * Geo<N>::A * 4, (cudaStream_t)stream, v, policy, value, pending);
         else
             k_expand<N><<<warp_blocks(v.G), kThreads, smem, (cudaStream_t)stream>>>(v, policy, value, pending);
     });
@@ -1311,7 +1328,7 @@ int tg_synth_provider(int n, int64_t rows, uint64_t seed, uint64_t wave, float* 
 
 int tg_synth_provider_dev(int n, int64_t rows, uint64_t seed, unsigned long long* wave_counter, float* policy, float* value, void* stream) {
     if (!policy || !value || !wave_counter || rows <= 0 || (n != 9 && n != 19)) return set_err(-1, "tg_synth_provider_dev");
-    k_synth_counted<<<warp_blocks(rows), kThreads, 0, (cudaStream_t)stream>>>(n * n + 1, rows, seed, wave_counter, policy, value);
+    launch_pdl(k_synth_counted, dim3(warp_blocks(rows)), dim3(kThreads), 0, (cudaStream_t)stream, n * n + 1, (long long)rows, (unsigned long long)seed, wave_counter, policy, value);
     return set_err((int)cudaGetLastError(), "tg_synth_provider_dev");
 }
 
