@@ -407,6 +407,10 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def _bytes_per_sim(d_bar, k_bar):
+    return d_bar * 24 * k_bar + 64 * (d_bar + 1) + 40 * k_bar + (4 * 82 + 4) + 16 + 2 * 48 + 3240
+
+
 def _hbm_peak():
     try:
         return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
@@ -651,9 +655,10 @@ def mcts_bench(torch, dist, dev, rank, world, args):
     rate, ms, n, waves = timed_moves(eng, moves)
     st = eng.search_stats()
     d_bar, k_bar = st["mean_depth"], st["mean_fanout"]
-    # SURVEY 8d traffic model with this engine's record sizes: 16 B hot edge per child scanned + 16 B node info per level, 40 B
-    # RMW per path node, 24 B per new child slot, policy row + value, legal mask, two states, the 3240 B of planes
-    bps = d_bar * (16 * k_bar + 16) + 40 * (d_bar + 1) + 24 * k_bar + (4 * 82 + 4) + 16 + 2 * 48 + 3240
+    # SURVEY 8d traffic model with this engine's record sizes: 24 B per child scanned (16 B hot record + 8 B child info), 64 B
+    # RMW per path node (hot + cold, read and written), 40 B per new child slot, policy row + value, legal mask, two states,
+    # the 3240 B of planes
+    bps = _bytes_per_sim(d_bar, k_bar)
     out["tree_only"] = {"value": rate, "unit": "MCTS sims/s", "ms": ms, "sims": n, "moves": moves, "waves": waves,
                         "provider": "tg_synth_provider (device-side synthetic policy/value, NOT the net); each wave (select, leaves, "
                                     "provider, expand) replayed as one CUDA graph",
@@ -696,7 +701,7 @@ def mcts_bench(torch, dist, dev, rank, world, args):
             best = row
         out.setdefault("tree_only_streams_sweep", []).append({"shards": shards, "value": rate_c, "ms": ms_c})
         del ceng, bufs
-    bps_c = best["mean_depth"] * (16 * best["mean_fanout"] + 16) + 40 * (best["mean_depth"] + 1) + 24 * best["mean_fanout"] + (4 * 82 + 4) + 16 + 2 * 48 + 3240
+    bps_c = _bytes_per_sim(best["mean_depth"], best["mean_fanout"])
     best.update(bytes_per_sim=bps_c, provider="tg_synth_provider per shard; the shards' waves (one CUDA graph each) are replayed round-robin on "
                                                "separate streams", roofline={"bound": "hbm", "achieved": best["value"] * bps_c / 1e9 / world, "peak": _hbm_peak(),
                                                                            "unit": "GB/s", "frac": best["value"] * bps_c / 1e9 / world / _hbm_peak()})

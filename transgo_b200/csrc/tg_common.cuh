@@ -52,9 +52,9 @@ template <int N, int T> __device__ __forceinline__ void planes_to_smem_staged(co
     constexpr int U = (int)(sizeof(typename G::word_t) / 4);      // u32 per board word
     constexpr int SW = 10 * G::W * U;
     const int lane = Tile<T>::lane();
+    if (lane == 0) {                                   // every lane holds the same bitboards: one lane parks them (SW plain stores)
 #pragma unroll
-    for (int i = 0; i < SW; ++i) {
-        if ((i & (T - 1)) == lane) {
+        for (int i = 0; i < SW; ++i) {
             const typename G::word_t wv = pl[i / (G::W * U)].w[(i / U) % G::W];
             stage[i] = (uint32_t)(U == 1 ? wv : (wv >> (32 * (i % U))));
         }
