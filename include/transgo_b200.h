@@ -258,6 +258,17 @@ int tg_net_add_bn_relu(const void* x, const void* y, float alpha, const float* y
 int tg_net_attention(const void* qkv, const void* x, float gamma, const float* scale, const float* shift, void* out,
                      int64_t B, int P, int dq, int channels, void* stream);
 
+
+/* The same block INCLUDING the q | k | v projection, as one tcgen05 kernel (csrc/tg_net_tc.cu; 9x9 boards: P <= 96):
+ *   x     bf16 [B][P][C]          wqkv bf16 [dq + dq + C][C] (query | key | gamma-scaled value rows, the three 1x1 convolutions
+ *   of model.py:290-292 stacked)   bqkv bf16 [dq + dq + C]
+ *   out   bf16 [B][P][C] = relu((x + gamma * o) * scale[c] + shift[c]),  q|k|v = x . wqkv^T + bqkv (rounded to bf16),
+ *                           o[j] = sum_i softmax_j(q_i . k_j) * v_i
+ * q, k, v and the scores stay in shared / tensor memory.  debug (may be NULL): float32 [128*192 + 128*96 + 128*128], the
+ * accumulator tiles of position 0 (projection + bias, scores, o) for stage-by-stage tests.  Returns -1 for unsupported shapes. */
+int tg_net_attention_fused(const void* x, const void* wqkv, const void* bqkv, float gamma, const float* scale, const float* shift,
+                           void* out, int64_t B, int P, int dq, int channels, float* debug, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -76,6 +76,75 @@ def test_attention_kernel_matches_fp32_reference(B, P):
                               B, 369, dq, C, _lib.stream_ptr()) != 0         # unsupported size is refused, not mangled
 
 
+def _attention_tc_case(B, P, seed):
+    """inputs and fp32 stage-by-stage expectations of tg_net_attention_fused on the same bf16 operands"""
+    g = torch.Generator(device="cuda"); g.manual_seed(seed)
+    dq, C = 32, 128
+    x = torch.randn([B, P, C], device="cuda", generator=g).to(torch.bfloat16)
+    w = (torch.randn([2 * dq + C, C], device="cuda", generator=g) * 0.09).to(torch.bfloat16)
+    b = (torch.randn([2 * dq + C], device="cuda", generator=g) * 0.2).to(torch.bfloat16)
+    scale = torch.rand([C], device="cuda", generator=g) + 0.5
+    shift = torch.randn([C], device="cuda", generator=g) * 0.3
+    gamma = 0.6
+    d1 = x.float() @ w.float().t() + b.float()                                    # projection + bias (fp32 accumulate)
+    qkv = d1.to(torch.bfloat16).float()                                           # parked as bf16
+    q, k, v = qkv[..., :dq], qkv[..., dq:2 * dq], qkv[..., 2 * dq:]
+    s = torch.bmm(q, k.transpose(1, 2))                                           # [B, i, j]
+    att = torch.softmax(s, dim=-1).to(torch.bfloat16).float()
+    o = torch.bmm(att.transpose(1, 2), v)                                         # o[j] = sum_i att[i, j] v[i]
+    ref = torch.relu((x.float() + gamma * o.to(torch.bfloat16).float()) * scale + shift)
+    return dict(x=x, w=w, b=b, scale=scale, shift=shift, gamma=gamma, d1=d1, s=s, o=o, ref=ref, dq=dq, C=C)
+
+
+@pytest.mark.parametrize("B,P", [(1, 81), (5, 81), (700, 81), (3, 96), (4, 49), (2, 1)])
+def test_attention_tcgen05_kernel_stage_by_stage(B, P):
+    """tg_net_attention_fused (tcgen05: projection, scores, att^T . v in tensor memory) against fp32 PyTorch on the same bf16
+    operands.  The accumulator tiles of position 0 are dumped and checked one contraction at a time (a wrong shared-memory
+    descriptor shows up in the first stage that uses it).  Tolerances: fp32 accumulators |d| <= 2e-3 + 2e-3 |ref| (operands are
+    exact bf16 products, only the summation order differs; the scores / o stages also see bf16-rounded q, k, v / p);
+    output |d| <= 2e-2 + 2e-2 |ref| (bf16 rounding of p, o and the result: 8 mantissa bits)."""
+    from transgo_b200 import _lib
+    L = _lib.lib()
+    c = _attention_tc_case(B, P, 1000 * B + P)
+    out = torch.full_like(c["x"], float("nan"))
+    dbg = torch.full([128 * 192 + 128 * 96 + 128 * 128], float("nan"), device="cuda")
+    _lib.check(L.tg_net_attention_fused(_lib.ptr(c["x"]), _lib.ptr(c["w"]), _lib.ptr(c["b"]), c["gamma"], _lib.ptr(c["scale"]),
+                                        _lib.ptr(c["shift"]), _lib.ptr(out), B, P, c["dq"], c["C"], _lib.ptr(dbg), _lib.stream_ptr()),
+               "tg_net_attention_fused")
+    torch.cuda.synchronize()
+    d1 = dbg[:128 * 192].reshape(128, 192)[:P]
+    s = dbg[128 * 192:128 * 192 + 128 * 96].reshape(128, 96)[:P, :P]
+    o = dbg[128 * 192 + 128 * 96:].reshape(128, 128)[:P]
+
+    def close(a, ref, tol, what):
+        err = (a - ref).abs()
+        assert bool((err <= tol + tol * ref.abs()).all()), (what, float(err.max()), float(ref.abs().max()))
+    close(d1, c["d1"][0], 2e-3, "projection")
+    close(s, c["s"][0], 3e-2, "scores")                   # q, k rounded to bf16 on both sides; fp32 sums of 32 products
+    close(o, c["o"][0], 2e-2, "att^T . v")                # p rounded to bf16 after an approximate exp2
+    assert not torch.isnan(out.float()).any()
+    close(out.float(), c["ref"], 2e-2, "output")
+    assert L.tg_net_attention_fused(_lib.ptr(c["x"]), _lib.ptr(c["w"]), _lib.ptr(c["b"]), c["gamma"], _lib.ptr(c["scale"]),
+                                    _lib.ptr(c["shift"]), _lib.ptr(out), B, 97, c["dq"], c["C"], None, _lib.stream_ptr()) != 0
+
+
+def test_attention_tcgen05_kernel_agrees_with_the_mma_sync_kernel():
+    """the tcgen05 block against the round-1 pair (library GEMM + tg_net_attention) on the same inputs: both round q, k, v, p
+    and o to bf16 at the same points, so they differ by summation order only (|d| <= 2e-2 + 2e-2 |ref|, in practice bf16 ulps)."""
+    from transgo_b200 import _lib
+    L = _lib.lib()
+    B, P = 64, 81
+    c = _attention_tc_case(B, P, 77)
+    out_tc = torch.empty_like(c["x"]); out_mma = torch.empty_like(c["x"])
+    _lib.check(L.tg_net_attention_fused(_lib.ptr(c["x"]), _lib.ptr(c["w"]), _lib.ptr(c["b"]), c["gamma"], _lib.ptr(c["scale"]),
+                                        _lib.ptr(c["shift"]), _lib.ptr(out_tc), B, P, c["dq"], c["C"], None, _lib.stream_ptr()))
+    qkv = torch.nn.functional.linear(c["x"], c["w"], c["b"])
+    _lib.check(L.tg_net_attention(_lib.ptr(qkv), _lib.ptr(c["x"]), c["gamma"], _lib.ptr(c["scale"]), _lib.ptr(c["shift"]), _lib.ptr(out_mma),
+                                  B, P, c["dq"], c["C"], _lib.stream_ptr()))
+    err = (out_tc.float() - out_mma.float()).abs()
+    assert bool((err <= 2e-2 + 2e-2 * out_mma.float().abs()).all()), float(err.max())
+
+
 def test_fused_forward_matches_fp32_module():
     """Tolerance: policy max |dp| <= 4e-3 (probabilities), value / ownership max |dv| <= 4e-2 -- bf16 activations through
     26 convolution layers; argmax of the policy must agree wherever the fp32 margin exceeds the tolerance."""
