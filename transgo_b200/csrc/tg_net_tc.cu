@@ -4,14 +4,19 @@
 // tensor cores (tcgen05.mma, operands in shared memory, accumulators in tensor memory) -- q, k, v and the scores never touch HBM.
 // (tg_net.cu keeps the mma.sync kernels: they are the cross-check, and the path for boards with more than 96 points.)
 //
-// One CTA = 128 threads = the 128 TMEM lanes = 128 operand rows (81 points padded); two CTAs per SM (2 x 256 TMEM columns,
-// 2 x 107 KB shared memory), each looping over positions.  Per position:
+// One CTA = 256 threads: the 128 TMEM lanes = 128 operand rows (81 points padded), TWO threads per row that split the columns
+// (warps w and w + 4 see the same 32 lanes); two CTAs per SM (2 x 256 TMEM columns, 2 x 107 KB shared memory), each looping over
+// positions with the next position's x tile fetched into registers a position ahead.  Per position:
 //   1. x tile  [128 x 128] bf16 -> shared memory (K-major panels)              D1[i][n] = sum_c x[i][c] w[n][c]     8 MMAs, N = 192
-//   2. thread i reads row i of D1 (tcgen05.ld 32x32b), adds the bias, rounds to bf16 and parks q / k (K-major) and v (MN-major)
-//                                                                               S[i][j]  = sum_d q[i][d] k[j][d]     2 MMAs, N = 96
-//   3. thread i owns row i of S: softmax over j in registers, p[i][:] -> shared memory as the MN-major A operand p^T
-//                                                                               O[j][c]  = sum_i p[i][j] v[i][c]     6 MMAs, N = 128
-//   4. thread j reads row j of O, junction epilogue against x[j][:] from global memory, 16-byte stores.
+//   2. the two threads of row i read it from TMEM (tcgen05.ld 32x32b), add the bias, round to bf16 and park q / k (K-major);
+//      the score MMA is issued at once                                          S[i][j]  = sum_d q[i][d] k[j][d]     2 MMAs, N = 96
+//      and runs while the same threads park v (MN-major)
+//   3. softmax over the keys j of row i: each thread of the pair owns 48 columns, one exchange of (max, sum) through shared
+//      memory; p[i][:] -> shared memory as the MN-major A operand p^T           O[j][c]  = sum_i p[i][j] v[i][c]     6 MMAs, N = 128
+//   4. row j of O -> bf16 -> shared memory (over the dead v panels); then the junction as a COALESCED pass over the tile: 16 threads
+//      per row, x from global memory (an L2 hit, requested before the MMA wait), relu(bn(gamma * o + x)), 16-byte stores.
+// TMEM columns: D1 = v [0,128) | q [128,160) | k [160,192) (the weight rows are permuted on the way into shared memory),
+// S [128,224) over the parked q | k, O [0,128) over the parked v.
 // Shared-memory operand layout ("panels"): the canonical no-swizzle layout of the UMMA descriptors with all rows of a
 // 16-byte column chunk contiguous --  byte(row r, chunk q) = q * PANEL + r * 16.  For a K-major operand (chunks along K) that
 // is SBO = 128 (8-row core-matrix groups), LBO = PANEL; for an MN-major operand (chunks along M / N, rows = K index) it is
@@ -28,7 +33,7 @@ namespace tc {
 constexpr int kM = 128;                 // MMA M = TMEM lanes = threads
 constexpr int kPts = 96;                // points padded to a multiple of 16 (N of the scores, K of att^T . v)
 constexpr int kC = 128, kDq = 32, kNqkv = kC + 2 * kDq;
-constexpr int kTcThreads = 128;
+constexpr int kTcThreads = 256;
 constexpr int PX = kM * 16 + 16;        // x:    16 channel chunks x 128 rows
 constexpr int PW = kNqkv * 16 + 16;     // w:    16 channel chunks x 192 rows (n)
 constexpr int PQ = kM * 16 + 16;        // q:     4 chunks x 128 rows (i)
@@ -43,12 +48,13 @@ constexpr int OFF_R1 = OFF_SHIFT + kC * 4;          // x, then q | k, then p^T (
 constexpr int R1_BYTES = 16 * PX;
 constexpr int OFF_Q = OFF_R1, OFF_K = OFF_R1 + 4 * PQ, OFF_P = OFF_R1;
 constexpr int OFF_V = OFF_R1 + R1_BYTES;
-constexpr int OFF_BAR = OFF_V + 16 * PV;
+constexpr int OFF_SM = OFF_V + 16 * PV;             // softmax exchange: float2 (max, sum) [2][128]
+constexpr int OFF_BAR = OFF_SM + 2 * kM * 8;
 constexpr int SMEM_BYTES = OFF_BAR + 16;
 static_assert(4 * PQ + 4 * PK <= R1_BYTES && 16 * PP <= R1_BYTES, "q | k and p^T live in the x tile");
 static_assert(SMEM_BYTES * 2 + 2048 <= 227 * 1024, "two CTAs per SM");
-constexpr int kTmemCols = 256;          // D1: [0,192)   S: [0,96) after D1 is parked   O: [96,224)
-constexpr int kColS = 0, kColO = 96;
+constexpr int kTmemCols = 256;
+constexpr int kColV = 0, kColQ = 128, kColK = 160, kColS = 128, kColO = 0;
 constexpr float kLog2e = 1.4426950408889634f;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -94,6 +100,12 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
                    "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
                  : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+                   "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
@@ -101,21 +113,51 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 }
 __device__ __forceinline__ float2 unpack_bf16(uint32_t w) { return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w)); }
 
-// dbg (may be null): position 0 dumps D1 + bias [128][192], S [128][96], O [128][128] as float32 (tests check every stage)
+__device__ __forceinline__ void load_x_tile(const __nv_bfloat16* __restrict__ xp, int P, int tid, uint4* v) {
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        const int i = (tid >> 4) + 16 * it, q = tid & 15;
+        v[it] = i < P ? __ldg(reinterpret_cast<const uint4*>(xp + (size_t)i * kC + q * 8)) : make_uint4(0, 0, 0, 0);
+    }
+}
+// 32 accumulator columns + bias -> four 16-byte bf16 chunks in a panel (chunk stride `pstride`); zero = write zeros instead
+__device__ __forceinline__ void park32(const uint32_t* r, const float* __restrict__ bias32, unsigned char* dst, int pstride, bool zero,
+                                       float* __restrict__ dump) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const float4 b0 = *reinterpret_cast<const float4*>(bias32 + 8 * q), b1 = *reinterpret_cast<const float4*>(bias32 + 8 * q + 4);
+        float f[8];
+        f[0] = __uint_as_float(r[8 * q]) + b0.x; f[1] = __uint_as_float(r[8 * q + 1]) + b0.y; f[2] = __uint_as_float(r[8 * q + 2]) + b0.z;
+        f[3] = __uint_as_float(r[8 * q + 3]) + b0.w; f[4] = __uint_as_float(r[8 * q + 4]) + b1.x; f[5] = __uint_as_float(r[8 * q + 5]) + b1.y;
+        f[6] = __uint_as_float(r[8 * q + 6]) + b1.z; f[7] = __uint_as_float(r[8 * q + 7]) + b1.w;
+        if (dump) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) dump[8 * q + e] = f[e];
+        }
+        uint4 o = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+        if (zero) o = make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4*>(dst + q * pstride) = o;
+    }
+}
+
+// dbg (may be null): position 0 dumps D1 + bias [128][192] (q | k | v order), S [128][96], O [128][128] as float32 (tests check
+// every stage).  PC: the point count as a compile-time constant (81: the 9x9 board), 0 = run-time P
+template <int PC>
 __global__ void __launch_bounds__(kTcThreads, 2)
 k_attention_tc(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w, const __nv_bfloat16* __restrict__ bias,
                float gamma, const float* __restrict__ scale, const float* __restrict__ shift, __nv_bfloat16* __restrict__ out,
-               int B, int P, float* __restrict__ dbg) {
+               int B, int Prt, float* __restrict__ dbg) {
+    const int P = PC ? PC : Prt;
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint32_t s_tmem;
     const int tid = threadIdx.x, warp = tid >> 5;
+    const int row = tid & (kM - 1), h = tid >> 7;                     // this thread's operand row / TMEM lane and its column half
     const uint32_t sbase = smem_u32(smem);
     const uint32_t bar = sbase + OFF_BAR;
-    float* s_bias = reinterpret_cast<float*>(smem + OFF_BIAS);
-    float* s_scale = reinterpret_cast<float*>(smem + OFF_SCALE);
-    float* s_shift = reinterpret_cast<float*>(smem + OFF_SHIFT);
+    float* s_bias = reinterpret_cast<float*>(smem + OFF_BIAS);        // in TMEM column order: v | q | k
+    float2* s_sm = reinterpret_cast<float2*>(smem + OFF_SM);
 
-    // ---- one-time setup: TMEM columns, the barrier, the weights as K-major panels, bias / scale / shift
+    // ---- one-time setup: TMEM columns, the barrier, the weights as K-major panels (rows permuted to v | q | k), the bias
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&s_tmem)), "r"(kTmemCols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -126,38 +168,37 @@ k_attention_tc(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restr
     }
     for (int idx = tid; idx < kNqkv * 16; idx += kTcThreads) {
         const int n = idx >> 4, q = idx & 15;
+        const int np = n < 2 * kDq ? n + kC : n - 2 * kDq;            // q | k | v  ->  v | q | k
         const uint4 v = *reinterpret_cast<const uint4*>(w + (size_t)n * kC + q * 8);
-        *reinterpret_cast<uint4*>(smem + OFF_W + q * PW + n * 16) = v;
+        *reinterpret_cast<uint4*>(smem + OFF_W + q * PW + np * 16) = v;
     }
-    for (int i = tid; i < kNqkv; i += kTcThreads) s_bias[i] = __bfloat162float(bias[i]);
-    for (int i = tid; i < kC; i += kTcThreads) { s_scale[i] = scale[i]; s_shift[i] = shift[i]; }
+    for (int n = tid; n < kNqkv; n += kTcThreads) s_bias[n < 2 * kDq ? n + kC : n - 2 * kDq] = __bfloat162float(bias[n]);
+    // the junction pass gives a thread the same 8 channels of every row it touches: their scale / shift live in registers
+    float sc[8], sh[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { sc[e] = scale[(tid & 15) * 8 + e]; sh[e] = shift[(tid & 15) * 8 + e]; }
     fence_async_smem();
     tc_before_sync();
     __syncthreads();
     tc_after_sync();
     const uint32_t tmem = s_tmem;
-    const uint32_t tlane = tmem + ((uint32_t)(warp * 32) << 16);      // this warp's 32 lanes; thread tid <-> lane tid <-> row tid
+    const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     uint32_t phase = 0;
     constexpr uint32_t ID_PROJ = instr_desc(kNqkv, 0, 0), ID_S = instr_desc(kPts, 0, 0), ID_O = instr_desc(kC, 1, 1);
+    const int tile_chunks = P * 16;                                   // 16-byte chunks of one position's [P][128] bf16 tile
 
+    uint4 xt[8];                                                      // the NEXT position's x tile, fetched a position ahead
+    if ((int)blockIdx.x < B) load_x_tile(x + (size_t)blockIdx.x * P * kC, P, tid, xt);
     for (int pos = blockIdx.x; pos < B; pos += gridDim.x) {
-        const __nv_bfloat16* xp = x + (size_t)pos * P * kC;
-        // ---- 1. the x tile, rows >= P zero; all 16 loads of a thread in flight before the first store
-        {
-            uint4 v[16];
+        const bool dump = dbg != nullptr && pos == 0;
+        // ---- 1. the x tile (rows >= P zero) from the registers that were filled during the previous position
 #pragma unroll
-            for (int it = 0; it < 16; ++it) {
-                const int i = (tid >> 4) + 8 * it, q = tid & 15;
-                v[it] = i < P ? __ldg(reinterpret_cast<const uint4*>(xp + (size_t)i * kC + q * 8)) : make_uint4(0, 0, 0, 0);
-            }
-#pragma unroll
-            for (int it = 0; it < 16; ++it) {
-                const int i = (tid >> 4) + 8 * it, q = tid & 15;
-                *reinterpret_cast<uint4*>(smem + OFF_R1 + q * PX + i * 16) = v[it];
-            }
+        for (int it = 0; it < 8; ++it) {
+            const int i = (tid >> 4) + 16 * it, q = tid & 15;
+            *reinterpret_cast<uint4*>(smem + OFF_R1 + q * PX + i * 16) = xt[it];
         }
         fence_async_smem();
-        tc_before_sync();                         // the previous position's tcgen05.ld of O precede the MMAs below
+        tc_before_sync();
         __syncthreads();
         if (tid == 0) {
             tc_after_sync();
@@ -168,33 +209,13 @@ k_attention_tc(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restr
         }
         mbar_wait(bar, phase); phase ^= 1;
         tc_after_sync();
-        // ---- 2. row tid of D1: + bias, bf16, q / k as K-major panels, v as MN-major panels (rows >= P zero)
-#pragma unroll 1
-        for (int ch = 0; ch < kNqkv / 32; ++ch) {
+        // ---- 2a. q (h = 0) / k (h = 1) of this row: + bias, bf16, K-major panels over the dead x tile; then the score MMA at once
+        {
             uint32_t r[32];
-            tmem_ld32(tlane + ch * 32, r);
+            tmem_ld32(tlane + (h ? kColK : kColQ), r);
             tmem_ld_wait();
-            float f[32];
-#pragma unroll
-            for (int e = 0; e < 32; ++e) f[e] = __uint_as_float(r[e]) + s_bias[ch * 32 + e];
-            if (dbg && pos == 0) {
-#pragma unroll
-                for (int e = 0; e < 32; ++e) dbg[tid * kNqkv + ch * 32 + e] = f[e];
-            }
-            const bool live = ch == 0 || tid < kPts;
-            const bool zero = ch >= 2 && tid >= P;
-            unsigned char* dst = ch == 0 ? smem + OFF_Q + tid * 16 : ch == 1 ? smem + OFF_K + tid * 16 : smem + OFF_V + (ch - 2) * 4 * PV + tid * 16;
-            const int pstride = ch == 0 ? PQ : ch == 1 ? PK : PV;
-            if (live) {
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    uint4 o;
-                    o.x = pack_bf16(f[8 * q], f[8 * q + 1]); o.y = pack_bf16(f[8 * q + 2], f[8 * q + 3]);
-                    o.z = pack_bf16(f[8 * q + 4], f[8 * q + 5]); o.w = pack_bf16(f[8 * q + 6], f[8 * q + 7]);
-                    if (zero) o = make_uint4(0, 0, 0, 0);
-                    *reinterpret_cast<uint4*>(dst + q * pstride) = o;
-                }
-            }
+            if (h == 0) park32(r, s_bias + kColQ, smem + OFF_Q + row * 16, PQ, false, dump ? dbg + row * kNqkv : nullptr);
+            else if (row < kPts) park32(r, s_bias + kColK, smem + OFF_K + row * 16, PK, false, dump ? dbg + row * kNqkv + kDq : nullptr);
         }
         fence_async_smem();
         tc_before_sync();
@@ -206,38 +227,62 @@ k_attention_tc(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restr
                 umma(tmem + kColS, smem_desc(sbase + OFF_Q + 2 * k * PQ, PQ, 128), smem_desc(sbase + OFF_K + 2 * k * PK, PK, 128), ID_S, k > 0);
             umma_commit(bar);
         }
+        // ---- 2b. meanwhile v: channels [64h, 64h + 64) of this row as MN-major panels (rows >= P zero: they must add nothing to o)
+        if (row < kPts) {
+#pragma unroll
+            for (int c2 = 0; c2 < 2; ++c2) {
+                uint32_t r[32];
+                const int c0 = 64 * h + 32 * c2;
+                tmem_ld32(tlane + kColV + c0, r);
+                tmem_ld_wait();
+                park32(r, s_bias + kColV + c0, smem + OFF_V + (c0 >> 3) * PV + row * 16, PV, row >= P, dump ? dbg + row * kNqkv + 2 * kDq + c0 : nullptr);
+            }
+        }
         mbar_wait(bar, phase); phase ^= 1;
         tc_after_sync();
-        // ---- 3. softmax over the keys j of row tid (model.py:304-305), p^T as the MN-major A operand
+        // ---- 3. softmax over the keys j of this row (model.py:304-305): this thread owns j in [48h, 48h + 48)
         {
-            float s[kPts];
-#pragma unroll
-            for (int ch = 0; ch < kPts / 32; ++ch) {
+            constexpr int HW = kPts / 2;
+            float s[HW];
+            {
                 uint32_t r[32];
-                tmem_ld32(tlane + kColS + ch * 32, r);
+                tmem_ld32(tlane + kColS + HW * h, r);
                 tmem_ld_wait();
 #pragma unroll
-                for (int e = 0; e < 32; ++e) s[ch * 32 + e] = __uint_as_float(r[e]);
+                for (int e = 0; e < 32; ++e) s[e] = __uint_as_float(r[e]);
+                tmem_ld16(tlane + kColS + HW * h + 32, r);
+                tmem_ld_wait();
+#pragma unroll
+                for (int e = 0; e < 16; ++e) s[32 + e] = __uint_as_float(r[e]);
             }
-            if (dbg && pos == 0) {
+            if (dump) {
 #pragma unroll
-                for (int e = 0; e < kPts; ++e) dbg[kM * kNqkv + tid * kPts + e] = s[e];
+                for (int e = 0; e < HW; ++e) dbg[kM * kNqkv + row * kPts + HW * h + e] = s[e];
             }
-            float m = -3.0e38f;
+            const int j0 = HW * h;
+            float m4[4] = {-3.0e38f, -3.0e38f, -3.0e38f, -3.0e38f};   // four independent chains
 #pragma unroll
-            for (int e = 0; e < kPts; ++e) m = (e < P) ? fmaxf(m, s[e]) : m;
-            const float mb = m * kLog2e;
-            float z = 0.0f;
+            for (int e = 0; e < HW; ++e) m4[e & 3] = (j0 + e < P) ? fmaxf(m4[e & 3], s[e]) : m4[e & 3];
+            const float mloc = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+            const float mb = mloc * kLog2e;
+            float z4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
-            for (int e = 0; e < kPts; ++e) { s[e] = (e < P) ? ex2_fast(fmaf(s[e], kLog2e, -mb)) : 0.0f; z += s[e]; }
-            const float inv = (tid < P) ? 1.0f / z : 0.0f;            // rows >= P do not exist: p = 0
-            if (tid < kPts) {
+            for (int e = 0; e < HW; ++e) { s[e] = (j0 + e < P) ? ex2_fast(fmaf(s[e], kLog2e, -mb)) : 0.0f; z4[e & 3] += s[e]; }
+            const float zloc = (z4[0] + z4[1]) + (z4[2] + z4[3]);
+            s_sm[h * kM + row] = make_float2(mloc, zloc);
+            __syncthreads();
+            const float2 other = s_sm[(h ^ 1) * kM + row];
+            const float mall = fmaxf(mloc, other.x);                  // the halves meet: exp(s - m) = exp(s - m_h) * exp(m_h - m)
+            const float fme = ex2_fast((mloc - mall) * kLog2e), fot = ex2_fast((other.x - mall) * kLog2e);
+            const float z = zloc * fme + other.y * fot;
+            const float inv = (row < P) ? fme / z : 0.0f;             // rows >= P do not exist: p = 0
+            if (row < kPts) {
 #pragma unroll
-                for (int q = 0; q < kPts / 8; ++q) {
+                for (int q = 0; q < HW / 8; ++q) {
                     uint4 o;
                     o.x = pack_bf16(s[8 * q] * inv, s[8 * q + 1] * inv); o.y = pack_bf16(s[8 * q + 2] * inv, s[8 * q + 3] * inv);
                     o.z = pack_bf16(s[8 * q + 4] * inv, s[8 * q + 5] * inv); o.w = pack_bf16(s[8 * q + 6] * inv, s[8 * q + 7] * inv);
-                    *reinterpret_cast<uint4*>(smem + OFF_P + q * PP + tid * 16) = o;
+                    *reinterpret_cast<uint4*>(smem + OFF_P + (HW / 8 * h + q) * PP + row * 16) = o;
                 }
             }
         }
@@ -251,42 +296,55 @@ k_attention_tc(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restr
                 umma(tmem + kColO, smem_desc(sbase + OFF_P + k * 256, 128, PP), smem_desc(sbase + OFF_V + k * 256, 128, PV), ID_O, k > 0);
             umma_commit(bar);
         }
+        // while the tensor core works: the x chunks of the junction pass (coalesced; an L2 hit, the tile was read a position ago)
+        // and the next position's tile
+        const uint4* xg = reinterpret_cast<const uint4*>(x + (size_t)pos * P * kC);
+        uint4 xj[6];
+#pragma unroll
+        for (int it = 0; it < 6; ++it) { const int idx = tid + kTcThreads * it; xj[it] = idx < tile_chunks ? __ldg(xg + idx) : make_uint4(0, 0, 0, 0); }
+        if (pos + (int)gridDim.x < B) load_x_tile(x + (size_t)(pos + gridDim.x) * P * kC, P, tid, xt);
         mbar_wait(bar, phase); phase ^= 1;
         tc_after_sync();
-        // ---- 4. row tid of O: relu(bn(gamma * o + x)) (model.py:312-313), o rounded to bf16 first like the unfused block
-        __nv_bfloat16* op = out + ((size_t)pos * P + tid) * kC;
-        const __nv_bfloat16* xr = xp + (size_t)tid * kC;
-#pragma unroll 1
-        for (int ch = 0; ch < kC / 32; ++ch) {
+        // ---- 4a. channels [64h, 64h + 64) of row `row` of O -> bf16 -> the dead v panels (chunk q, row j at q * PV + j * 16)
+#pragma unroll
+        for (int c2 = 0; c2 < 2; ++c2) {
             uint32_t r[32];
-            tmem_ld32(tlane + kColO + ch * 32, r);
-            uint4 xv[4];
-            if (tid < P) {
-#pragma unroll
-                for (int q = 0; q < 4; ++q) xv[q] = __ldg(reinterpret_cast<const uint4*>(xr + ch * 32 + q * 8));
-            }
+            const int c0 = 64 * h + 32 * c2;
+            tmem_ld32(tlane + kColO + c0, r);
             tmem_ld_wait();
-            if (dbg && pos == 0) {
+            if (dump) {
 #pragma unroll
-                for (int e = 0; e < 32; ++e) dbg[kM * kNqkv + kM * kPts + tid * kC + ch * 32 + e] = __uint_as_float(r[e]);
+                for (int e = 0; e < 32; ++e) dbg[kM * kNqkv + kM * kPts + row * kC + c0 + e] = __uint_as_float(r[e]);
             }
-            if (tid < P) {
+            if (row < kPts) {
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const uint32_t xw[4] = {xv[q].x, xv[q].y, xv[q].z, xv[q].w};
-                    uint32_t ow[4];
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const int c = ch * 32 + q * 8 + 2 * k;
-                        const float2 xf = unpack_bf16(xw[k]);
-                        const float2 of = unpack_bf16(pack_bf16(__uint_as_float(r[q * 8 + 2 * k]), __uint_as_float(r[q * 8 + 2 * k + 1])));
-                        const float s0 = fmaf(gamma, of.x, xf.x), s1 = fmaf(gamma, of.y, xf.y);
-                        ow[k] = pack_bf16(fmaxf(fmaf(s0, s_scale[c], s_shift[c]), 0.0f), fmaxf(fmaf(s1, s_scale[c + 1], s_shift[c + 1]), 0.0f));
-                    }
-                    *reinterpret_cast<uint4*>(op + ch * 32 + q * 8) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
-                }
+                for (int q = 0; q < 4; ++q)
+                    *reinterpret_cast<uint4*>(smem + OFF_V + ((c0 >> 3) + q) * PV + row * 16) =
+                        make_uint4(pack_bf16(__uint_as_float(r[8 * q]), __uint_as_float(r[8 * q + 1])), pack_bf16(__uint_as_float(r[8 * q + 2]), __uint_as_float(r[8 * q + 3])),
+                                   pack_bf16(__uint_as_float(r[8 * q + 4]), __uint_as_float(r[8 * q + 5])), pack_bf16(__uint_as_float(r[8 * q + 6]), __uint_as_float(r[8 * q + 7])));
             }
         }
+        tc_before_sync();                         // these tcgen05.ld precede the next position's MMAs into the same columns
+        __syncthreads();
+        // ---- 4b. the junction, coalesced: relu(bn(gamma * o + x)) (model.py:312-313); thread -> chunk tid & 15 of rows (tid >> 4) + 16 it
+        uint4* og = reinterpret_cast<uint4*>(out + (size_t)pos * P * kC);
+#pragma unroll
+        for (int it = 0; it < 6; ++it) {
+            const int idx = tid + kTcThreads * it;
+            if (idx < tile_chunks) {
+                const uint4 ov = *reinterpret_cast<const uint4*>(smem + OFF_V + (tid & 15) * PV + (idx >> 4) * 16);
+                const uint32_t ow[4] = {ov.x, ov.y, ov.z, ov.w}, xw[4] = {xj[it].x, xj[it].y, xj[it].z, xj[it].w};
+                uint32_t res[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float2 of = unpack_bf16(ow[k]), xf = unpack_bf16(xw[k]);
+                    const float s0 = fmaf(gamma, of.x, xf.x), s1 = fmaf(gamma, of.y, xf.y);
+                    res[k] = pack_bf16(fmaxf(fmaf(s0, sc[2 * k], sh[2 * k]), 0.0f), fmaxf(fmaf(s1, sc[2 * k + 1], sh[2 * k + 1]), 0.0f));
+                }
+                og[idx] = make_uint4(res[0], res[1], res[2], res[3]);
+            }
+        }
+        // (the next position's v panels are written three barriers from here: the reads above are long done)
     }
     tc_before_sync();
     __syncthreads();
@@ -305,14 +363,16 @@ extern "C" int tg_net_attention_fused(const void* x, const void* wqkv, const voi
     static unsigned long long attr_done = 0;                 // one bit per device
     int dev = 0; cudaGetDevice(&dev);
     if (!((attr_done >> (dev & 63)) & 1ull)) {
-        const cudaError_t e = cudaFuncSetAttribute(k_attention_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(k_attention_tc<81>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_attention_tc<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
         if (e != cudaSuccess) return set_err((int)e, "tg_net_attention_fused (shared memory attribute)");
         attr_done |= 1ull << (dev & 63);
     }
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const long long grid = B < 2LL * sms ? B : 2LL * sms;    // persistent: two CTAs per SM, each walks positions blockIdx, + grid, ...
-    k_attention_tc<<<(unsigned)grid, kTcThreads, SMEM_BYTES, (cudaStream_t)stream>>>(
+    auto kern = P == 81 ? k_attention_tc<81> : k_attention_tc<0>;
+    kern<<<(unsigned)grid, kTcThreads, SMEM_BYTES, (cudaStream_t)stream>>>(
         (const __nv_bfloat16*)x, (const __nv_bfloat16*)wqkv, (const __nv_bfloat16*)bqkv, gamma, scale, shift, (__nv_bfloat16*)out, (int)B, P, debug);
     return set_err((int)cudaGetLastError(), "tg_net_attention_fused");
 }
