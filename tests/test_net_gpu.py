@@ -145,12 +145,13 @@ def test_attention_tcgen05_kernel_agrees_with_the_mma_sync_kernel():
     assert bool((err <= 2e-2 + 2e-2 * out_mma.float().abs()).all()), float(err.max())
 
 
-def test_fused_forward_matches_fp32_module():
+@pytest.mark.parametrize("attention", ["tcgen05", "mma"])
+def test_fused_forward_matches_fp32_module(attention):
     """Tolerance: policy max |dp| <= 4e-3 (probabilities), value / ownership max |dv| <= 4e-2 -- bf16 activations through
     26 convolution layers; argmax of the policy must agree wherever the fp32 margin exceeds the tolerance."""
     from transgo_b200.fused_net import FusedTransGoInference
     m = _perturbed_model()
-    fused = FusedTransGoInference(m)
+    fused = FusedTransGoInference(m, attention=attention)
     g = torch.Generator(device="cuda"); g.manual_seed(3)
     obs = (torch.rand([257, 10, 9, 9], device="cuda", generator=g) > 0.75).float()
     with torch.no_grad():

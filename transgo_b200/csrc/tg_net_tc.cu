@@ -140,6 +140,55 @@ __device__ __forceinline__ void park32(const uint32_t* r, const float* __restric
     }
 }
 
+// softmax of one row, columns [48 H, 48 H + 48) (H is a template parameter so that the key mask j < P folds at compile time when
+// P is a constant); the two halves of a row meet through `sm` (one __syncthreads inside: every thread of the CTA calls this)
+template <int H>
+__device__ __forceinline__ void softmax_half(uint32_t tlane, int row, int P, float2* __restrict__ sm, unsigned char* __restrict__ smem,
+                                             float* __restrict__ dump) {
+    constexpr int HW = kPts / 2, j0 = HW * H;
+    float s[HW];
+    {
+        uint32_t r[32];
+        tmem_ld32(tlane + kColS + j0, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 32; ++e) s[e] = __uint_as_float(r[e]);
+        tmem_ld16(tlane + kColS + j0 + 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 16; ++e) s[32 + e] = __uint_as_float(r[e]);
+    }
+    if (dump) {
+#pragma unroll
+        for (int e = 0; e < HW; ++e) dump[row * kPts + j0 + e] = s[e];
+    }
+    float m4[4] = {-3.0e38f, -3.0e38f, -3.0e38f, -3.0e38f};           // four independent chains
+#pragma unroll
+    for (int e = 0; e < HW; ++e) m4[e & 3] = (j0 + e < P) ? fmaxf(m4[e & 3], s[e]) : m4[e & 3];
+    const float mloc = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+    const float mb = mloc * kLog2e;
+    float z4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+    for (int e = 0; e < HW; ++e) { s[e] = (j0 + e < P) ? ex2_fast(fmaf(s[e], kLog2e, -mb)) : 0.0f; z4[e & 3] += s[e]; }
+    const float zloc = (z4[0] + z4[1]) + (z4[2] + z4[3]);
+    sm[H * kM + row] = make_float2(mloc, zloc);
+    __syncthreads();
+    const float2 other = sm[(H ^ 1) * kM + row];
+    const float mall = fmaxf(mloc, other.x);                          // exp(s - m) = exp(s - m_half) * exp(m_half - m)
+    const float fme = ex2_fast((mloc - mall) * kLog2e), fot = ex2_fast((other.x - mall) * kLog2e);
+    const float z = zloc * fme + other.y * fot;
+    const float inv = (row < P) ? fme / z : 0.0f;                     // rows >= P do not exist: p = 0
+    if (row < kPts) {
+#pragma unroll
+        for (int q = 0; q < HW / 8; ++q) {
+            uint4 o;
+            o.x = pack_bf16(s[8 * q] * inv, s[8 * q + 1] * inv); o.y = pack_bf16(s[8 * q + 2] * inv, s[8 * q + 3] * inv);
+            o.z = pack_bf16(s[8 * q + 4] * inv, s[8 * q + 5] * inv); o.w = pack_bf16(s[8 * q + 6] * inv, s[8 * q + 7] * inv);
+            *reinterpret_cast<uint4*>(smem + OFF_P + (HW / 8 * H + q) * PP + row * 16) = o;
+        }
+    }
+}
+
 // dbg (may be null): position 0 dumps D1 + bias [128][192] (q | k | v order), S [128][96], O [128][128] as float32 (tests check
 // every stage).  PC: the point count as a compile-time constant (81: the 9x9 board), 0 = run-time P
 template <int PC>
@@ -166,11 +215,17 @@ k_attention_tc(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restr
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(1) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int idx = tid; idx < kNqkv * 16; idx += kTcThreads) {
-        const int n = idx >> 4, q = idx & 15;
-        const int np = n < 2 * kDq ? n + kC : n - 2 * kDq;            // q | k | v  ->  v | q | k
-        const uint4 v = *reinterpret_cast<const uint4*>(w + (size_t)n * kC + q * 8);
-        *reinterpret_cast<uint4*>(smem + OFF_W + q * PW + np * 16) = v;
+    {
+        constexpr int WIT = kNqkv * 16 / kTcThreads;                  // 12 chunks per thread, all loads in flight before the first store
+        uint4 wv[WIT];
+#pragma unroll
+        for (int it = 0; it < WIT; ++it) wv[it] = __ldg(reinterpret_cast<const uint4*>(w) + tid + kTcThreads * it);
+#pragma unroll
+        for (int it = 0; it < WIT; ++it) {
+            const int idx = tid + kTcThreads * it, n = idx >> 4, q = idx & 15;
+            const int np = n < 2 * kDq ? n + kC : n - 2 * kDq;        // q | k | v  ->  v | q | k
+            *reinterpret_cast<uint4*>(smem + OFF_W + q * PW + np * 16) = wv[it];
+        }
     }
     for (int n = tid; n < kNqkv; n += kTcThreads) s_bias[n < 2 * kDq ? n + kC : n - 2 * kDq] = __bfloat162float(bias[n]);
     // the junction pass gives a thread the same 8 channels of every row it touches: their scale / shift live in registers
@@ -241,51 +296,10 @@ k_attention_tc(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restr
         mbar_wait(bar, phase); phase ^= 1;
         tc_after_sync();
         // ---- 3. softmax over the keys j of this row (model.py:304-305): this thread owns j in [48h, 48h + 48)
-        {
-            constexpr int HW = kPts / 2;
-            float s[HW];
-            {
-                uint32_t r[32];
-                tmem_ld32(tlane + kColS + HW * h, r);
-                tmem_ld_wait();
-#pragma unroll
-                for (int e = 0; e < 32; ++e) s[e] = __uint_as_float(r[e]);
-                tmem_ld16(tlane + kColS + HW * h + 32, r);
-                tmem_ld_wait();
-#pragma unroll
-                for (int e = 0; e < 16; ++e) s[32 + e] = __uint_as_float(r[e]);
-            }
-            if (dump) {
-#pragma unroll
-                for (int e = 0; e < HW; ++e) dbg[kM * kNqkv + row * kPts + HW * h + e] = s[e];
-            }
-            const int j0 = HW * h;
-            float m4[4] = {-3.0e38f, -3.0e38f, -3.0e38f, -3.0e38f};   // four independent chains
-#pragma unroll
-            for (int e = 0; e < HW; ++e) m4[e & 3] = (j0 + e < P) ? fmaxf(m4[e & 3], s[e]) : m4[e & 3];
-            const float mloc = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
-            const float mb = mloc * kLog2e;
-            float z4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-#pragma unroll
-            for (int e = 0; e < HW; ++e) { s[e] = (j0 + e < P) ? ex2_fast(fmaf(s[e], kLog2e, -mb)) : 0.0f; z4[e & 3] += s[e]; }
-            const float zloc = (z4[0] + z4[1]) + (z4[2] + z4[3]);
-            s_sm[h * kM + row] = make_float2(mloc, zloc);
-            __syncthreads();
-            const float2 other = s_sm[(h ^ 1) * kM + row];
-            const float mall = fmaxf(mloc, other.x);                  // the halves meet: exp(s - m) = exp(s - m_h) * exp(m_h - m)
-            const float fme = ex2_fast((mloc - mall) * kLog2e), fot = ex2_fast((other.x - mall) * kLog2e);
-            const float z = zloc * fme + other.y * fot;
-            const float inv = (row < P) ? fme / z : 0.0f;             // rows >= P do not exist: p = 0
-            if (row < kPts) {
-#pragma unroll
-                for (int q = 0; q < HW / 8; ++q) {
-                    uint4 o;
-                    o.x = pack_bf16(s[8 * q] * inv, s[8 * q + 1] * inv); o.y = pack_bf16(s[8 * q + 2] * inv, s[8 * q + 3] * inv);
-                    o.z = pack_bf16(s[8 * q + 4] * inv, s[8 * q + 5] * inv); o.w = pack_bf16(s[8 * q + 6] * inv, s[8 * q + 7] * inv);
-                    *reinterpret_cast<uint4*>(smem + OFF_P + (HW / 8 * h + q) * PP + row * 16) = o;
-                }
-            }
-        }
+        // (the next position's tile is requested first: it has the rest of this position to arrive)
+        if (pos + (int)gridDim.x < B) load_x_tile(x + (size_t)(pos + gridDim.x) * P * kC, P, tid, xt);
+        if (h == 0) softmax_half<0>(tlane, row, P, s_sm, smem, dump ? dbg + kM * kNqkv : nullptr);
+        else softmax_half<1>(tlane, row, P, s_sm, smem, dump ? dbg + kM * kNqkv : nullptr);
         fence_async_smem();
         tc_before_sync();
         __syncthreads();
@@ -297,12 +311,10 @@ k_attention_tc(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restr
             umma_commit(bar);
         }
         // while the tensor core works: the x chunks of the junction pass (coalesced; an L2 hit, the tile was read a position ago)
-        // and the next position's tile
         const uint4* xg = reinterpret_cast<const uint4*>(x + (size_t)pos * P * kC);
         uint4 xj[6];
 #pragma unroll
         for (int it = 0; it < 6; ++it) { const int idx = tid + kTcThreads * it; xj[it] = idx < tile_chunks ? __ldg(xg + idx) : make_uint4(0, 0, 0, 0); }
-        if (pos + (int)gridDim.x < B) load_x_tile(x + (size_t)(pos + gridDim.x) * P * kC, P, tid, xt);
         mbar_wait(bar, phase); phase ^= 1;
         tc_after_sync();
         // ---- 4a. channels [64h, 64h + 64) of row `row` of O -> bf16 -> the dead v panels (chunk q, row j at q * PV + j * 16)

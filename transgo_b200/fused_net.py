@@ -6,8 +6,9 @@ with bias+ReLU epilogue, cuBLAS GEMMs for the 1x1 convolutions / attention / hea
  - into a per-channel scale/shift otherwise, applied by ONE hand-written kernel per residual junction
    (tg_net_add_bn_relu: residual add / gamma*attention + x, next BatchNorm, ReLU in a single NHWC bf16 pass);
  - the four self-attention blocks (scores, softmax, weighted sum, junction) run as ONE hand-written kernel per block
-   (tg_net_attention, mma.sync bf16: scores in registers up to 96 points, a two-pass variant up to 368) fed by a single
-   q|k|v GEMM; larger boards use library batched GEMMs.
+   -- up to 96 points (9x9) INCLUDING the q|k|v projection: tg_net_attention_fused, a tcgen05 kernel (UMMA from shared-memory
+   operand panels, accumulators in tensor memory; csrc/tg_net_tc.cu); up to 368 points (19x19) tg_net_attention (mma.sync bf16,
+   two passes over the scores) fed by a single q|k|v GEMM; larger boards use library batched GEMMs.
 Activations are NHWC bf16 end to end, so the attention blocks read them as [B, P, C] views without layout copies.
 
 ``FusedTransGoInference(model)`` snapshots a ``TransGoNetwork``; ``refresh()`` re-folds after ``set_weights``.
@@ -52,8 +53,10 @@ def _copy_tree(old, new):
 
 
 class FusedTransGoInference:
-    def __init__(self, model, dtype=torch.bfloat16):
-        self.model, self.dtype = model, dtype
+    def __init__(self, model, dtype=torch.bfloat16, attention="tcgen05"):
+        """attention: "tcgen05" (default: the one-kernel block wherever it applies) or "mma" (GEMM + tg_net_attention everywhere;
+        kept as the cross-check and for timing comparisons)"""
+        self.model, self.dtype, self.attention = model, dtype, attention
         self.lib = _lib.lib()
         self._w = None
         self.refresh()
@@ -136,9 +139,16 @@ class FusedTransGoInference:
     def _attention(self, x, p):
         """model.py:299-314 on an NHWC tensor: returns relu(bn(gamma * (V . softmax(Q^T K)) + x))"""
         B, C = x.shape[0], x.shape[1]
+        dq = p["dq"]
+        if self.attention == "tcgen05" and self.P <= 96 and dq == 32 and C == 128 and self.dtype == torch.bfloat16:
+            # projection, scores, softmax, att^T . v and the junction in ONE tcgen05 kernel (csrc/tg_net_tc.cu: k_attention_tc)
+            act = torch.empty_like(x)
+            _lib.check(self.lib.tg_net_attention_fused(_lib.ptr(x), _lib.ptr(p["w"]), _lib.ptr(p["b"]), p["gamma"], _lib.ptr(p["s"]),
+                                                       _lib.ptr(p["t"]), _lib.ptr(act), B, self.P, dq, C, None,
+                                                       _lib.stream_ptr(device=x.device)), "tg_net_attention_fused")
+            return act
         x2 = x.permute(0, 2, 3, 1).reshape(B, self.P, C)                       # free view of channels_last memory
         qkv = F.linear(x2, p["w"], p["b"])
-        dq = p["dq"]
         if self.P <= 368 and dq == 32 and C == 128 and self.dtype == torch.bfloat16:
             # scores, softmax, att^T . v and the junction in ONE hand-written kernel (csrc/tg_net.cu: k_attention)
             act = torch.empty_like(x)
@@ -197,12 +207,12 @@ class FusedTransGoInference:
         return policy, value, own
 
 
-def make_fused_evaluator(model, dtype=torch.bfloat16, cuda_graph=True):
+def make_fused_evaluator(model, dtype=torch.bfloat16, cuda_graph=True, attention="tcgen05"):
     """evaluator(obs) -> (policy, value) for BatchedMCTS, forward captured once per static input tensor as a CUDA graph.
     cuda_graph=False: plain launches (use it when the caller captures a larger graph, e.g. BatchedMCTS(graph_waves=True));
     cuda_graph="roots": plain launches while the current stream is being captured, own graphs otherwise (the search's wave
     batch is captured by the engine, the per-move root batch runs outside it)."""
-    net = FusedTransGoInference(model, dtype)
+    net = FusedTransGoInference(model, dtype, attention=attention)
     graphs = {}
 
     def evaluator(obs):
