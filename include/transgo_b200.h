@@ -190,6 +190,9 @@ int tg_mcts_pending(const TgMctsConfig* cfg, void* ws, int32_t* out, void* strea
 /* test hook: 1 = run the selection of every wave with one warp per game in the reference's descent order (the default kernel
  * pipelines the descents of a wave over one warp each and falls back to that order by itself where needed); returns the old value */
 int tg_mcts_debug_sequential_select(int on);
+/* diagnostics: device buffer of 4 x u64 per game (start, selection done, end in globaltimer ns; deepest path) written by every
+ * pipelined selection launch; NULL stops the recording */
+int tg_mcts_debug_times(unsigned long long* times);
 
 /* wave, second half: policy float32 [G*readouts][A] (softmaxed, model.py:111), value float32 [G*readouts];
  * pending (may be NULL; prefer tg_mcts_pending) is INCREMENTED by the number of active games still below N0 + num_simulation */

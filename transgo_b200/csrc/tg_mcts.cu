@@ -423,6 +423,11 @@ __global__ void __launch_bounds__(kThreads) k_select(View v) {
 // kernel takes two rounds: 8 CTAs of 4 warps per SM (<= 64 registers) hold 1184 games of 9x9, 4 per SM 592 games of 19x19.
 // FUSE: the leaves (step + legal mask + feature planes) follow in the same launch.  Off at 19x19, where the leaf code's register
 // needs (ten 7-word bitboards) would spill inside the residency bound above.
+// diagnostics (tg_mcts_debug_times): when set, every game's CTA of k_select_par records globaltimer at its start, after the
+// selection pipeline and at its end, plus its deepest path, as 4 x u64 per game
+__device__ unsigned long long* d_dbg_times = nullptr;
+__device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+
 template <int N, bool FUSE>
 __global__ void __launch_bounds__(32 * kParWarps, N == 9 ? 8 : 4) k_select_par(View v, float* __restrict__ obs) {
     using GG = Geo<N>;
@@ -434,6 +439,8 @@ __global__ void __launch_bounds__(32 * kParWarps, N == 9 ? 8 : 4) k_select_par(V
     const int g = blockIdx.x, R = v.R;
     const int j = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int* h = v.hdr + (size_t)g * H_WORDS;
+    unsigned long long* dbg_t = d_dbg_times;
+    if (dbg_t && threadIdx.x == 0) dbg_t[4 * g] = gtimer();
     if (!game_runs<N>(v, h)) { if (threadIdx.x == 0) h[H_NPATHS] = 0; return; }   // CTA-uniform
     volatile int* sel_node = sm_sel;
     volatile int* sel_k = sm_sel + v.MAXD * R;
@@ -514,6 +521,7 @@ __global__ void __launch_bounds__(32 * kParWarps, N == 9 ? 8 : 4) k_select_par(V
         vprog[j] = 1 << 30;
     }
     __syncthreads();
+    if (dbg_t && threadIdx.x == 0) { int md = 0; for (int jp = 0; jp < R; ++jp) md = plen[jp] > md ? plen[jp] : md; dbg_t[4 * g + 1] = gtimer(); dbg_t[4 * g + 3] = (unsigned long long)md; }
     int any_flag = 0, all_ties = 0;
     for (int jp = 0; jp < R; ++jp) { any_flag |= s_flag[jp]; all_ties += s_ties[jp]; }
     uint32_t* sm_planes = reinterpret_cast<uint32_t*>(sm_sel) + j * leaf_smem_words<N>();   // the pipeline state is dead by now
@@ -544,6 +552,7 @@ __global__ void __launch_bounds__(32 * kParWarps, N == 9 ? 8 : 4) k_select_par(V
     // ---- the leaf of this descent: step + legal mask + feature planes, straight into the evaluator's input (k_leaves fused:
     // a game goes on to its leaves as soon as ITS descents are done instead of waiting for the slowest game of the batch)
     if (FUSE) leaf_work<N>(v, nodes, slot, node, action, obs, sm_planes, lane);
+    if (dbg_t) { __syncthreads(); if (threadIdx.x == 0) dbg_t[4 * g + 2] = gtimer(); }
 }
 
 // ---------------------------------------------------------------------------------------------- leaves
@@ -1270,6 +1279,10 @@ int tg_mcts_pending(const TgMctsConfig* cfg, void* ws, int32_t* out, void* strea
     if (check_cfg(cfg) || !ws || !out) return set_err(-1, "tg_mcts_pending");
     TG_MCTS_N(cfg, { View v = make_view<N>(cfg, ws); k_pending<N><<<1, 256, 0, (cudaStream_t)stream>>>(v, out); });
     return set_err((int)cudaGetLastError(), "tg_mcts_pending");
+}
+
+int tg_mcts_debug_times(unsigned long long* times /* device, 4 x u64 per game, or NULL to stop */) {
+    return set_err((int)cudaMemcpyToSymbol(tg::d_dbg_times, &times, sizeof(times)), "tg_mcts_debug_times");
 }
 
 int tg_mcts_debug_sequential_select(int on) { const int old = g_force_sequential_select; g_force_sequential_select = on; return old; }

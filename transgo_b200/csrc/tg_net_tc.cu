@@ -189,6 +189,28 @@ __device__ __forceinline__ void softmax_half(uint32_t tlane, int row, int P, flo
     }
 }
 
+// the junction of one position, coalesced: relu(bn(gamma * o + x)) (model.py:312-313) with o (bf16) from the staging panels;
+// thread -> chunk tid & 15 of rows (tid >> 4) + 16 it
+__device__ __forceinline__ void junction_pass(const unsigned char* __restrict__ smem, const uint4* xj, uint4* __restrict__ og, int tile_chunks,
+                                              int tid, float gamma, const float* sc, const float* sh) {
+#pragma unroll
+    for (int it = 0; it < 6; ++it) {
+        const int idx = tid + kTcThreads * it;
+        if (idx < tile_chunks) {
+            const uint4 ov = *reinterpret_cast<const uint4*>(smem + OFF_V + (tid & 15) * PV + (idx >> 4) * 16);
+            const uint32_t ow[4] = {ov.x, ov.y, ov.z, ov.w}, xw[4] = {xj[it].x, xj[it].y, xj[it].z, xj[it].w};
+            uint32_t res[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float2 of = unpack_bf16(ow[k]), xf = unpack_bf16(xw[k]);
+                const float s0 = fmaf(gamma, of.x, xf.x), s1 = fmaf(gamma, of.y, xf.y);
+                res[k] = pack_bf16(fmaxf(fmaf(s0, sc[2 * k], sh[2 * k]), 0.0f), fmaxf(fmaf(s1, sc[2 * k + 1], sh[2 * k + 1]), 0.0f));
+            }
+            og[idx] = make_uint4(res[0], res[1], res[2], res[3]);
+        }
+    }
+}
+
 // dbg (may be null): position 0 dumps D1 + bias [128][192] (q | k | v order), S [128][96], O [128][128] as float32 (tests check
 // every stage).  PC: the point count as a compile-time constant (81: the 9x9 board), 0 = run-time P
 template <int PC>
@@ -215,6 +237,8 @@ k_attention_tc(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restr
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(1) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    uint4 xt[8];                                                      // the NEXT position's x tile, fetched a position ahead
+    if ((int)blockIdx.x < B) load_x_tile(x + (size_t)blockIdx.x * P * kC, P, tid, xt);      // (the first one: under the weight staging)
     {
         constexpr int WIT = kNqkv * 16 / kTcThreads;                  // 12 chunks per thread, all loads in flight before the first store
         uint4 wv[WIT];
@@ -242,8 +266,8 @@ k_attention_tc(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restr
     constexpr uint32_t ID_PROJ = instr_desc(kNqkv, 0, 0), ID_S = instr_desc(kPts, 0, 0), ID_O = instr_desc(kC, 1, 1);
     const int tile_chunks = P * 16;                                   // 16-byte chunks of one position's [P][128] bf16 tile
 
-    uint4 xt[8];                                                      // the NEXT position's x tile, fetched a position ahead
-    if ((int)blockIdx.x < B) load_x_tile(x + (size_t)blockIdx.x * P * kC, P, tid, xt);
+    uint4 xj[6];                                                      // x chunks of the pending junction pass
+    uint4* og_prev = nullptr;                                         // where the pending junction pass writes (null: none pending)
     for (int pos = blockIdx.x; pos < B; pos += gridDim.x) {
         const bool dump = dbg != nullptr && pos == 0;
         // ---- 1. the x tile (rows >= P zero) from the registers that were filled during the previous position
@@ -262,6 +286,9 @@ k_attention_tc(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restr
                 umma(tmem, smem_desc(sbase + OFF_R1 + 2 * k * PX, PX, 128), smem_desc(sbase + OFF_W + 2 * k * PW, PW, 128), ID_PROJ, k > 0);
             umma_commit(bar);
         }
+        // ---- 4b (of the PREVIOUS position). its junction pass runs while the tensor core projects this one; the barrier above
+        // also published its O staging panels
+        if (og_prev) junction_pass(smem, xj, og_prev, tile_chunks, tid, gamma, sc, sh);
         mbar_wait(bar, phase); phase ^= 1;
         tc_after_sync();
         // ---- 2a. q (h = 0) / k (h = 1) of this row: + bias, bf16, K-major panels over the dead x tile; then the score MMA at once
@@ -312,7 +339,6 @@ k_attention_tc(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restr
         }
         // while the tensor core works: the x chunks of the junction pass (coalesced; an L2 hit, the tile was read a position ago)
         const uint4* xg = reinterpret_cast<const uint4*>(x + (size_t)pos * P * kC);
-        uint4 xj[6];
 #pragma unroll
         for (int it = 0; it < 6; ++it) { const int idx = tid + kTcThreads * it; xj[it] = idx < tile_chunks ? __ldg(xg + idx) : make_uint4(0, 0, 0, 0); }
         mbar_wait(bar, phase); phase ^= 1;
@@ -337,27 +363,11 @@ k_attention_tc(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restr
             }
         }
         tc_before_sync();                         // these tcgen05.ld precede the next position's MMAs into the same columns
-        __syncthreads();
-        // ---- 4b. the junction, coalesced: relu(bn(gamma * o + x)) (model.py:312-313); thread -> chunk tid & 15 of rows (tid >> 4) + 16 it
-        uint4* og = reinterpret_cast<uint4*>(out + (size_t)pos * P * kC);
-#pragma unroll
-        for (int it = 0; it < 6; ++it) {
-            const int idx = tid + kTcThreads * it;
-            if (idx < tile_chunks) {
-                const uint4 ov = *reinterpret_cast<const uint4*>(smem + OFF_V + (tid & 15) * PV + (idx >> 4) * 16);
-                const uint32_t ow[4] = {ov.x, ov.y, ov.z, ov.w}, xw[4] = {xj[it].x, xj[it].y, xj[it].z, xj[it].w};
-                uint32_t res[4];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const float2 of = unpack_bf16(ow[k]), xf = unpack_bf16(xw[k]);
-                    const float s0 = fmaf(gamma, of.x, xf.x), s1 = fmaf(gamma, of.y, xf.y);
-                    res[k] = pack_bf16(fmaxf(fmaf(s0, sc[2 * k], sh[2 * k]), 0.0f), fmaxf(fmaf(s1, sc[2 * k + 1], sh[2 * k + 1]), 0.0f));
-                }
-                og[idx] = make_uint4(res[0], res[1], res[2], res[3]);
-            }
-        }
-        // (the next position's v panels are written three barriers from here: the reads above are long done)
+        og_prev = reinterpret_cast<uint4*>(out + (size_t)pos * P * kC);
+        // (the staging panels are read after the next barrier; the next v panels are written two barriers after that)
     }
+    __syncthreads();
+    if (og_prev) junction_pass(smem, xj, og_prev, tile_chunks, tid, gamma, sc, sh);
     tc_before_sync();
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(kTmemCols) : "memory");
