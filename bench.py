@@ -8,8 +8,10 @@ Headline workload (BASELINE.json configs[1]): 9x9 env-only batc
 games per GPU from the empty board to termination.  One *step* = one such batch: reset + playout kernel (every ply:
 group analysis -> legal mask -> hashed move draw -> capture/ko/step) + Tromp-Taylor scoring.
   value      board steps (plies) per second, whole job, game states resident in HBM, CUDA-event timed
-  e2e        same metric through the C ABI with HOST buffers: pinned initial states H2D, kernels, final states + scores +
-             the per-ply action trace D2H, all inside the timed region
+  e2e        same metric through the C ABI with HOST buffers, all transfers inside the timed region; two routes are timed and the
+             faster one is reported (both under e2e.routes): "copies" = pinned initial states H2D, kernels, final states + scores +
+             the per-ply action trace D2H as separate copy operations; "zero_copy" = ONE launch whose kernel reads / writes the
+             same pinned host buffers across PCIe itself
   roofline   k_playout against the measured HBM peak with SURVEY 8d's 115 algorithmic bytes per ply
   cpu_baseline  the UNMODIFIED reference engine (oracle/_ref/go_env9.so, compiled from /root/reference) driven through
              ctypes exactly like GoEnv/environment.py (getLegalAction + Step per ply) on every host core, same move rule
@@ -309,28 +311,56 @@ def run_ours(args):
         h_out_states.copy_(env.states, non_blocking=True)
         h_scores.copy_(d_scores, non_blocking=True)
         h_trace.copy_(d_trace, non_blocking=True)
-    for i in range(W):
-        e2e_step(2000 + i)
-    counter.zero_()
-    ee = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-    barrier()
-    sampler.active.set()
-    for i in range(K):
-        flush.zero_()
-        ee[i][0].record()
-        e2e_step(i)
-        ee[i][1].record()
-    barrier()
-    sampler.active.clear()
-    ms_e2e = sum(a.elapsed_time(b) for a, b in ee)
-    plies_e2e = int(counter.item())
-    t = torch.tensor([ms_e2e], dtype=torch.float64, device=dev)
-    p = torch.tensor([plies_e2e], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(p, op=dist.ReduceOp.SUM)
-    e2e_value = float(p[0]) / (float(t[0]) * 1e-3)
+    # the same bytes without separate copy operations: the kernel reads the pinned host states and writes the final states, the
+    # scores and the move trace into pinned host memory itself (zero-copy over PCIe; every buffer still crosses the bus once)
+    h_zc_states = torch.zeros([SQ, G, 4], dtype=torch.int32).pin_memory()
+    h_zc_scores = torch.zeros([G], dtype=torch.float32).pin_memory()
+    h_zc_trace = torch.zeros([plies_max, G], dtype=torch.int16).pin_memory()
+
+    def time_e2e(step_fn, prep=None):
+        for i in range(W):
+            if prep:
+                prep()
+            step_fn(2000 + i)
+        torch.cuda.synchronize()
+        counter.zero_()
+        ee = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+        barrier()
+        sampler.active.set()
+        for i in range(K):
+            flush.zero_()
+            if prep:
+                torch.cuda.synchronize()                       # the previous launch has finished with the host buffer
+            ee[i][0].record()
+            if prep:
+                prep()                                         # host-side input preparation INSIDE the timed region
+            step_fn(i)
+            ee[i][1].record()
+        barrier()
+        sampler.active.clear()
+        ms = sum(a.elapsed_time(b) for a, b in ee)
+        n = int(counter.item())
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        p = torch.tensor([n], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dist.all_reduce(p, op=dist.ReduceOp.SUM)
+        return float(p[0]) / (float(t[0]) * 1e-3), float(t[0])
+
+    e2e_copies_value, ms_e2e_copies = time_e2e(e2e_step)
     assert bool((h_scores * 2 % 2 == 1).all())                 # host really received final area scores
+
+    def zc_launch(i):
+        env.playout(plies_max, seed=SEED + i, game_id0=rank * G, trace=h_zc_trace, counter=counter, score_out=h_zc_scores,
+                    states=h_zc_states)
+    e2e_zc_value, ms_e2e_zc = time_e2e(zc_launch, prep=lambda: h_zc_states.copy_(h_states))
+    torch.cuda.synchronize()
+    # the two routes deliver the same bytes to the host (last timed step of each: same seed)
+    assert torch.equal(h_zc_scores, h_scores) and torch.equal(h_zc_trace, h_trace) and torch.equal(h_zc_states, h_out_states)
+    if e2e_zc_value >= e2e_copies_value:
+        e2e_value, ms_e2e, e2e_route = e2e_zc_value, ms_e2e_zc, "zero-copy: one launch, the kernel reads / writes the pinned host buffers across PCIe itself"
+    else:
+        e2e_value, ms_e2e, e2e_route = e2e_copies_value, ms_e2e_copies, "cudaMemcpyAsync H2D + launch + three cudaMemcpyAsync D2H"
 
     # ---- per-launch kernels of the stepwise API + saturation sweep (explanatory, not the headline)
     extras = {}
@@ -377,7 +407,10 @@ def run_ours(args):
                        "games_per_gpu": G, "playout_layout": env.playout_layout() + (" (library choice)" if not env.tile else ""), "board": 9,
                        "l2": "256 MB flush buffer written between timed iterations", "sharding": "games by id, no collective"},
             "e2e": {"value": e2e_value, "unit": "board steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": float(t[0]) / K},
+                    "ms_per_step": ms_e2e / K, "route": e2e_route,
+                    "routes": {"copies": {"value": e2e_copies_value, "ms_per_step": ms_e2e_copies / K},
+                               "zero_copy": {"value": e2e_zc_value, "ms_per_step": ms_e2e_zc / K,
+                                             "note": "the timed region holds the host refill of the in-place input buffer and the launch"}}},
             "gpu_launches": launches[0],
             "clocks": sampler.summary(),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -340,3 +340,25 @@ def test_fused_reset_playout_score_equals_three_launches(n, G, tile):
     se = torch.empty([G], dtype=torch.float32, device="cuda")
     e.playout(0, from_reset=True, score_out=se)                        # stone-less boards score -komi (board.cc:932-935)
     assert bool((se == -7.5).all())
+
+
+def test_playout_on_pinned_host_buffers_equals_the_device_run():
+    """zero-copy route: states, move trace and scores in pinned host memory, read / written by the kernel across PCIe; every
+    byte must equal the device-resident run (9x9 headline batch and a 19x19 batch)."""
+    import torch
+    from transgo_b200.environment import BatchedGoEnv
+    for n, G in ((9, 4096), (19, 96)):
+        env = BatchedGoEnv(G, board_size=n)
+        T = env.max_step + 1
+        d_trace = torch.full([T, G], -9, dtype=torch.int16, device="cuda")
+        d_score = torch.empty([G], dtype=torch.float32, device="cuda")
+        env.playout(T, seed=77, trace=d_trace, score_out=d_score)
+        h_states = torch.zeros([env.SQ, G, 4], dtype=torch.int32).pin_memory()
+        h_states.copy_(BatchedGoEnv(G, board_size=n).states)
+        h_trace = torch.full([T, G], -9, dtype=torch.int16).pin_memory()
+        h_score = torch.zeros([G], dtype=torch.float32).pin_memory()
+        env.playout(T, seed=77, trace=h_trace, score_out=h_score, states=h_states)
+        torch.cuda.synchronize()
+        assert torch.equal(h_states, env.states.cpu()) and torch.equal(h_trace, d_trace.cpu()) and torch.equal(h_score, d_score.cpu())
+        with pytest.raises(AssertionError):
+            env.playout(T, states=torch.zeros([env.SQ, G, 4], dtype=torch.int32))       # pageable host memory is refused
