@@ -69,10 +69,12 @@ int         tg_supported_board(int n);          /* 1 for n in {9, 19} */
 int         tg_state_bytes(int n);              /* 48 / 128 */
 int         tg_legal_words(int n);              /* u32 words of a dense legal mask, padded to 16 B: 4 / 12 */
 
-/* All pointers are device pointers; `stream` is a cudaStream_t (NULL = default stream).
+/* All pointers are device pointers; `stream` is a cudaStream_t (NULL = default stream).  The playout entry points also accept
+ * PINNED HOST pointers for `states`, `trace` and `score_out` (zero-copy: the kernel reads / writes them across PCIe once).
  * `tile` = lanes cooperating on one game: 32 (lowest latency, small batches) ... 1 (highest throughput,
- * very large batches); 0 lets the library choose from G.  tg_env_playout also takes TG_TILE_ROWS: one board ROW per lane,
- * 31 / (n + 1) games side by side in a warp (csrc/tg_rows.cuh) -- the fastest layout at the BASELINE batch sizes. */
+ * very large batches); 0 lets the library choose from G (for playouts: the incremental engine below, measured fastest at
+ * every batch size).  tg_env_playout also takes TG_TILE_ROWS: one board ROW per lane, 31 / (n + 1) games side by side in a
+ * warp (csrc/tg_rows.cuh) -- an independent formulation kept as a cross-check. */
 #define TG_TILE_ROWS (-1)
 /* tg_env_playout: OR into a tile width of 4, 8 or 16 to run the tiles that share a warp in lock step (warp-uniform control
  * flow: one warp never executes two games' branches one after the other) */
