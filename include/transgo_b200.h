@@ -253,6 +253,9 @@ int tg_dirichlet(double* noise, const int32_t* root_k, int64_t G, int A, double 
  * i.e. a residual junction of model.py:208-262 / :286-314 with the next eval-mode BatchNorm folded to scale/shift (f32). */
 int tg_net_add_bn_relu(const void* x, const void* y, float alpha, const float* ybias, const float* scale, const float* shift,
                        void* sum_out, void* act_out, int64_t rows, int channels, void* stream);
+/* diagnostics: 1 walks the junction's tensors back to front (the tail of y is what L2 may still hold), 0 (default) front to back;
+ * returns the previous setting */
+int tg_net_debug_reverse(int on);
 
 
 /* Fused single-head spatial self-attention block of model.py:286-314 in inference, NHWC bf16:

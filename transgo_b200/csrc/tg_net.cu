@@ -58,11 +58,14 @@ __device__ __forceinline__ void junction8(const uint4& xq, const uint4& yq, bool
 // Two 128-bit vectors per thread and iteration, all four loads issued before the first use (more bytes in flight per thread).
 __global__ void __launch_bounds__(256)
 k_add_bn_relu(const uint4* __restrict__ x, const uint4* __restrict__ y, float alpha, const float* __restrict__ ybias, const float* __restrict__ scale,
-              const float* __restrict__ shift, uint4* __restrict__ sum_out, uint4* __restrict__ act_out, long long n_vec, int cvec) {
+              const float* __restrict__ shift, uint4* __restrict__ sum_out, uint4* __restrict__ act_out, long long n_vec, int cvec, int reverse) {
     const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_vec; i += 2 * stride) {
-        const long long i2 = i + stride;
-        const bool two = i2 < n_vec;
+    // reverse: walk the tensors from the END.  y was written front to back by the kernel before this one, so its tail is what the
+    // 126 MB L2 still holds; reading it first turns those reads into L2 hits instead of evicting them before they are reached.
+    for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < n_vec; j += 2 * stride) {
+        const long long j2 = j + stride;
+        const bool two = j2 < n_vec;
+        const long long i = reverse ? n_vec - 1 - j : j, i2 = reverse ? n_vec - 1 - j2 : j2;
         const uint4 z = make_uint4(0, 0, 0, 0);
         const uint4 x0 = x[i], x1 = two ? x[i2] : z;
         const uint4 y0 = y ? y[i] : z, y1 = (y && two) ? y[i2] : z;
@@ -73,6 +76,9 @@ k_add_bn_relu(const uint4* __restrict__ x, const uint4* __restrict__ y, float al
 
 }  // namespace tg
 
+static int g_net_reverse = 0;
+extern "C" int tg_net_debug_reverse(int on) { const int old = g_net_reverse; g_net_reverse = on; return old; }
+
 extern "C" int tg_net_add_bn_relu(const void* x, const void* y, float alpha, const float* ybias, const float* scale, const float* shift,
                                    void* sum_out, void* act_out, int64_t rows, int channels, void* stream) {
     using namespace tg;
@@ -82,7 +88,7 @@ extern "C" int tg_net_add_bn_relu(const void* x, const void* y, float alpha, con
     long long blocks = (n_vec + 255) / 256;
     if (blocks > 148LL * 32) blocks = 148LL * 32;          // grid-stride over a multiple of the SM count
     k_add_bn_relu<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const uint4*)x, (const uint4*)y, alpha, ybias, scale, shift,
-                                                                         (uint4*)sum_out, (uint4*)act_out, n_vec, channels / 8);
+                                                                         (uint4*)sum_out, (uint4*)act_out, n_vec, channels / 8, g_net_reverse);
     return set_err((int)cudaGetLastError(), "tg_net_add_bn_relu");
 }
 
