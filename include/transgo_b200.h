@@ -195,6 +195,9 @@ int tg_mcts_debug_sequential_select(int on);
 /* diagnostics: device buffer of 4 x u64 per game (start, selection done, end in globaltimer ns; deepest path) written by every
  * pipelined selection launch; NULL stops the recording */
 int tg_mcts_debug_times(unsigned long long* times);
+/* diagnostics: 1 / 0 (default) = speculative L2 prefetch of the most-visited child's edge records during selection (never changes
+ * a result) */
+int tg_mcts_debug_prefetch(int on);
 
 /* wave, second half: policy float32 [G*readouts][A] (softmaxed, model.py:111), value float32 [G*readouts];
  * pending (may be NULL; prefer tg_mcts_pending) is INCREMENTED by the number of active games still below N0 + num_simulation */

@@ -423,6 +423,8 @@ __global__ void __launch_bounds__(kThreads) k_select(View v) {
 // kernel takes two rounds: 8 CTAs of 4 warps per SM (<= 64 registers) hold 1184 games of 9x9, 4 per SM 592 games of 19x19.
 // FUSE: the leaves (step + legal mask + feature planes) follow in the same launch.  Off at 19x19, where the leaf code's register
 // needs (ten 7-word bitboards) would spill inside the residency bound above.
+__device__ int g_prefetch_guess = 0;      // tg_mcts_debug_prefetch: speculative prefetch of the most-visited child's edges (results unaffected)
+
 // diagnostics (tg_mcts_debug_times): when set, every game's CTA of k_select_par records globaltimer at its start, after the
 // selection pipeline and at its end, plus its deepest path, as 4 x u64 per game
 __device__ unsigned long long* d_dbg_times = nullptr;
@@ -476,6 +478,29 @@ __global__ void __launch_bounds__(32 * kParWarps, N == 9 ? 8 : 4) k_select_par(V
         // about how far a long descent j-2 has come
         for (int jp = 0; jp < j; ++jp) { while (vprog[jp] <= L) __nanosleep(40); }
         __syncwarp();
+        // speculation: the most-visited child is the likely pick.  Pull ITS edge records towards L2 while the scores are worked
+        // out (a pick is ~1 us, the round trip it hides ~0.5 us); a wrong guess costs a few idle prefetches, never a result.
+        if (g_prefetch_guess) {
+            unsigned key = 0;
+#pragma unroll
+            for (int r = 0; r < MAXR; ++r) {
+                const int k = lane + 32 * r;
+                const unsigned kk = k < K && sr.ch[r] != kNoChild ? (((unsigned)pk_n(sr.q[r].w) << 12) | ((unsigned)r << 5) | (unsigned)lane) + 1u : 0u;
+                key = kk > key ? kk : key;
+            }
+            key = __reduce_max_sync(0xffffffffu, key);
+            if (key) {
+                const int rs = (int)(((key - 1u) >> 5) & 127u), ls = (int)((key - 1u) & 31u);
+                uint32_t kdg = 0;
+#pragma unroll
+                for (int r = 0; r < MAXR; ++r) { const uint32_t t = __shfl_sync(0xffffffffu, sr.kd[r], ls); kdg = r == rs ? t : kdg; }
+                const int ebg = (int)(kdg & 0x3fffffu), Kg = (int)(kdg >> 22);
+                const char* ph = reinterpret_cast<const char*>(hot + ebg);
+                const char* pk = reinterpret_cast<const char*>(kid + ebg);
+                if (lane * 128 < Kg * 16) asm volatile("prefetch.global.L2 [%0];" :: "l"(ph + lane * 128));
+                if (lane * 128 < Kg * 8) asm volatile("prefetch.global.L2 [%0];" :: "l"(pk + lane * 128));
+            }
+        }
         // virtual loss of the earlier descents that stand on this node at this level
         int same = 0, xo[MAXR];
 #pragma unroll
@@ -1279,6 +1304,10 @@ int tg_mcts_pending(const TgMctsConfig* cfg, void* ws, int32_t* out, void* strea
     if (check_cfg(cfg) || !ws || !out) return set_err(-1, "tg_mcts_pending");
     TG_MCTS_N(cfg, { View v = make_view<N>(cfg, ws); k_pending<N><<<1, 256, 0, (cudaStream_t)stream>>>(v, out); });
     return set_err((int)cudaGetLastError(), "tg_mcts_pending");
+}
+
+int tg_mcts_debug_prefetch(int on) {
+    return set_err((int)cudaMemcpyToSymbol(tg::g_prefetch_guess, &on, sizeof(on)), "tg_mcts_debug_prefetch");
 }
 
 int tg_mcts_debug_times(unsigned long long* times /* device, 4 x u64 per game, or NULL to stop */) {
