@@ -122,6 +122,9 @@ int tg_env_playout_scored(int n, void* states, int64_t G, int plies, int max_ste
 
 /* the layout tg_env_playout uses for (n, G, tile): TG_TILE_ROWS or the number of lanes per game (tile = 0: measured choice) */
 int tg_env_playout_tile(int n, int64_t G, int tile);
+/* diagnostics: games per warp of the incremental engine's tiled layouts (0 = fill the warp: 32 / lanes per game); returns the
+ * previous setting */
+int tg_env_debug_games_per_warp(int gw);
 
 /* board.cc:1166-1271: float32[B][C][n][n] -> float32[B][cuts][C][sub][sub] */
 int tg_sub_encode(int n, const float* enc, int64_t B, int channels, int sub, int cuts, float* out, void* stream);

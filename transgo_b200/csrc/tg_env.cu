@@ -205,10 +205,14 @@ template <int N, int T, bool NOEYE>
 __global__ void __launch_bounds__(kThreads)
 k_playout_inc(uint4* __restrict__ states, long long G, int plies, int max_step, unsigned long long seed, long long game_id0,
               int16_t* __restrict__ trace, unsigned long long* __restrict__ plies_done, int from_reset, float* __restrict__ score_out,
-              float komi) {
+              float komi, int gw) {
     using namespace inc;
-    const long long g = (blockIdx.x * (long long)blockDim.x + threadIdx.x) / T;
-    const bool exists = g < G;
+    // gw = games per warp (T > 1): 32 / T fills the warp; fewer leave the upper tiles empty (they idle through the lock-step votes
+    // without prolonging them), which trades lanes for a shorter slowest-of-the-warp flood and more warps per scheduler
+    const long long gt = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const int slot = (int)(threadIdx.x & 31) / T;
+    const long long g = T == 1 ? gt : (gt >> 5) * gw + slot;
+    const bool exists = g < G && (T == 1 || slot < gw);
     if (T > 1 ? !__any_sync(0xffffffffu, exists) : !exists) return;
     const int j = (int)(threadIdx.x & (T - 1));
     const bool lead = j == 0;
@@ -415,15 +419,19 @@ template <int N, int TC> void launch_playout(cudaStream_t st, uint4* states, lon
         k_playout<N, T><<<blocks_for(G, T), kThreads, 0, st>>>(states, G, plies, max_step, seed, game_id0, no_eye, trace, plies_done);
 }
 
+static int g_playout_games_per_warp = 0;     // tg_env_debug_games_per_warp: 0 = fill the warp
+
 template <int N, int T> int launch_playout_inc(cudaStream_t st, uint4* states, long long G, int plies, int max_step, unsigned long long seed,
                                                 long long game_id0, int no_eye, int16_t* trace, unsigned long long* plies_done,
                                                 int from_reset = 0, float* score_out = nullptr, float komi = 0.0f) {
     // a playout CTA lives for the whole game: with few warps per SM one-warp CTAs spread them evenly over the 148 SMs
-    const long long warps = (G * T + 31) / 32;
+    int gw = 32 / T;
+    if (T > 1 && g_playout_games_per_warp > 0 && g_playout_games_per_warp < gw) gw = g_playout_games_per_warp;
+    const long long warps = T == 1 ? (G + 31) / 32 : (G + gw - 1) / gw;
     const int threads = warps < 148LL * 16 ? 32 : kThreads;
-    const unsigned blocks = (unsigned)((G * T + threads - 1) / threads);
-    if (no_eye) k_playout_inc<N, T, true><<<blocks, threads, 0, st>>>(states, G, plies, max_step, seed, game_id0, trace, plies_done, from_reset, score_out, komi);
-    else k_playout_inc<N, T, false><<<blocks, threads, 0, st>>>(states, G, plies, max_step, seed, game_id0, trace, plies_done, from_reset, score_out, komi);
+    const unsigned blocks = (unsigned)((warps * 32 + threads - 1) / threads);
+    if (no_eye) k_playout_inc<N, T, true><<<blocks, threads, 0, st>>>(states, G, plies, max_step, seed, game_id0, trace, plies_done, from_reset, score_out, komi, gw);
+    else k_playout_inc<N, T, false><<<blocks, threads, 0, st>>>(states, G, plies, max_step, seed, game_id0, trace, plies_done, from_reset, score_out, komi, gw);
     return 0;
 }
 
@@ -536,6 +544,8 @@ static int playout_impl(int n, void* states, int64_t G, int plies, int max_step,
     else return set_err(-1, "board size must be 9 or 19");
     return set_err((int)cudaGetLastError(), "tg_env_playout");
 }
+
+int tg_env_debug_games_per_warp(int gw) { const int old = g_playout_games_per_warp; g_playout_games_per_warp = gw; return old; }
 
 int tg_env_playout(int n, void* states, int64_t G, int plies, int max_step, uint64_t seed, int64_t game_id0, int no_eye,
                    int16_t* trace_actions, unsigned long long* plies_done, int tile, void* stream) {
