@@ -273,6 +273,12 @@ int tg_net_attention(const void* qkv, const void* x, float gamma, const float* s
                      int64_t B, int P, int dq, int channels, void* stream);
 
 
+/* The head convolutions of the net (model.py:93-94, :105-106): 3x3, 128 -> nout (<= 4) channels, folded BatchNorm, ReLU, 9x9 boards.
+ *   x bf16 [B][81][128]   w bf16 [8][9][128] = [output channel][tap ky * 3 + kx][input channel] (rows >= nout zero)   bias f32 [8]
+ *   out bf16 [B][81][nout] = relu(conv3x3(x) + bias)                                   (one pass over x: mma.sync, csrc/tg_net.cu) */
+int tg_net_conv3x3_head(const void* x, const void* w, const float* bias, void* out, int64_t B, int board, int channels, int nout,
+                        void* stream);
+
 /* The same block INCLUDING the q | k | v projection, as one tcgen05 kernel (csrc/tg_net_tc.cu; 9x9 boards: P <= 96):
  *   x     bf16 [B][P][C]          wqkv bf16 [dq + dq + C][C] (query | key | gamma-scaled value rows, the three 1x1 convolutions
  *   of model.py:290-292 stacked)   bqkv bf16 [dq + dq + C]

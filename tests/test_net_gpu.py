@@ -145,13 +145,37 @@ def test_attention_tcgen05_kernel_agrees_with_the_mma_sync_kernel():
     assert bool((err <= 2e-2 + 2e-2 * out_mma.float().abs()).all()), float(err.max())
 
 
-@pytest.mark.parametrize("attention", ["tcgen05", "mma"])
-def test_fused_forward_matches_fp32_module(attention):
+@pytest.mark.parametrize("B,nout", [(1, 2), (7, 4), (700, 4), (300, 2), (3, 3), (2, 1)])
+def test_head_conv_kernel_matches_fp32_reference(B, nout):
+    """tg_net_conv3x3_head (3x3, 128 -> nout channels, bias, ReLU; zero-bordered frames in shared memory + mma.sync) against
+    torch.nn.functional.conv2d in fp32 on the same bf16 operands.  Tolerance |d| <= 1e-2 + 1e-2 |ref| (fp32 accumulation of 1152
+    bf16 products on both sides; the result is rounded to bf16)."""
+    from transgo_b200 import _lib
+    L = _lib.lib()
+    g = torch.Generator(device="cuda"); g.manual_seed(10 * B + nout)
+    x = torch.randn([B, 81, 128], device="cuda", generator=g).to(torch.bfloat16)
+    w = (torch.randn([nout, 128, 3, 3], device="cuda", generator=g) * 0.05).to(torch.bfloat16)
+    bias = torch.randn([nout], device="cuda", generator=g) * 0.3
+    w8 = torch.zeros([8, 9, 128], dtype=torch.bfloat16, device="cuda"); w8[:nout] = w.permute(0, 2, 3, 1).reshape(nout, 9, 128)
+    b8 = torch.zeros([8], dtype=torch.float32, device="cuda"); b8[:nout] = bias
+    out = torch.full([B, 81, nout], float("nan"), dtype=torch.bfloat16, device="cuda")
+    _lib.check(L.tg_net_conv3x3_head(_lib.ptr(x), _lib.ptr(w8), _lib.ptr(b8), _lib.ptr(out), B, 9, 128, nout, _lib.stream_ptr()), "tg_net_conv3x3_head")
+    xi = x.float().reshape(B, 9, 9, 128).permute(0, 3, 1, 2)
+    ref = torch.relu(torch.nn.functional.conv2d(xi, w.float(), bias, padding=1)).permute(0, 2, 3, 1).reshape(B, 81, nout)
+    assert not torch.isnan(out.float()).any()
+    err = (out.float() - ref).abs()
+    assert bool((err <= 1e-2 + 1e-2 * ref.abs()).all()), float(err.max())
+    assert L.tg_net_conv3x3_head(_lib.ptr(x), _lib.ptr(w8), _lib.ptr(b8), _lib.ptr(out), B, 19, 128, nout, _lib.stream_ptr()) != 0
+    assert L.tg_net_conv3x3_head(_lib.ptr(x), _lib.ptr(w8), _lib.ptr(b8), _lib.ptr(out), B, 9, 128, 5, _lib.stream_ptr()) != 0
+
+
+@pytest.mark.parametrize("attention,head_conv", [("tcgen05", "mma"), ("mma", "library"), ("tcgen05", "library")])
+def test_fused_forward_matches_fp32_module(attention, head_conv):
     """Tolerance: policy max |dp| <= 4e-3 (probabilities), value / ownership max |dv| <= 4e-2 -- bf16 activations through
     26 convolution layers; argmax of the policy must agree wherever the fp32 margin exceeds the tolerance."""
     from transgo_b200.fused_net import FusedTransGoInference
     m = _perturbed_model()
-    fused = FusedTransGoInference(m, attention=attention)
+    fused = FusedTransGoInference(m, attention=attention, head_conv=head_conv)
     g = torch.Generator(device="cuda"); g.manual_seed(3)
     obs = (torch.rand([257, 10, 9, 9], device="cuda", generator=g) > 0.75).float()
     with torch.no_grad():

@@ -463,6 +463,128 @@ k_attention_big(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __re
 
 }  // namespace tg
 
+// ------------------------------------------------------------------------------------------------------------------
+// The two head convolutions of the net (model.py:93-94, :105-106: 3x3, 128 -> 2 / 4 channels, BatchNorm folded, ReLU).  A library
+// implicit GEMM pads the 2 / 4 output channels to a 64-wide tile and takes 87 us for 4096 positions; the work is one pass over x
+// (85 MB).  Here a position's [81][128] bf16 tile is copied by cp.async into a zero-bordered 11x11 FRAME in shared memory (two
+// buffers: the next position loads while this one is multiplied) and the nine taps become extra OUTPUT COLUMNS of one plain GEMM:
+//     Y[f][tap * nout + co] = sum_ci frame[f][ci] * w[co][tap][ci]          (mma.sync m16n8k16: M = 128 frame rows, N = 9 nout, K = 128)
+//     out[p][co] = relu(bias[co] + sum_tap Y[f(p) + 11 dy + dx][tap * nout + co])
+// so that every A fragment is loaded once and feeds all N tiles, and the B fragments (the weights) live in registers for the whole
+// launch -- a tap-by-tap formulation re-reads the tile nine times for 8 output columns and is bound by shared-memory bandwidth
+// (75 us measured).  Eight warps, one 16-row M tile each; out bf16 [B][P][nout].
+namespace tg {
+
+constexpr int kHcN = 9, kHcP = 81, kHcF = 11;                             // board, points, frame side (121 frame rows)
+constexpr int kHcRS = kAttC * 2 + 16;                                     // frame row stride (bytes): 4 banks per row
+constexpr int kHcTileRows = 128;                                          // 8 M tiles; rows >= 121 stay zero
+constexpr int kHcTile = kHcTileRows * kHcRS;
+constexpr int kHcWarps = 8;
+template <int NT> __host__ __device__ constexpr int hc_ystride() { return NT * 8 + 1; }       // floats per Y row (+1: the gather walks rows)
+template <int NT> __host__ __device__ constexpr int hc_smem() { return 2 * kHcTile + kHcTileRows * hc_ystride<NT>() * 4; }
+
+template <int NT>                                                         // NT = N tiles of 8 columns: ceil(9 * nout / 8)
+__global__ void __launch_bounds__(kHcWarps * 32, 2)
+k_conv3x3_head(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w, const float* __restrict__ bias,
+               __nv_bfloat16* __restrict__ out, int B, int nout) {
+    extern __shared__ __align__(16) unsigned char hc_smem_raw[];
+    float* sY = reinterpret_cast<float*>(hc_smem_raw + 2 * kHcTile);
+    constexpr int YS = hc_ystride<NT>();
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, g = lane >> 2, t = lane & 3;
+    // zero both frames once (borders and rows >= 121 stay zero: the copies only ever touch interior rows)
+    for (int i = tid; i < 2 * kHcTile / 16; i += blockDim.x) reinterpret_cast<uint4*>(hc_smem_raw)[i] = make_uint4(0, 0, 0, 0);
+    // B fragments of every (N tile, k step) in registers: column n = tap * nout + co of the GEMM is w[co][tap][:]
+    uint32_t bw[NT][kAttC / 16][2];
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+        const int n = nt * 8 + g;
+        const bool live = n < 9 * nout;
+        const int tap = live ? n / nout : 0, co = live ? n - tap * nout : 0;
+        const uint32_t* wr = reinterpret_cast<const uint32_t*>(w + ((size_t)co * 9 + tap) * kAttC);
+#pragma unroll
+        for (int kc = 0; kc < kAttC / 16; ++kc) {
+            bw[nt][kc][0] = live ? wr[kc * 8 + t] : 0u;
+            bw[nt][kc][1] = live ? wr[kc * 8 + 4 + t] : 0u;
+        }
+    }
+    __syncthreads();
+    auto load_tile = [&](int pos, int buf) {
+        const uint4* src = reinterpret_cast<const uint4*>(x + (size_t)pos * kHcP * kAttC);
+        unsigned char* dst = hc_smem_raw + buf * kHcTile;
+        for (int i = tid; i < kHcP * (kAttC / 8); i += blockDim.x) {
+            const int p = i >> 4, q = i & 15;
+            const int fr = (p / kHcN + 1) * kHcF + (p % kHcN) + 1;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" :: "r"((uint32_t)__cvta_generic_to_shared(dst + fr * kHcRS + q * 16)), "l"(src + i));
+        }
+        asm volatile("cp.async.commit_group;\n" ::);
+    };
+    const int mrow = (lane & 7) + ((lane >> 3) & 1) * 8, mcol = (lane >> 4) * 8;   // ldmatrix.x4 lane -> (row, col) of its 8x8 tile
+    int buf = 0;
+    if ((int)blockIdx.x < B) load_tile(blockIdx.x, 0);
+    for (int pos = blockIdx.x; pos < B; pos += gridDim.x) {
+        const int nxt = pos + gridDim.x;
+        if (nxt < B) load_tile(nxt, buf ^ 1);                                     // (that buffer was fully read an iteration ago)
+        if (nxt < B) asm volatile("cp.async.wait_group 1;\n" ::); else asm volatile("cp.async.wait_group 0;\n" ::);
+        __syncthreads();                                                          // the tile is in; the previous gather is done with sY
+        const unsigned char* arow = hc_smem_raw + buf * kHcTile + (wid * 16 + mrow) * kHcRS + mcol * 2;
+        float acc[NT][4];
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.0f;
+#pragma unroll
+        for (int kc = 0; kc < kAttC / 16; ++kc) {
+            uint32_t a[4];
+            ldsm_x4(a, arow + kc * 32);
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) mma_bf16(acc[nt], a, bw[nt][kc][0], bw[nt][kc][1]);
+        }
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {                                         // rows g, g + 8 of this warp's tile; columns 2t, 2t + 1
+            float* y0 = sY + (wid * 16 + g) * YS + nt * 8 + 2 * t;
+            y0[0] = acc[nt][0]; y0[1] = acc[nt][1];
+            y0[8 * YS] = acc[nt][2]; y0[8 * YS + 1] = acc[nt][3];
+        }
+        __syncthreads();
+        // the nine shifted partial sums of every output
+        __nv_bfloat16* o = out + (size_t)pos * kHcP * nout;
+        for (int i = tid; i < kHcP * nout; i += blockDim.x) {
+            const int p = i / nout, co = i - p * nout;
+            const int fr = (p / kHcN + 1) * kHcF + (p % kHcN) + 1;
+            float v = bias[co];
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) v += sY[(fr + (tap / 3 - 1) * kHcF + (tap % 3 - 1)) * YS + tap * nout + co];
+            o[i] = __float2bfloat16(fmaxf(v, 0.0f));
+        }
+        buf ^= 1;
+    }
+}
+
+}  // namespace tg
+
+extern "C" int tg_net_conv3x3_head(const void* x, const void* w, const float* bias, void* out, int64_t B, int board, int channels, int nout,
+                                    void* stream) {
+    using namespace tg;
+    if (!x || !w || !bias || !out || B <= 0 || board != kHcN || channels != kAttC || nout < 1 || nout > 4)
+        return set_err(-1, "tg_net_conv3x3_head (supports 9x9 boards, 128 input channels, 1..4 output channels)");
+    static unsigned long long attr_done = 0;                 // one bit per device
+    int dev = 0; cudaGetDevice(&dev);
+    if (!((attr_done >> (dev & 63)) & 1ull)) {
+        cudaError_t e = cudaFuncSetAttribute(k_conv3x3_head<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, hc_smem<3>());
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_conv3x3_head<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, hc_smem<5>());
+        if (e != cudaSuccess) return set_err((int)e, "tg_net_conv3x3_head (shared memory attribute)");
+        attr_done |= 1ull << (dev & 63);
+    }
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long long grid = B < 2LL * sms ? B : 2LL * sms;
+    if (9 * nout <= 24)
+        k_conv3x3_head<3><<<(unsigned)grid, kHcWarps * 32, hc_smem<3>(), (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)w, bias,
+                                                                                               (__nv_bfloat16*)out, (int)B, nout);
+    else
+        k_conv3x3_head<5><<<(unsigned)grid, kHcWarps * 32, hc_smem<5>(), (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)w, bias,
+                                                                                               (__nv_bfloat16*)out, (int)B, nout);
+    return set_err((int)cudaGetLastError(), "tg_net_conv3x3_head");
+}
+
 extern "C" int tg_net_attention(const void* qkv, const void* x, float gamma, const float* scale, const float* shift, void* out,
                                 int64_t B, int P, int dq, int channels, void* stream) {
     using namespace tg;

@@ -40,6 +40,21 @@ def _conv_bn(conv, bn, dtype, pad_in=None):
     return w.to(dtype).contiguous(memory_format=torch.channels_last), b.to(dtype).contiguous()
 
 
+def _conv_head(conv, bn, dtype):
+    """a head convolution (3x3, few output channels) + BatchNorm for tg_net_conv3x3_head: (weight [8, 9, I] = [output channel,
+    tap ky * 3 + kx, input channel] in `dtype`, rows beyond the real output channels zero; bias float32 [8]; channel count)"""
+    w, b = conv.weight.detach().float(), conv.bias.detach().float()
+    s, t = _fold(bn)
+    w = w * s[:, None, None, None]
+    b = b * s + t
+    O, I = w.shape[0], w.shape[1]
+    w8 = torch.zeros([8, 9, I], dtype=torch.float32, device=w.device)
+    w8[:O] = w.permute(0, 2, 3, 1).reshape(O, 9, I)
+    b8 = torch.zeros([8], dtype=torch.float32, device=w.device)
+    b8[:O] = b
+    return w8.to(dtype).contiguous(), b8.contiguous()
+
+
 def _copy_tree(old, new):
     """copy every tensor of the nested structure `new` into the same place of `old` (same layout by construction)"""
     if isinstance(old, torch.Tensor):
@@ -53,10 +68,10 @@ def _copy_tree(old, new):
 
 
 class FusedTransGoInference:
-    def __init__(self, model, dtype=torch.bfloat16, attention="tcgen05"):
+    def __init__(self, model, dtype=torch.bfloat16, attention="tcgen05", head_conv="mma"):
         """attention: "tcgen05" (default: the one-kernel block wherever it applies) or "mma" (GEMM + tg_net_attention everywhere;
-        kept as the cross-check and for timing comparisons)"""
-        self.model, self.dtype, self.attention = model, dtype, attention
+        kept as the cross-check and for timing comparisons).  head_conv: "mma" (default: tg_net_conv3x3_head on 9x9) or "library"."""
+        self.model, self.dtype, self.attention, self.head_conv = model, dtype, attention, head_conv
         self.lib = _lib.lib()
         self._w = None
         self.refresh()
@@ -103,6 +118,8 @@ class FusedTransGoInference:
         vc = _conv_bn(m.conv_val_own.conv[0], m.conv_val_own.conv[1], dt)
         w["val_conv"] = (F.pad(vc[0], (0, 0, 0, 0, 0, 0, 0, 6)).contiguous(memory_format=torch.channels_last),
                          F.pad(vc[1], (0, 6)))                                  # 2 -> 8 output channels (tensor-core friendly)
+        w["val_head"] = _conv_head(m.conv_val_own.conv[0], m.conv_val_own.conv[1], dt)       # the same two convolutions packed for
+        w["act_head"] = _conv_head(m.conv_act.conv[0], m.conv_act.conv[1], dt)               # tg_net_conv3x3_head (9x9 boards)
         w["fc_val_own"] = nhwc_fc(m.fc_val_own, 2)
         w["fc_val"] = (m.fc_val.weight.detach().to(dt).contiguous(), m.fc_val.bias.detach().to(dt).contiguous())
         w["fc_own"] = (m.fc_own.weight.detach().to(dt).contiguous(), m.fc_own.bias.detach().to(dt).contiguous())
@@ -162,6 +179,17 @@ class FusedTransGoInference:
         _, act = self._junction(x, o, p["gamma"], p["s"], p["t"], False, True)
         return act
 
+    def _head_conv(self, x, packed, lib_w, nout):
+        """relu(bn(conv3x3(x))) with `nout` output channels, flattened per position in (point, channel) order: [B, P * nout]"""
+        B = x.shape[0]
+        if self.head_conv == "mma" and self.n == 9 and x.shape[1] == 128 and self.dtype == torch.bfloat16:
+            out = torch.empty([B, self.P * nout], dtype=self.dtype, device=x.device)
+            _lib.check(self.lib.tg_net_conv3x3_head(_lib.ptr(x), _lib.ptr(packed[0]), _lib.ptr(packed[1]), _lib.ptr(out), B, self.n, 128, nout,
+                                                    _lib.stream_ptr(device=x.device)), "tg_net_conv3x3_head")
+            return out
+        h = torch.cudnn_convolution_relu(x, lib_w[0], lib_w[1], [1, 1], [1, 1], [1, 1], 1)[:, :nout]
+        return h.permute(0, 2, 3, 1).reshape(B, self.P * nout)
+
     # ------------------------------------------------------------------ forward
     @torch.no_grad()
     def __call__(self, obs):
@@ -194,25 +222,23 @@ class FusedTransGoInference:
             else:
                 x = self._attention(x, p)
         # value / ownership head (model.py:93-99)
-        hv = conv_relu(x, self.val_conv[0], self.val_conv[1], one, pad, one, 1)[:, :2]
-        hv = hv.permute(0, 2, 3, 1).reshape(B, self.P * 2)
+        hv = self._head_conv(x, self.val_head, self.val_conv, 2)
         hv = F.relu(F.linear(hv, *self.fc_val_own))
         value = torch.tanh(F.linear(hv, *self.fc_val).float()).reshape(-1)
         own = torch.tanh(F.linear(hv, *self.fc_own).float())
         # policy head (model.py:103-111)
         xa = self._attention(x, self.act_attn)
-        ha = conv_relu(xa, self.act_conv[0], self.act_conv[1], one, pad, one, 1)[:, :4]
-        ha = ha.permute(0, 2, 3, 1).reshape(B, self.P * 4)
+        ha = self._head_conv(xa, self.act_head, self.act_conv, 4)
         policy = torch.softmax(F.linear(ha, *self.fc_act).float(), -1)
         return policy, value, own
 
 
-def make_fused_evaluator(model, dtype=torch.bfloat16, cuda_graph=True, attention="tcgen05"):
+def make_fused_evaluator(model, dtype=torch.bfloat16, cuda_graph=True, attention="tcgen05", head_conv="mma"):
     """evaluator(obs) -> (policy, value) for BatchedMCTS, forward captured once per static input tensor as a CUDA graph.
     cuda_graph=False: plain launches (use it when the caller captures a larger graph, e.g. BatchedMCTS(graph_waves=True));
     cuda_graph="roots": plain launches while the current stream is being captured, own graphs otherwise (the search's wave
     batch is captured by the engine, the per-move root batch runs outside it)."""
-    net = FusedTransGoInference(model, dtype, attention=attention)
+    net = FusedTransGoInference(model, dtype, attention=attention, head_conv=head_conv)
     graphs = {}
 
     def evaluator(obs):
