@@ -288,6 +288,11 @@ int tg_net_conv3x3_head(const void* x, const void* w, const float* bias, void* o
  * accumulator tiles of position 0 (projection + bias, scores, o) for stage-by-stage tests.  Returns -1 for unsupported shapes. */
 int tg_net_attention_fused(const void* x, const void* wqkv, const void* bqkv, float gamma, const float* scale, const float* shift,
                            void* out, int64_t B, int P, int dq, int channels, float* debug, void* stream);
+/* ... with a second output out2 = relu(out * scale2[c] + shift2[c]) (out2 may be NULL): the BatchNorm + ReLU that opens the residual
+ * block after the attention block (model.py:216-217), so that no separate pass over `out` is needed */
+int tg_net_attention_fused2(const void* x, const void* wqkv, const void* bqkv, float gamma, const float* scale, const float* shift,
+                            void* out, const float* scale2, const float* shift2, void* out2, int64_t B, int P, int dq, int channels,
+                            float* debug, void* stream);
 
 #ifdef __cplusplus
 }

@@ -128,6 +128,26 @@ def test_attention_tcgen05_kernel_stage_by_stage(B, P):
                                     _lib.ptr(c["shift"]), _lib.ptr(out), B, 97, c["dq"], c["C"], None, _lib.stream_ptr()) != 0
 
 
+def test_attention_tcgen05_second_output_is_the_next_blocks_activation():
+    """tg_net_attention_fused2: out2 = relu(out * scale2 + shift2) computed from the bf16-rounded out -- bit-equal to running the
+    junction kernel (tg_net_add_bn_relu) on out, and out itself unchanged by asking for it."""
+    from transgo_b200 import _lib
+    L = _lib.lib()
+    B, P = 300, 81
+    c = _attention_tc_case(B, P, 4242)
+    g = torch.Generator(device="cuda"); g.manual_seed(9)
+    s2 = torch.rand([128], device="cuda", generator=g) + 0.5
+    t2 = torch.randn([128], device="cuda", generator=g) * 0.3
+    out = torch.empty_like(c["x"]); out2 = torch.full_like(c["x"], float("nan")); out_plain = torch.empty_like(c["x"])
+    _lib.check(L.tg_net_attention_fused2(_lib.ptr(c["x"]), _lib.ptr(c["w"]), _lib.ptr(c["b"]), c["gamma"], _lib.ptr(c["scale"]), _lib.ptr(c["shift"]),
+                                         _lib.ptr(out), _lib.ptr(s2), _lib.ptr(t2), _lib.ptr(out2), B, P, c["dq"], c["C"], None, _lib.stream_ptr()))
+    _lib.check(L.tg_net_attention_fused(_lib.ptr(c["x"]), _lib.ptr(c["w"]), _lib.ptr(c["b"]), c["gamma"], _lib.ptr(c["scale"]), _lib.ptr(c["shift"]),
+                                        _lib.ptr(out_plain), B, P, c["dq"], c["C"], None, _lib.stream_ptr()))
+    ref2 = torch.empty_like(out)
+    _lib.check(L.tg_net_add_bn_relu(_lib.ptr(out), None, 1.0, None, _lib.ptr(s2), _lib.ptr(t2), None, _lib.ptr(ref2), B * P, 128, _lib.stream_ptr()))
+    assert torch.equal(out, out_plain) and torch.equal(out2, ref2)
+
+
 def test_attention_tcgen05_kernel_agrees_with_the_mma_sync_kernel():
     """the tcgen05 block against the round-1 pair (library GEMM + tg_net_attention) on the same inputs: both round q, k, v, p
     and o to bf16 at the same points, so they differ by summation order only (|d| <= 2e-2 + 2e-2 |ref|, in practice bf16 ulps)."""

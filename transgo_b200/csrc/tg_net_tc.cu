@@ -191,8 +191,10 @@ __device__ __forceinline__ void softmax_half(uint32_t tlane, int row, int P, flo
 
 // the junction of one position, coalesced: relu(bn(gamma * o + x)) (model.py:312-313) with o (bf16) from the staging panels;
 // thread -> chunk tid & 15 of rows (tid >> 4) + 16 it
+// og2 (may be null): a second output relu(out * scale2 + shift2) -- the BatchNorm + ReLU that opens the NEXT residual block
+// (model.py:216-217), applied to the bf16-rounded out like the separate junction kernel would; its scale / shift come from shared memory
 __device__ __forceinline__ void junction_pass(const unsigned char* __restrict__ smem, const uint4* xj, uint4* __restrict__ og, int tile_chunks,
-                                              int tid, float gamma, const float* sc, const float* sh) {
+                                              int tid, float gamma, const float* sc, const float* sh, uint4* __restrict__ og2) {
 #pragma unroll
     for (int it = 0; it < 6; ++it) {
         const int idx = tid + kTcThreads * it;
@@ -207,6 +209,23 @@ __device__ __forceinline__ void junction_pass(const unsigned char* __restrict__ 
                 res[k] = pack_bf16(fmaxf(fmaf(s0, sc[2 * k], sh[2 * k]), 0.0f), fmaxf(fmaf(s1, sc[2 * k + 1], sh[2 * k + 1]), 0.0f));
             }
             og[idx] = make_uint4(res[0], res[1], res[2], res[3]);
+            if (og2) {
+                const float* s2 = reinterpret_cast<const float*>(smem + OFF_SCALE) + (tid & 15) * 8;
+                const float* t2 = reinterpret_cast<const float*>(smem + OFF_SHIFT) + (tid & 15) * 8;
+                const float4 sa = *reinterpret_cast<const float4*>(s2), sb = *reinterpret_cast<const float4*>(s2 + 4);
+                const float4 ta = *reinterpret_cast<const float4*>(t2), tb = *reinterpret_cast<const float4*>(t2 + 4);
+                const float s2v[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w}, t2v[8] = {ta.x, ta.y, ta.z, ta.w, tb.x, tb.y, tb.z, tb.w};
+                uint32_t r2[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float2 of = unpack_bf16(res[k]);
+                    // multiply and add rounded separately, exactly like tg_net_add_bn_relu (its file is built with -fmad=false): the fused
+                    // and the two-kernel route give the same bits
+                    r2[k] = pack_bf16(fmaxf(__fadd_rn(__fmul_rn(of.x, s2v[2 * k]), t2v[2 * k]), 0.0f),
+                                      fmaxf(__fadd_rn(__fmul_rn(of.y, s2v[2 * k + 1]), t2v[2 * k + 1]), 0.0f));
+                }
+                og2[idx] = make_uint4(r2[0], r2[1], r2[2], r2[3]);
+            }
         }
     }
 }
@@ -217,7 +236,8 @@ template <int PC>
 __global__ void __launch_bounds__(kTcThreads, 2)
 k_attention_tc(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w, const __nv_bfloat16* __restrict__ bias,
                float gamma, const float* __restrict__ scale, const float* __restrict__ shift, __nv_bfloat16* __restrict__ out,
-               int B, int Prt, float* __restrict__ dbg) {
+               int B, int Prt, float* __restrict__ dbg, const float* __restrict__ scale2, const float* __restrict__ shift2,
+               __nv_bfloat16* __restrict__ out2) {
     const int P = PC ? PC : Prt;
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint32_t s_tmem;
@@ -252,6 +272,12 @@ k_attention_tc(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restr
         }
     }
     for (int n = tid; n < kNqkv; n += kTcThreads) s_bias[n < 2 * kDq ? n + kC : n - 2 * kDq] = __bfloat162float(bias[n]);
+    if (out2) {
+        for (int c = tid; c < kC; c += kTcThreads) {
+            reinterpret_cast<float*>(smem + OFF_SCALE)[c] = scale2[c];
+            reinterpret_cast<float*>(smem + OFF_SHIFT)[c] = shift2[c];
+        }
+    }
     // the junction pass gives a thread the same 8 channels of every row it touches: their scale / shift live in registers
     float sc[8], sh[8];
 #pragma unroll
@@ -268,6 +294,7 @@ k_attention_tc(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restr
 
     uint4 xj[6];                                                      // x chunks of the pending junction pass
     uint4* og_prev = nullptr;                                         // where the pending junction pass writes (null: none pending)
+    uint4* og2_prev = nullptr;
     for (int pos = blockIdx.x; pos < B; pos += gridDim.x) {
         const bool dump = dbg != nullptr && pos == 0;
         // ---- 1. the x tile (rows >= P zero) from the registers that were filled during the previous position
@@ -288,7 +315,7 @@ k_attention_tc(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restr
         }
         // ---- 4b (of the PREVIOUS position). its junction pass runs while the tensor core projects this one; the barrier above
         // also published its O staging panels
-        if (og_prev) junction_pass(smem, xj, og_prev, tile_chunks, tid, gamma, sc, sh);
+        if (og_prev) junction_pass(smem, xj, og_prev, tile_chunks, tid, gamma, sc, sh, og2_prev);
         mbar_wait(bar, phase); phase ^= 1;
         tc_after_sync();
         // ---- 2a. q (h = 0) / k (h = 1) of this row: + bias, bf16, K-major panels over the dead x tile; then the score MMA at once
@@ -364,10 +391,11 @@ k_attention_tc(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restr
         }
         tc_before_sync();                         // these tcgen05.ld precede the next position's MMAs into the same columns
         og_prev = reinterpret_cast<uint4*>(out + (size_t)pos * P * kC);
+        og2_prev = out2 ? reinterpret_cast<uint4*>(out2 + (size_t)pos * P * kC) : nullptr;
         // (the staging panels are read after the next barrier; the next v panels are written two barriers after that)
     }
     __syncthreads();
-    if (og_prev) junction_pass(smem, xj, og_prev, tile_chunks, tid, gamma, sc, sh);
+    if (og_prev) junction_pass(smem, xj, og_prev, tile_chunks, tid, gamma, sc, sh, og2_prev);
     tc_before_sync();
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(kTmemCols) : "memory");
@@ -376,11 +404,13 @@ k_attention_tc(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restr
 }  // namespace tc
 }  // namespace tg
 
-extern "C" int tg_net_attention_fused(const void* x, const void* wqkv, const void* bqkv, float gamma, const float* scale, const float* shift,
-                                      void* out, int64_t B, int P, int dq, int channels, float* debug, void* stream) {
+extern "C" int tg_net_attention_fused2(const void* x, const void* wqkv, const void* bqkv, float gamma, const float* scale, const float* shift,
+                                       void* out, const float* scale2, const float* shift2, void* out2, int64_t B, int P, int dq, int channels,
+                                       float* debug, void* stream) {
     using namespace tg;
     using namespace tg::tc;
-    if (!x || !wqkv || !bqkv || !scale || !shift || !out || B <= 0 || P <= 0 || P > kPts || dq != kDq || channels != kC)
+    if (!x || !wqkv || !bqkv || !scale || !shift || !out || B <= 0 || P <= 0 || P > kPts || dq != kDq || channels != kC ||
+        (out2 && (!scale2 || !shift2)))
         return set_err(-1, "tg_net_attention_fused (supports P <= 96, 32 query channels, 128 value channels)");
     static unsigned long long attr_done = 0;                 // one bit per device
     int dev = 0; cudaGetDevice(&dev);
@@ -395,6 +425,12 @@ extern "C" int tg_net_attention_fused(const void* x, const void* wqkv, const voi
     const long long grid = B < 2LL * sms ? B : 2LL * sms;    // persistent: two CTAs per SM, each walks positions blockIdx, + grid, ...
     auto kern = P == 81 ? k_attention_tc<81> : k_attention_tc<0>;
     kern<<<(unsigned)grid, kTcThreads, SMEM_BYTES, (cudaStream_t)stream>>>(
-        (const __nv_bfloat16*)x, (const __nv_bfloat16*)wqkv, (const __nv_bfloat16*)bqkv, gamma, scale, shift, (__nv_bfloat16*)out, (int)B, P, debug);
+        (const __nv_bfloat16*)x, (const __nv_bfloat16*)wqkv, (const __nv_bfloat16*)bqkv, gamma, scale, shift, (__nv_bfloat16*)out, (int)B, P, debug,
+        scale2, shift2, (__nv_bfloat16*)out2);
     return set_err((int)cudaGetLastError(), "tg_net_attention_fused");
+}
+
+extern "C" int tg_net_attention_fused(const void* x, const void* wqkv, const void* bqkv, float gamma, const float* scale, const float* shift,
+                                      void* out, int64_t B, int P, int dq, int channels, float* debug, void* stream) {
+    return tg_net_attention_fused2(x, wqkv, bqkv, gamma, scale, shift, out, nullptr, nullptr, nullptr, B, P, dq, channels, debug, stream);
 }

@@ -153,17 +153,21 @@ class FusedTransGoInference:
                    "tg_net_add_bn_relu")
         return s_out, a_out
 
-    def _attention(self, x, p):
-        """model.py:299-314 on an NHWC tensor: returns relu(bn(gamma * (V . softmax(Q^T K)) + x))"""
+    def _attention(self, x, p, nxt=None):
+        """model.py:299-314 on an NHWC tensor: returns relu(bn(gamma * (V . softmax(Q^T K)) + x)) and, when the next block is a
+        residual block (nxt = its folded first BatchNorm (scale, shift)) and the one-kernel path runs, that block's opening
+        activation relu(bn1(out)) as a second output (None otherwise: the caller then runs the junction kernel)"""
         B, C = x.shape[0], x.shape[1]
         dq = p["dq"]
         if self.attention == "tcgen05" and self.P <= 96 and dq == 32 and C == 128 and self.dtype == torch.bfloat16:
             # projection, scores, softmax, att^T . v and the junction in ONE tcgen05 kernel (csrc/tg_net_tc.cu: k_attention_tc)
             act = torch.empty_like(x)
-            _lib.check(self.lib.tg_net_attention_fused(_lib.ptr(x), _lib.ptr(p["w"]), _lib.ptr(p["b"]), p["gamma"], _lib.ptr(p["s"]),
-                                                       _lib.ptr(p["t"]), _lib.ptr(act), B, self.P, dq, C, None,
-                                                       _lib.stream_ptr(device=x.device)), "tg_net_attention_fused")
-            return act
+            act2 = torch.empty_like(x) if nxt is not None else None
+            _lib.check(self.lib.tg_net_attention_fused2(_lib.ptr(x), _lib.ptr(p["w"]), _lib.ptr(p["b"]), p["gamma"], _lib.ptr(p["s"]),
+                                                        _lib.ptr(p["t"]), _lib.ptr(act), _lib.ptr(nxt[0]) if nxt else None,
+                                                        _lib.ptr(nxt[1]) if nxt else None, _lib.ptr(act2), B, self.P, dq, C, None,
+                                                        _lib.stream_ptr(device=x.device)), "tg_net_attention_fused")
+            return act, act2
         x2 = x.permute(0, 2, 3, 1).reshape(B, self.P, C)                       # free view of channels_last memory
         qkv = F.linear(x2, p["w"], p["b"])
         if self.P <= 368 and dq == 32 and C == 128 and self.dtype == torch.bfloat16:
@@ -171,13 +175,13 @@ class FusedTransGoInference:
             act = torch.empty_like(x)
             _lib.check(self.lib.tg_net_attention(_lib.ptr(qkv), _lib.ptr(x), p["gamma"], _lib.ptr(p["s"]), _lib.ptr(p["t"]),
                                                  _lib.ptr(act), B, self.P, dq, C, _lib.stream_ptr(device=x.device)), "tg_net_attention")
-            return act
+            return act, None
         q, k, v = qkv[..., :dq], qkv[..., dq:2 * dq], qkv[..., 2 * dq:]
         att = torch.softmax(torch.bmm(q, k.transpose(1, 2)), dim=-1)           # [B, P, P], rows = query position
         o = torch.bmm(att.transpose(1, 2), v)                                  # out[:, j] = sum_i att[i, j] * v[i]
         o = o.reshape(B, self.n, self.n, C).permute(0, 3, 1, 2)                # NHWC memory, NCHW view
         _, act = self._junction(x, o, p["gamma"], p["s"], p["t"], False, True)
-        return act
+        return act, None
 
     def _head_conv(self, x, packed, lib_w, nout):
         """relu(bn(conv3x3(x))) with `nout` output channels, flattened per position in (point, channel) order: [B, P * nout]"""
@@ -220,14 +224,15 @@ class FusedTransGoInference:
                 else:
                     x = self._junction(x, y, 1.0, None, None, True, False, b2)[0]
             else:
-                x = self._attention(x, p)
+                nxt = self.blocks[i + 1] if i + 1 < nb else None
+                x, pending = self._attention(x, p, (nxt[1]["s1"], nxt[1]["t1"]) if nxt is not None and nxt[0] == "R" else None)
         # value / ownership head (model.py:93-99)
         hv = self._head_conv(x, self.val_head, self.val_conv, 2)
         hv = F.relu(F.linear(hv, *self.fc_val_own))
         value = torch.tanh(F.linear(hv, *self.fc_val).float()).reshape(-1)
         own = torch.tanh(F.linear(hv, *self.fc_own).float())
         # policy head (model.py:103-111)
-        xa = self._attention(x, self.act_attn)
+        xa, _ = self._attention(x, self.act_attn)
         ha = self._head_conv(xa, self.act_head, self.act_conv, 4)
         policy = torch.softmax(F.linear(ha, *self.fc_act).float(), -1)
         return policy, value, own
