@@ -273,6 +273,13 @@ int tg_net_attention(const void* qkv, const void* x, float gamma, const float* s
                      int64_t B, int P, int dq, int channels, void* stream);
 
 
+/* The stem of the net (model.py:43, :81): 3x3 convolution from the feature planes to 128 channels, folded BatchNorm, ReLU, 9x9 boards.
+ *   obs float32 [B][cin][81] (the planes as the leaf kernels write them, cin <= 12)    w bf16 [128][9][16] = [output channel][tap][input
+ *   channel, zero beyond cin]    bias f32 [128]    out bf16 [B][81][128] (NHWC) = relu(conv3x3(obs) + bias)
+ *   out2 (may be NULL) = relu(out * scale2[c] + shift2[c]): the opening activation of the first residual block (model.py:216-217) */
+int tg_net_stem(const float* obs, int cin, const void* w, const float* bias, const float* scale2, const float* shift2, void* out, void* out2,
+                int64_t B, int board, int channels, void* stream);
+
 /* The head convolutions of the net (model.py:93-94, :105-106): 3x3, 128 -> nout (<= 4) channels, folded BatchNorm, ReLU, 9x9 boards.
  *   x bf16 [B][81][128]   w bf16 [8][9][128] = [output channel][tap ky * 3 + kx][input channel] (rows >= nout zero)   bias f32 [8]
  *   out bf16 [B][81][nout] = relu(conv3x3(x) + bias)                                   (one pass over x: mma.sync, csrc/tg_net.cu) */

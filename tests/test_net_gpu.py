@@ -165,6 +165,35 @@ def test_attention_tcgen05_kernel_agrees_with_the_mma_sync_kernel():
     assert bool((err <= 2e-2 + 2e-2 * out_mma.float().abs()).all()), float(err.max())
 
 
+@pytest.mark.parametrize("B,with_second", [(1, True), (9, False), (700, True)])
+def test_stem_kernel_matches_fp32_reference(B, with_second):
+    """tg_net_stem (planes float32 [B,10,81] -> relu(conv3x3 + bias) NHWC bf16, optional second output relu(out * s2 + t2)) against
+    conv2d in fp32 on the same bf16-rounded operands.  Tolerance |d| <= 1e-2 + 1e-2 |ref|; the second output is bit-equal to
+    the junction kernel applied to the first."""
+    from transgo_b200 import _lib
+    L = _lib.lib()
+    g = torch.Generator(device="cuda"); g.manual_seed(31 * B)
+    obs = (torch.rand([B, 10, 9, 9], device="cuda", generator=g) > 0.6).float()
+    obs[:, 3] = torch.rand([B, 9, 9], device="cuda", generator=g)                  # not only 0 / 1 inputs
+    w = (torch.randn([128, 10, 3, 3], device="cuda", generator=g) * 0.2).to(torch.bfloat16)
+    bias = torch.randn([128], device="cuda", generator=g) * 0.3
+    s2 = torch.rand([128], device="cuda", generator=g) + 0.5
+    t2 = torch.randn([128], device="cuda", generator=g) * 0.3
+    wk = torch.nn.functional.pad(w.permute(0, 2, 3, 1).reshape(128, 9, 10), (0, 6)).contiguous()
+    out = torch.full([B, 81, 128], float("nan"), dtype=torch.bfloat16, device="cuda")
+    out2 = torch.full_like(out, float("nan")) if with_second else None
+    _lib.check(L.tg_net_stem(_lib.ptr(obs), 10, _lib.ptr(wk), _lib.ptr(bias), _lib.ptr(s2) if with_second else None, _lib.ptr(t2) if with_second else None,
+                             _lib.ptr(out), _lib.ptr(out2), B, 9, 128, _lib.stream_ptr()), "tg_net_stem")
+    ref = torch.relu(torch.nn.functional.conv2d(obs.to(torch.bfloat16).float(), w.float(), bias, padding=1)).permute(0, 2, 3, 1).reshape(B, 81, 128)
+    assert not torch.isnan(out.float()).any()
+    err = (out.float() - ref).abs()
+    assert bool((err <= 1e-2 + 1e-2 * ref.abs()).all()), float(err.max())
+    if with_second:
+        ref2 = torch.empty_like(out)
+        _lib.check(L.tg_net_add_bn_relu(_lib.ptr(out), None, 1.0, None, _lib.ptr(s2), _lib.ptr(t2), None, _lib.ptr(ref2), B * 81, 128, _lib.stream_ptr()))
+        assert torch.equal(out2, ref2)
+
+
 @pytest.mark.parametrize("B,nout", [(1, 2), (7, 4), (700, 4), (300, 2), (3, 3), (2, 1)])
 def test_head_conv_kernel_matches_fp32_reference(B, nout):
     """tg_net_conv3x3_head (3x3, 128 -> nout channels, bias, ReLU; zero-bordered frames in shared memory + mma.sync) against
@@ -189,13 +218,14 @@ def test_head_conv_kernel_matches_fp32_reference(B, nout):
     assert L.tg_net_conv3x3_head(_lib.ptr(x), _lib.ptr(w8), _lib.ptr(b8), _lib.ptr(out), B, 9, 128, 5, _lib.stream_ptr()) != 0
 
 
-@pytest.mark.parametrize("attention,head_conv", [("tcgen05", "mma"), ("mma", "library"), ("tcgen05", "library")])
-def test_fused_forward_matches_fp32_module(attention, head_conv):
+@pytest.mark.parametrize("attention,head_conv,stem_conv", [("tcgen05", "mma", "mma"), ("mma", "library", "library"), ("tcgen05", "library", "mma"),
+                                                           ("mma", "mma", "library")])
+def test_fused_forward_matches_fp32_module(attention, head_conv, stem_conv):
     """Tolerance: policy max |dp| <= 4e-3 (probabilities), value / ownership max |dv| <= 4e-2 -- bf16 activations through
     26 convolution layers; argmax of the policy must agree wherever the fp32 margin exceeds the tolerance."""
     from transgo_b200.fused_net import FusedTransGoInference
     m = _perturbed_model()
-    fused = FusedTransGoInference(m, attention=attention, head_conv=head_conv)
+    fused = FusedTransGoInference(m, attention=attention, head_conv=head_conv, stem_conv=stem_conv)
     g = torch.Generator(device="cuda"); g.manual_seed(3)
     obs = (torch.rand([257, 10, 9, 9], device="cuda", generator=g) > 0.75).float()
     with torch.no_grad():

@@ -585,6 +585,130 @@ extern "C" int tg_net_conv3x3_head(const void* x, const void* w, const float* bi
     return set_err((int)cudaGetLastError(), "tg_net_conv3x3_head");
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// The stem of the net (model.py:43, :81: 3x3 convolution from the 10 feature planes to 128 channels, BatchNorm folded, ReLU)
+// straight from the float32 planes [B][10][81] the leaf kernels write, to NHWC bf16 -- and, optionally, the opening activation
+// relu(bn1(out)) of the first residual block as a second output.  The library route is a staging copy into a 16-channel NHWC
+// tensor, an implicit GEMM (69 us for 4096 positions: K = 90 is tiny, the 85 MB output is the work) and a junction pass.
+// One position at a time per CTA: planes -> zero-bordered 11x11 frame [row][16 channels] in shared memory (double buffered, the
+// next position's planes are fetched into registers meanwhile); a tap is a row offset and ONE k step of mma.sync m16n8k16
+// (10 of 16 channels used).  Warp w owns output channels [16w, 16w + 16) for all six 16-pixel M tiles, its 18 B fragments live in
+// registers for the whole launch.
+namespace tg {
+
+constexpr int kStRS = 48;                               // frame row stride (bytes): 16 channels bf16 + 16 pad -> conflict-free ldmatrix
+constexpr int kStTile = 128 * kStRS;
+constexpr int kStWarps = 8;
+
+__global__ void __launch_bounds__(kStWarps * 32, 2)
+k_stem(const float* __restrict__ obs, int cin, const __nv_bfloat16* __restrict__ w, const float* __restrict__ bias,
+       const float* __restrict__ scale2, const float* __restrict__ shift2, __nv_bfloat16* __restrict__ out,
+       __nv_bfloat16* __restrict__ out2, int B) {
+    __shared__ __align__(16) unsigned char st_smem[2 * kStTile];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, g = lane >> 2, t = lane & 3;
+    for (int i = tid; i < 2 * kStTile / 16; i += blockDim.x) reinterpret_cast<uint4*>(st_smem)[i] = make_uint4(0, 0, 0, 0);
+    // B fragments: column n of tap `tap` is w[n][tap][0..15]
+    uint32_t bw[2][9][2];
+    float bs[2][2], s2[2][2], t2[2][2];
+#pragma unroll
+    for (int nl = 0; nl < 2; ++nl) {
+        const int n = wid * 16 + nl * 8 + g;
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+            const uint32_t* wr = reinterpret_cast<const uint32_t*>(w + ((size_t)n * 9 + tap) * 16);
+            bw[nl][tap][0] = wr[t]; bw[nl][tap][1] = wr[4 + t];
+        }
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int c = wid * 16 + nl * 8 + 2 * t + e;               // the accumulator columns of this lane
+            bs[nl][e] = bias[c];
+            s2[nl][e] = out2 ? scale2[c] : 0.0f; t2[nl][e] = out2 ? shift2[c] : 0.0f;
+        }
+    }
+    const int per = cin * kHcP;                                      // floats of one position
+    const int mrow = (lane & 7) + ((lane >> 3) & 1) * 8, mcol = (lane >> 4) * 8;
+    int fra[6];
+#pragma unroll
+    for (int mt = 0; mt < 6; ++mt) { int p = mt * 16 + mrow; p = p < kHcP ? p : kHcP - 1; fra[mt] = (p / kHcN + 1) * kHcF + (p % kHcN) + 1; }
+    float nx[4];
+    auto fetch = [&](int pos) {
+        const float* src = obs + (size_t)pos * per;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { const int e = tid + k * 256; nx[k] = e < per ? __ldg(src + e) : 0.0f; }
+    };
+    if ((int)blockIdx.x < B) fetch(blockIdx.x);
+    __syncthreads();
+    int buf = 0;
+    for (int pos = blockIdx.x; pos < B; pos += gridDim.x) {
+        unsigned char* tile = st_smem + buf * kStTile;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int e = tid + k * 256;
+            if (e < per) {
+                const int c = e / kHcP, p = e - c * kHcP;
+                const int fr = (p / kHcN + 1) * kHcF + (p % kHcN) + 1;
+                *reinterpret_cast<__nv_bfloat16*>(tile + fr * kStRS + c * 2) = __float2bfloat16(nx[k]);
+            }
+        }
+        if (pos + (int)gridDim.x < B) fetch(pos + gridDim.x);
+        __syncthreads();
+        float acc[6][2][4];
+#pragma unroll
+        for (int mt = 0; mt < 6; ++mt)
+#pragma unroll
+            for (int nl = 0; nl < 2; ++nl) acc[mt][nl][0] = acc[mt][nl][1] = acc[mt][nl][2] = acc[mt][nl][3] = 0.0f;
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+            const int off = (tap / 3 - 1) * kHcF + (tap % 3 - 1);
+#pragma unroll
+            for (int mt = 0; mt < 6; ++mt) {
+                uint32_t a[4];
+                ldsm_x4(a, tile + (fra[mt] + off) * kStRS + mcol * 2);
+                mma_bf16(acc[mt][0], a, bw[0][tap][0], bw[0][tap][1]);
+                mma_bf16(acc[mt][1], a, bw[1][tap][0], bw[1][tap][1]);
+            }
+        }
+        __nv_bfloat16* o = out + (size_t)pos * kHcP * kAttC;
+        __nv_bfloat16* o2 = out2 ? out2 + (size_t)pos * kHcP * kAttC : nullptr;
+#pragma unroll
+        for (int mt = 0; mt < 6; ++mt)
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const int p = mt * 16 + g + 8 * r;
+                if (p < kHcP) {
+#pragma unroll
+                    for (int nl = 0; nl < 2; ++nl) {
+                        const int c = wid * 16 + nl * 8 + 2 * t;
+                        const uint32_t v = pack_bf16(fmaxf(acc[mt][nl][2 * r] + bs[nl][0], 0.0f), fmaxf(acc[mt][nl][2 * r + 1] + bs[nl][1], 0.0f));
+                        *reinterpret_cast<uint32_t*>(o + p * kAttC + c) = v;
+                        if (o2) {                                              // like tg_net_add_bn_relu on the bf16-rounded value
+                            const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v));
+                            *reinterpret_cast<uint32_t*>(o2 + p * kAttC + c) =
+                                pack_bf16(fmaxf(__fadd_rn(__fmul_rn(f.x, s2[nl][0]), t2[nl][0]), 0.0f), fmaxf(__fadd_rn(__fmul_rn(f.y, s2[nl][1]), t2[nl][1]), 0.0f));
+                        }
+                    }
+                }
+            }
+        buf ^= 1;
+    }
+}
+
+}  // namespace tg
+
+extern "C" int tg_net_stem(const float* obs, int cin, const void* w, const float* bias, const float* scale2, const float* shift2, void* out,
+                            void* out2, int64_t B, int board, int channels, void* stream) {
+    using namespace tg;
+    if (!obs || !w || !bias || !out || B <= 0 || board != kHcN || channels != kAttC || cin < 1 || cin > 12 || (out2 && (!scale2 || !shift2)))
+        return set_err(-1, "tg_net_stem (supports 9x9 boards, up to 12 input planes, 128 output channels)");
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long long grid = B < 2LL * sms ? B : 2LL * sms;
+    k_stem<<<(unsigned)grid, kStWarps * 32, 0, (cudaStream_t)stream>>>(obs, cin, (const __nv_bfloat16*)w, bias, scale2, shift2, (__nv_bfloat16*)out,
+                                                                        (__nv_bfloat16*)out2, (int)B);
+    return set_err((int)cudaGetLastError(), "tg_net_stem");
+}
+
 extern "C" int tg_net_attention(const void* qkv, const void* x, float gamma, const float* scale, const float* shift, void* out,
                                 int64_t B, int P, int dq, int channels, void* stream) {
     using namespace tg;

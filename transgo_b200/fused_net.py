@@ -68,10 +68,11 @@ def _copy_tree(old, new):
 
 
 class FusedTransGoInference:
-    def __init__(self, model, dtype=torch.bfloat16, attention="tcgen05", head_conv="mma"):
+    def __init__(self, model, dtype=torch.bfloat16, attention="tcgen05", head_conv="mma", stem_conv="mma"):
         """attention: "tcgen05" (default: the one-kernel block wherever it applies) or "mma" (GEMM + tg_net_attention everywhere;
-        kept as the cross-check and for timing comparisons).  head_conv: "mma" (default: tg_net_conv3x3_head on 9x9) or "library"."""
-        self.model, self.dtype, self.attention, self.head_conv = model, dtype, attention, head_conv
+        kept as the cross-check and for timing comparisons).  head_conv / stem_conv: "mma" (default: tg_net_conv3x3_head / tg_net_stem on
+        9x9) or "library"."""
+        self.model, self.dtype, self.attention, self.head_conv, self.stem_conv = model, dtype, attention, head_conv, stem_conv
         self.lib = _lib.lib()
         self._w = None
         self.refresh()
@@ -96,6 +97,11 @@ class FusedTransGoInference:
         self.device = next(m.parameters()).device
         w = {}
         w["stem"] = _conv_bn(m.conv1.conv[0], m.conv1.conv[1], dt, pad_in=16)
+        ws, bs = (t.float() for t in _conv_bn(m.conv1.conv[0], m.conv1.conv[1], torch.float32))      # the same, packed for tg_net_stem:
+        cin = ws.shape[1]                                                                              # [128][tap][16 input channels]
+        w["stem_k"] = (F.pad(ws.permute(0, 2, 3, 1).reshape(ws.shape[0], 9, cin), (0, 16 - cin)).to(dt).contiguous(), bs.contiguous()) \
+            if cin <= 12 else None
+        self.cin = cin
         blocks = []
         i = 2
         while hasattr(m, "res_conv%d" % i):
@@ -202,13 +208,23 @@ class FusedTransGoInference:
         key = (B, obs.device)
         if key not in self._bufs:
             self._bufs[key] = torch.zeros([B, 16, self.n, self.n], dtype=self.dtype, device=obs.device).contiguous(memory_format=torch.channels_last)
-        x16 = self._bufs[key]
-        x16[:, :obs.shape[1]] = obs
         conv_relu = torch.cudnn_convolution_relu
         one, pad = [1, 1], [1, 1]
-        x = conv_relu(x16, self.stem[0], self.stem[1], one, pad, one, 1)       # stem: conv + folded BN + ReLU
         pending = None                                                         # activation already prepared for the next R block
         nb = len(self.blocks)
+        if (self.stem_conv == "mma" and self.n == 9 and self.dtype == torch.bfloat16 and self.stem_k is not None and obs.dtype == torch.float32
+                and obs.is_contiguous() and self.stem[0].shape[0] == 128):
+            # planes -> NHWC bf16 trunk input in one hand-written kernel, with the first residual block's opening activation
+            x = torch.empty([B, 128, self.n, self.n], dtype=self.dtype, device=obs.device).contiguous(memory_format=torch.channels_last)
+            first = self.blocks[0] if nb and self.blocks[0][0] == "R" else None
+            pending = torch.empty_like(x) if first is not None else None
+            _lib.check(self.lib.tg_net_stem(_lib.ptr(obs), self.cin, _lib.ptr(self.stem_k[0]), _lib.ptr(self.stem_k[1]),
+                                            _lib.ptr(first[1]["s1"]) if first else None, _lib.ptr(first[1]["t1"]) if first else None,
+                                            _lib.ptr(x), _lib.ptr(pending), B, self.n, 128, _lib.stream_ptr(device=obs.device)), "tg_net_stem")
+        else:
+            x16 = self._bufs[key]
+            x16[:, :obs.shape[1]] = obs
+            x = conv_relu(x16, self.stem[0], self.stem[1], one, pad, one, 1)   # stem: conv + folded BN + ReLU
         for i, (kind, p) in enumerate(self.blocks):
             if kind == "R":
                 a1 = pending if pending is not None else self._junction(x, None, 1.0, p["s1"], p["t1"], False, True)[1]
@@ -238,12 +254,12 @@ class FusedTransGoInference:
         return policy, value, own
 
 
-def make_fused_evaluator(model, dtype=torch.bfloat16, cuda_graph=True, attention="tcgen05", head_conv="mma"):
+def make_fused_evaluator(model, dtype=torch.bfloat16, cuda_graph=True, attention="tcgen05", head_conv="mma", stem_conv="mma"):
     """evaluator(obs) -> (policy, value) for BatchedMCTS, forward captured once per static input tensor as a CUDA graph.
     cuda_graph=False: plain launches (use it when the caller captures a larger graph, e.g. BatchedMCTS(graph_waves=True));
     cuda_graph="roots": plain launches while the current stream is being captured, own graphs otherwise (the search's wave
     batch is captured by the engine, the per-move root batch runs outside it)."""
-    net = FusedTransGoInference(model, dtype, attention=attention, head_conv=head_conv)
+    net = FusedTransGoInference(model, dtype, attention=attention, head_conv=head_conv, stem_conv=stem_conv)
     graphs = {}
 
     def evaluator(obs):
