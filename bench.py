@@ -758,8 +758,9 @@ def mcts_bench(torch, dist, dev, rank, world, args):
         rate, ms, n, waves = timed_moves(eng, 1)
         out[name] = {"value": rate, "unit": "MCTS sims/s", "ms": ms, "sims": n, "moves": 1, "waves": waves,
                      "net": "TransGoNetwork 2.97 M params random init (seed 0), eval mode, 0.457 GFLOP/position" +
-                            ("; BN folded, NHWC bf16, residual junctions (tg_net_add_bn_relu) and attention blocks (tg_net_attention) "
-                             "hand-written, convolutions / GEMMs in cuDNN / cuBLAS" if dtype == "fused" else ""),
+                            ("; BN folded, NHWC bf16; hand-written: stem (tg_net_stem), residual junctions (tg_net_add_bn_relu), attention "
+                             "blocks incl. their 1x1 convolutions (tg_net_attention_fused2: tcgen05), head convolutions "
+                             "(tg_net_conv3x3_head); the 18 trunk convolutions in cuDNN, the head GEMMs in cuBLAS" if dtype == "fused" else ""),
                      "net_tflops": rate * 0.457e9 / 1e12}
         del eng
     return out
