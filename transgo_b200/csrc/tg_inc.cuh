@@ -186,13 +186,28 @@ template <int N, int T> __device__ __forceinline__ DS<N> dflood(DS<N> g, const D
 
 // Flood the group of the seed g inside `col`, counting its liberties, until it is complete or `lim` liberties are known.
 // On return: complete -> g is the whole group and libs exact; otherwise libs >= lim.  (tg_board.cuh: flood_group)
+// TG_FLOOD_STEPS flood steps per lock-step vote (T > 1).  Extra steps are harmless: at the fixed point a step changes nothing,
+// before it g and libs only grow, and the callers only act on (complete && libs == 1) or on the complete group.
+// Measured (B200, 4096 / 2048 / 16384 games of 9x9): two steps per vote -3 % / -5 % / -2 % launch time, three steps no better;
+// 19x19 (12-word boards: a step costs four times as much as a vote) is faster with one.
+#ifndef TG_FLOOD_STEPS_SMALL
+#define TG_FLOOD_STEPS_SMALL 2
+#endif
+#ifndef TG_FLOOD_STEPS_LARGE
+#define TG_FLOOD_STEPS_LARGE 1
+#endif
+#define TG_FLOOD_STEPS (DGeo<N>::NW <= 4 ? TG_FLOOD_STEPS_SMALL : TG_FLOOD_STEPS_LARGE)
 template <int N, int T> __device__ __forceinline__ void dflood_group(DS<N>& g, const DS<N>& col, const DS<N>& empty, int lim, int& libs, bool& complete) {
     while (true) {
-        const DS<N> nb = dnbrs<N>(g);
-        const DS<N> n1 = defill<N>((g | nb) & col, col);
-        libs = dcount<N>(nb & empty);
-        const bool ch = dnot_within<N>(n1, g);
-        g = n1;
+        bool ch = false;
+#pragma unroll
+        for (int rep = 0; rep < (T == 1 ? 1 : TG_FLOOD_STEPS); ++rep) {
+            const DS<N> nb = dnbrs<N>(g);
+            const DS<N> n1 = defill<N>((g | nb) & col, col);
+            libs = dcount<N>(nb & empty);
+            ch = dnot_within<N>(n1, g);
+            g = n1;
+        }
         complete = !ch;
         if (!vany<T>(ch && libs < lim)) break;
     }
@@ -260,7 +275,10 @@ __device__ __forceinline__ int ply(Game<N>& s, DS<N>& me, DS<N>& op, int max_ste
     DS<N> src; TG_DW src.w[i] = empty.w[i] | (me.w[i] & ~s.l1.w[i]) | (op.w[i] & s.l1.w[i]);
     DS<N> lg = empty & dnbrs<N>(src);
     const bool kocond = active && s.ko_age == 0 && s.ko_color == s.player && s.ko_loc >= 0 && s.ko_loc < D::P;   // board.cc:198-200
-    if (vany<T>(kocond)) { if (kocond) lg = dandn<N>(lg, dpoint<N>(action_to_bit<N>(s.ko_loc))); }
+    {   // branch-free: a vote + branch costs more latency here than the ten instructions it would skip
+        const int kb = kocond ? action_to_bit<N>(s.ko_loc) : -1;
+        TG_DW lg.w[i] &= ~((kb >> 5) == i ? (1u << (kb & 31)) : 0u);
+    }
     if (NOEYE) lg = dandn<N>(lg, dtrue_eyes<N>(me, op));                                       // board.cc:510-512
     const int nl = dcount<N>(lg);
     const bool placing = active && nl > 0;
