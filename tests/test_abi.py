@@ -63,3 +63,36 @@ def test_product_never_imports_the_oracle():
                 if re.search(r"^\s*(from|import)\s+oracle\b|liboracle_go|oracle/_ref", txt, flags=re.M):
                     bad.append(f)
     assert not bad, bad
+
+
+def test_header_compiles_as_plain_c_and_a_c_program_links_the_library(tmp_path):
+    """The boundary is a C ABI: include/transgo_b200.h must be valid C99 (no C++-isms, no torch types), and a C translation unit
+    that references entry points of every family must link against the shared library (nothing is CALLED here: no GPU)."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    from transgo_b200 import _lib
+    if not os.path.exists(_lib.LIB_PATH):
+        import __graft_entry__ as ge
+        ge.build()
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-x", "c", HEADER], check=True)
+    src = tmp_path / "consumer.c"
+    src.write_text("""
+#include <stdio.h>
+#include "transgo_b200.h"
+int main(int argc, char** argv) {
+    /* take the addresses so that the linker must resolve them; call only what needs no device */
+    void* fns[] = {(void*)Reset, (void*)Step, (void*)getLegalAction, (void*)Encode, (void*)getScore,
+                   (void*)tg_env_step, (void*)tg_env_playout_scored, (void*)tg_mcts_wave_begin, (void*)tg_mcts_wave_end,
+                   (void*)tg_traj_assemble, (void*)tg_net_attention_fused2, (void*)tg_net_conv3x3_head, (void*)tg_net_stem};
+    printf("%d %d %d %d\\n", tg_version(), tg_state_bytes(9), tg_state_bytes(19), (int)(sizeof(fns) / sizeof(fns[0])));
+    return argc > 100 ? (int)(size_t)fns[0] : 0;
+}
+""")
+    exe = tmp_path / "consumer"
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                    "-L", libdir, "-l:libtransgo_b200.so", "-Wl,-rpath," + libdir], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    assert int(out[0]) >= 100 and out[1:3] == ["48", "128"]
