@@ -600,6 +600,19 @@ constexpr int kStRS = 48;                               // frame row stride (byt
 constexpr int kStTile = 128 * kStRS;
 constexpr int kStWarps = 8;
 
+// 4 x 4 transpose of 32-bit words inside a quad (lanes t = 0..3 of the same g), two shuffle rounds.  In: a[k], k = 2 * (row half) +
+// (8-column tile), each word = this lane's columns 2t, 2t + 1 of that (row half, tile).  Out: the four words are columns 0..7 of
+// ONE (row half, tile) combination: row half = t & 1, tile = t >> 1.
+__device__ __forceinline__ void quad_transpose(uint32_t* a, int t) {
+    const bool odd = t & 1, hi = t & 2;
+    // reorder to the accumulator order the attention epilogue uses: k = 2 * tile + row half
+    const uint32_t s1 = a[1]; a[1] = a[2]; a[2] = s1;
+    const uint32_t r0 = __shfl_xor_sync(0xffffffffu, odd ? a[0] : a[1], 1), r1 = __shfl_xor_sync(0xffffffffu, odd ? a[2] : a[3], 1);
+    if (odd) { a[0] = r0; a[2] = r1; } else { a[1] = r0; a[3] = r1; }
+    const uint32_t q0 = __shfl_xor_sync(0xffffffffu, hi ? a[0] : a[2], 2), q1 = __shfl_xor_sync(0xffffffffu, hi ? a[1] : a[3], 2);
+    if (hi) { a[0] = q0; a[1] = q1; } else { a[2] = q0; a[3] = q1; }
+}
+
 __global__ void __launch_bounds__(kStWarps * 32, 2)
 k_stem(const float* __restrict__ obs, int cin, const __nv_bfloat16* __restrict__ w, const float* __restrict__ bias,
        const float* __restrict__ scale2, const float* __restrict__ shift2, __nv_bfloat16* __restrict__ out,
@@ -671,24 +684,26 @@ k_stem(const float* __restrict__ obs, int cin, const __nv_bfloat16* __restrict__
         __nv_bfloat16* o = out + (size_t)pos * kHcP * kAttC;
         __nv_bfloat16* o2 = out2 ? out2 + (size_t)pos * kHcP * kAttC : nullptr;
 #pragma unroll
-        for (int mt = 0; mt < 6; ++mt)
+        for (int mt = 0; mt < 6; ++mt) {
+            // this lane's four bf16 pairs of the 16 x 16 tile (rows g / g + 8, channel tiles 0 / 1), then a 4 x 4 transpose inside
+            // the quad: every lane ends up with 8 consecutive channels of ONE row -> 16-byte stores, full sectors
+            uint32_t a[4], b[4];
 #pragma unroll
-            for (int r = 0; r < 2; ++r) {
-                const int p = mt * 16 + g + 8 * r;
-                if (p < kHcP) {
-#pragma unroll
-                    for (int nl = 0; nl < 2; ++nl) {
-                        const int c = wid * 16 + nl * 8 + 2 * t;
-                        const uint32_t v = pack_bf16(fmaxf(acc[mt][nl][2 * r] + bs[nl][0], 0.0f), fmaxf(acc[mt][nl][2 * r + 1] + bs[nl][1], 0.0f));
-                        *reinterpret_cast<uint32_t*>(o + p * kAttC + c) = v;
-                        if (o2) {                                              // like tg_net_add_bn_relu on the bf16-rounded value
-                            const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v));
-                            *reinterpret_cast<uint32_t*>(o2 + p * kAttC + c) =
-                                pack_bf16(fmaxf(__fadd_rn(__fmul_rn(f.x, s2[nl][0]), t2[nl][0]), 0.0f), fmaxf(__fadd_rn(__fmul_rn(f.y, s2[nl][1]), t2[nl][1]), 0.0f));
-                        }
-                    }
-                }
+            for (int k = 0; k < 4; ++k) {
+                const int r = k >> 1, nl = k & 1;
+                a[k] = pack_bf16(fmaxf(acc[mt][nl][2 * r] + bs[nl][0], 0.0f), fmaxf(acc[mt][nl][2 * r + 1] + bs[nl][1], 0.0f));
+                const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&a[k]));   // like tg_net_add_bn_relu on the rounded value
+                b[k] = pack_bf16(fmaxf(__fadd_rn(__fmul_rn(f.x, s2[nl][0]), t2[nl][0]), 0.0f), fmaxf(__fadd_rn(__fmul_rn(f.y, s2[nl][1]), t2[nl][1]), 0.0f));
             }
+            // a[] is indexed [row half][channel tile]; the transpose wants [channel tile][row half] pairs: reorder to (r0 n0, r0 n1, r1 n0, r1 n1)
+            quad_transpose(a, t);
+            if (o2) quad_transpose(b, t);
+            const int p = mt * 16 + g + (t & 1) * 8, c = wid * 16 + (t >> 1) * 8;
+            if (p < kHcP) {
+                *reinterpret_cast<uint4*>(o + p * kAttC + c) = make_uint4(a[0], a[1], a[2], a[3]);
+                if (o2) *reinterpret_cast<uint4*>(o2 + p * kAttC + c) = make_uint4(b[0], b[1], b[2], b[3]);
+            }
+        }
         buf ^= 1;
     }
 }
