@@ -10,8 +10,8 @@ group analysis -> legal mask -> hashed move draw -> capture/ko/step) + Tromp-Tay
   value      board steps (plies) per second, whole job, game states resident in HBM, CUDA-event timed
   e2e        same metric through the C ABI with HOST buffers, all transfers inside the timed region; two routes are timed and the
              faster one is reported (both under e2e.routes): "copies" = pinned initial states H2D, kernels, final states + scores +
-             the per-ply action trace D2H as separate copy operations; "zero_copy" = ONE launch whose kernel reads / writes the
-             same pinned host buffers across PCIe itself
+             the per-ply action trace D2H as separate copy operations; "zero_copy" = ONE launch (tg_env_playout_io) whose kernel
+             reads the pinned start positions and writes final positions, scores and trace into pinned host memory across PCIe itself
   roofline   k_playout against the measured HBM peak with SURVEY 8d's 115 algorithmic bytes per ply
   cpu_baseline  the UNMODIFIED reference engine (oracle/_ref/go_env9.so, compiled from /root/reference) driven through
              ctypes exactly like GoEnv/environment.py (getLegalAction + Step per ply) on every host core, same move rule
@@ -351,9 +351,10 @@ def run_ours(args):
     assert bool((h_scores * 2 % 2 == 1).all())                 # host really received final area scores
 
     def zc_launch(i):
+        # start positions are READ from h_states and the final ones written to h_zc_states (tg_env_playout_io): nothing to refill
         env.playout(plies_max, seed=SEED + i, game_id0=rank * G, trace=h_zc_trace, counter=counter, score_out=h_zc_scores,
-                    states=h_zc_states)
-    e2e_zc_value, ms_e2e_zc = time_e2e(zc_launch, prep=lambda: h_zc_states.copy_(h_states))
+                    states=h_zc_states, states_in=h_states)
+    e2e_zc_value, ms_e2e_zc = time_e2e(zc_launch)
     torch.cuda.synchronize()
     # the two routes deliver the same bytes to the host (last timed step of each: same seed)
     assert torch.equal(h_zc_scores, h_scores) and torch.equal(h_zc_trace, h_trace) and torch.equal(h_zc_states, h_out_states)
@@ -410,7 +411,7 @@ def run_ours(args):
                     "ms_per_step": ms_e2e / K, "route": e2e_route,
                     "routes": {"copies": {"value": e2e_copies_value, "ms_per_step": ms_e2e_copies / K},
                                "zero_copy": {"value": e2e_zc_value, "ms_per_step": ms_e2e_zc / K,
-                                             "note": "the timed region holds the host refill of the in-place input buffer and the launch"}}},
+                                             "note": "one launch of tg_env_playout_io: pinned start positions read, final positions / scores / trace written by the kernel"}}},
             "gpu_launches": launches[0],
             "clocks": sampler.summary(),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -120,6 +120,12 @@ int tg_env_playout_scored(int n, void* states, int64_t G, int plies, int max_ste
                           int no_eye, int16_t* trace_actions, unsigned long long* plies_done, int from_reset,
                           float* score_out, float komi, int tile, void* stream);
 
+/* the same with separate input and output positions (states_in is only read, states_out only written; they may be the same
+ * buffer): a host that keeps its start positions in pinned memory needs no refill between launches.  score_out may be NULL. */
+int tg_env_playout_io(int n, const void* states_in, void* states_out, int64_t G, int plies, int max_step, uint64_t seed, int64_t game_id0,
+                      int no_eye, int16_t* trace_actions, unsigned long long* plies_done, float* score_out, float komi, int tile,
+                      void* stream);
+
 /* the layout tg_env_playout uses for (n, G, tile): TG_TILE_ROWS or the number of lanes per game (tile = 0: measured choice) */
 int tg_env_playout_tile(int n, int64_t G, int tile);
 /* diagnostics: games per warp of the incremental engine's tiled layouts (0 = fill the warp: 32 / lanes per game); returns the

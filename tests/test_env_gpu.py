@@ -360,5 +360,20 @@ def test_playout_on_pinned_host_buffers_equals_the_device_run():
         env.playout(T, seed=77, trace=h_trace, score_out=h_score, states=h_states)
         torch.cuda.synchronize()
         assert torch.equal(h_states, env.states.cpu()) and torch.equal(h_trace, d_trace.cpu()) and torch.equal(h_score, d_score.cpu())
+        # separate input / output buffers (tg_env_playout_io): the input stays untouched, the output equals the in-place result
+        h_in = torch.zeros([env.SQ, G, 4], dtype=torch.int32).pin_memory()
+        h_in.copy_(BatchedGoEnv(G, board_size=n).states)
+        keep = h_in.clone()
+        h_out = torch.zeros_like(h_in).pin_memory()
+        h_trace.fill_(-9); h_score.zero_()
+        env.playout(T, seed=77, trace=h_trace, score_out=h_score, states=h_out, states_in=h_in)
+        torch.cuda.synchronize()
+        assert torch.equal(h_in, keep) and torch.equal(h_out, h_states) and torch.equal(h_trace, d_trace.cpu()) and torch.equal(h_score, d_score.cpu())
+        for tile in (-1, 8 | 64):                                                        # layouts that play in place: copy, then play
+            other = BatchedGoEnv(G, board_size=n, tile=tile)
+            d_out = torch.zeros_like(env.states)
+            other.playout(T, seed=77, states=d_out, states_in=h_in)
+            torch.cuda.synchronize()
+            assert torch.equal(d_out.cpu(), h_states), tile
         with pytest.raises(AssertionError):
             env.playout(T, states=torch.zeros([env.SQ, G, 4], dtype=torch.int32))       # pageable host memory is refused

@@ -32,6 +32,8 @@ def _declare(L):
                                  ctypes.c_int, c_vp, c_vp, ctypes.c_int, c_vp]
     L.tg_env_playout_scored.argtypes = [ctypes.c_int, c_vp, c_i64, ctypes.c_int, ctypes.c_int, ctypes.c_uint64, c_i64,
                                         ctypes.c_int, c_vp, c_vp, ctypes.c_int, c_vp, ctypes.c_float, ctypes.c_int, c_vp]
+    L.tg_env_playout_io.argtypes = [ctypes.c_int, c_vp, c_vp, c_i64, ctypes.c_int, ctypes.c_int, ctypes.c_uint64, c_i64, ctypes.c_int,
+                                    c_vp, c_vp, c_vp, ctypes.c_float, ctypes.c_int, c_vp]
     L.tg_env_playout_tile.argtypes = [ctypes.c_int, c_i64, ctypes.c_int]
     L.tg_sub_encode.argtypes = [ctypes.c_int, c_vp, c_i64, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_vp, c_vp]
     L.tg_traj_assemble.argtypes = [ctypes.c_int, ctypes.c_int, c_i64, c_i64] + [c_vp] * 11 + [c_i64, c_i64, ctypes.c_int, c_vp, c_vp]

@@ -205,7 +205,7 @@ template <int N, int T, bool NOEYE>
 __global__ void __launch_bounds__(kThreads)
 k_playout_inc(uint4* __restrict__ states, long long G, int plies, int max_step, unsigned long long seed, long long game_id0,
               int16_t* __restrict__ trace, unsigned long long* __restrict__ plies_done, int from_reset, float* __restrict__ score_out,
-              float komi, int gw) {
+              float komi, int gw, const uint4* __restrict__ states_in) {
     using namespace inc;
     // gw = games per warp (T > 1): 32 / T fills the warp; fewer leave the upper tiles empty (they idle through the lock-step votes
     // without prolonging them), which trades lanes for a shorter slowest-of-the-warp flood and more warps per scheduler
@@ -220,7 +220,7 @@ k_playout_inc(uint4* __restrict__ states, long long G, int plies, int max_step, 
     const int sl = j == 0 ? 1 : (j == 2 ? DGeo<N>::STR : 0), sr = j == 1 ? 1 : (j == 3 ? DGeo<N>::STR : 0);
     // from_reset: the games start from the empty board (Reset, go_env.cc:34-41) without reading the states first
     Pos<N> p0; pos_reset(p0); p0.terminated = exists && from_reset ? 0 : 1;
-    if (exists && !from_reset) pos_load<N>(p0, states, g, G, 1);
+    if (exists && !from_reset) pos_load<N>(p0, states_in ? states_in : states, g, G, 1);   // states_in: read there, write `states`
     Game<N> s;
     const bool first_black = p0.player == kBlack;
     s.a = to_dense<N>(bb_select(first_black, p0.stones[0], p0.stones[1]));
@@ -423,15 +423,16 @@ static int g_playout_games_per_warp = 0;     // tg_env_debug_games_per_warp: 0 =
 
 template <int N, int T> int launch_playout_inc(cudaStream_t st, uint4* states, long long G, int plies, int max_step, unsigned long long seed,
                                                 long long game_id0, int no_eye, int16_t* trace, unsigned long long* plies_done,
-                                                int from_reset = 0, float* score_out = nullptr, float komi = 0.0f) {
+                                                int from_reset = 0, float* score_out = nullptr, float komi = 0.0f,
+                                                const uint4* states_in = nullptr) {
     // a playout CTA lives for the whole game: with few warps per SM one-warp CTAs spread them evenly over the 148 SMs
     int gw = 32 / T;
     if (T > 1 && g_playout_games_per_warp > 0 && g_playout_games_per_warp < gw) gw = g_playout_games_per_warp;
     const long long warps = T == 1 ? (G + 31) / 32 : (G + gw - 1) / gw;
     const int threads = warps < 148LL * 16 ? 32 : kThreads;
     const unsigned blocks = (unsigned)((warps * 32 + threads - 1) / threads);
-    if (no_eye) k_playout_inc<N, T, true><<<blocks, threads, 0, st>>>(states, G, plies, max_step, seed, game_id0, trace, plies_done, from_reset, score_out, komi, gw);
-    else k_playout_inc<N, T, false><<<blocks, threads, 0, st>>>(states, G, plies, max_step, seed, game_id0, trace, plies_done, from_reset, score_out, komi, gw);
+    if (no_eye) k_playout_inc<N, T, true><<<blocks, threads, 0, st>>>(states, G, plies, max_step, seed, game_id0, trace, plies_done, from_reset, score_out, komi, gw, states_in);
+    else k_playout_inc<N, T, false><<<blocks, threads, 0, st>>>(states, G, plies, max_step, seed, game_id0, trace, plies_done, from_reset, score_out, komi, gw, states_in);
     return 0;
 }
 
@@ -512,9 +513,16 @@ int tg_env_playout_tile(int n, int64_t G, int tile) {
 }
 
 static int playout_impl(int n, void* states, int64_t G, int plies, int max_step, uint64_t seed, int64_t game_id0, int no_eye,
-                        int16_t* trace_actions, unsigned long long* plies_done, int tile, void* stream, int from_reset, float* score_out, float komi) {
+                        int16_t* trace_actions, unsigned long long* plies_done, int tile, void* stream, int from_reset, float* score_out, float komi,
+                        const void* states_in = nullptr) {
     if (!states || G <= 0 || plies < 0) return set_err(-1, "tg_env_playout");
     cudaStream_t st = (cudaStream_t)stream;
+    if (states_in && !(tg_env_playout_tile(n, G, tile) > 0 && (tg_env_playout_tile(n, G, tile) & TG_TILE_INC))) {
+        // the other layouts play in place: bring the input over first (either side may be pinned host memory)
+        const cudaError_t e = cudaMemcpyAsync(states, states_in, (size_t)G * tg_state_bytes(n), cudaMemcpyDefault, st);
+        if (e != cudaSuccess) return set_err((int)e, "tg_env_playout_io (copy)");
+        states_in = nullptr;
+    }
     // tile == 0, measured on B200 (profiles/r01_playout_layouts.txt): 19x19 -> rows layout at every batch size (up to 3.6x over
     // the bitboard tiles); 9x9 -> four games per warp in lock step while the batch cannot fill the SMs, one thread per game beyond
     tile = tg_env_playout_tile(n, G, tile);
@@ -532,7 +540,7 @@ static int playout_impl(int n, void* states, int64_t G, int plies, int max_step,
     }
     if (tile & TG_TILE_INC) {
         const int t = tile & (TG_TILE_UNIFORM - 1);
-#define TG_INC_CASE(NN, TT) launch_playout_inc<NN, TT>(st, (uint4*)states, G, plies, max_step, seed, game_id0, no_eye, trace_actions, plies_done, from_reset, score_out, komi)
+#define TG_INC_CASE(NN, TT) launch_playout_inc<NN, TT>(st, (uint4*)states, G, plies, max_step, seed, game_id0, no_eye, trace_actions, plies_done, from_reset, score_out, komi, (const uint4*)states_in)
         if (n == 9) { if (t == 32) TG_INC_CASE(9, 32); else if (t == 16) TG_INC_CASE(9, 16); else if (t == 8) TG_INC_CASE(9, 8); else if (t == 4) TG_INC_CASE(9, 4); else TG_INC_CASE(9, 1); }
         else if (n == 19) { if (t == 32) TG_INC_CASE(19, 32); else if (t == 16) TG_INC_CASE(19, 16); else if (t == 8) TG_INC_CASE(19, 8); else if (t == 4) TG_INC_CASE(19, 4); else TG_INC_CASE(19, 1); }
         else return set_err(-1, "board size must be 9 or 19");
@@ -556,6 +564,13 @@ int tg_env_playout_scored(int n, void* states, int64_t G, int plies, int max_ste
                           int16_t* trace_actions, unsigned long long* plies_done, int from_reset, float* score_out, float komi,
                           int tile, void* stream) {
     return playout_impl(n, states, G, plies, max_step, seed, game_id0, no_eye, trace_actions, plies_done, tile, stream, from_reset, score_out, komi);
+}
+
+int tg_env_playout_io(int n, const void* states_in, void* states_out, int64_t G, int plies, int max_step, uint64_t seed, int64_t game_id0,
+                      int no_eye, int16_t* trace_actions, unsigned long long* plies_done, float* score_out, float komi, int tile, void* stream) {
+    if (!states_in) return set_err(-1, "tg_env_playout_io");
+    return playout_impl(n, states_out, G, plies, max_step, seed, game_id0, no_eye, trace_actions, plies_done, tile, stream, 0, score_out, komi,
+                        states_in == states_out ? nullptr : states_in);
 }
 
 #ifdef TG_ROWS_STATS

@@ -190,18 +190,27 @@ class BatchedGoEnv:
         return (sc, terr) if want_territory else sc
 
     def playout(self, plies, seed=0x7261, game_id0=0, no_eye=False, trace=None, counter=None, from_reset=False, score_out=None,
-                states=None):
+                states=None, states_in=None):
         """Every game plays up to ``plies`` moves of the SURVEY 8d C2 rule in one launch.  ``from_reset`` starts from empty boards
         (no separate reset launch, the old states are not read); ``score_out`` (float32 [G]) receives the final area scores
         (no separate score launch).  ``states`` (int32 [SQ, G, 4]) plays that buffer in place instead of ``self.states``.
         ``states``, ``trace`` and ``score_out`` may be PINNED HOST tensors: the kernel then reads the positions and writes the
         moves / results across PCIe itself (zero-copy; a board lives in registers for the whole launch, so each buffer
-        crosses the bus once) -- for a host caller that is one launch instead of a launch and four copies."""
+        crosses the bus once) -- for a host caller that is one launch instead of a launch and four copies.  ``states_in`` (same
+        shape) is read instead of ``states``, which is then only written: start positions kept in a read-only buffer need no
+        refill between launches."""
         st = self.states if states is None else states
         assert st.dtype == self.torch.int32 and st.numel() == self.SQ * self.G * 4 and st.is_contiguous()
         assert st.is_cuda or st.is_pinned(), "states must live on the device or in pinned host memory"
         for t in (trace, score_out):
             assert t is None or t.is_cuda or t.is_pinned(), "trace / score_out must live on the device or in pinned host memory"
+        if states_in is not None:
+            assert not from_reset and states_in.dtype == self.torch.int32 and states_in.numel() == st.numel() and states_in.is_contiguous()
+            assert states_in.is_cuda or states_in.is_pinned(), "states_in must live on the device or in pinned host memory"
+            _lib.check(self.lib.tg_env_playout_io(self.n, _lib.ptr(states_in), _lib.ptr(st), self.G, int(plies), self.max_step, int(seed),
+                                                  int(game_id0), int(no_eye), _lib.ptr(trace), _lib.ptr(counter), _lib.ptr(score_out),
+                                                  self.komi, self.tile, self._s()), "tg_env_playout_io")
+            return
         if from_reset or score_out is not None:
             _lib.check(self.lib.tg_env_playout_scored(self.n, _lib.ptr(st), self.G, int(plies), self.max_step, int(seed),
                                                       int(game_id0), int(no_eye), _lib.ptr(trace), _lib.ptr(counter), int(from_reset),
