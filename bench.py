@@ -493,6 +493,22 @@ def stepwise_and_sweep(torch, dev, BatchedGoEnv):
     env.playout(40, seed=2)
     ms = step_ms(env)
     out["step_kernel"] = {"games": GAMES, "ms": ms, "steps_per_s": GAMES / ms * 1e3, "gbps_algorithmic": GAMES * 115 / ms / 1e6}
+    # a ply-by-ply driver: step + encode per ply, eager C-ABI calls vs one CUDA-graph replay per ply (host wall clock per ply)
+    planes = torch.zeros([GAMES, 10, 9, 9], dtype=torch.float32, device=dev)
+    env2 = BatchedGoEnv(GAMES, device=dev)
+    acts0 = torch.full([GAMES], 40, dtype=torch.int16, device=dev)
+    step_graph = env2.make_step_graph(planes=planes)
+    def loop(fn, n=200):
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        for _ in range(n):
+            fn()
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) / n * 1e6
+    def eager():
+        env2.step(acts0); env2.encode(out=planes)
+    loop(eager, 20); loop(lambda: step_graph(acts0), 20)
+    out["stepwise_driver"] = {"games": GAMES, "what": "step + encode per ply (the reference's per-ply usage), host wall clock per ply",
+                              "eager_us_per_ply": loop(eager), "graph_us_per_ply": loop(lambda: step_graph(acts0))}
     ms = best_ms(lambda: env.encode())
     out["encode_kernel"] = {"games": GAMES, "ms": ms, "positions_per_s": GAMES / ms * 1e3, "gbps_algorithmic": GAMES * 3288 / ms / 1e6}
     sweep = []

@@ -377,3 +377,25 @@ def test_playout_on_pinned_host_buffers_equals_the_device_run():
             assert torch.equal(d_out.cpu(), h_states), tile
         with pytest.raises(AssertionError):
             env.playout(T, states=torch.zeros([env.SQ, G, 4], dtype=torch.int32))       # pageable host memory is refused
+
+
+def test_step_graph_replays_equal_eager_steps():
+    """BatchedGoEnv.make_step_graph: step (+ encode) captured once and replayed per ply must give what the eager calls give."""
+    import torch
+    from transgo_b200.environment import BatchedGoEnv
+    G = 512
+    a = BatchedGoEnv(G, board_size=9); b = BatchedGoEnv(G, board_size=9)
+    planes = torch.zeros([G, 10, 9, 9], dtype=torch.float32, device="cuda")
+    step = b.make_step_graph(planes=planes)
+    assert torch.equal(a.states, b.states)                       # building the graph leaves the position alone
+    gen = torch.Generator(device="cuda"); gen.manual_seed(3)
+    for ply in range(40):
+        legal = a.unpack_legal(a.legal_mask())                   # [G, 82]
+        r = torch.rand([G, 82], device="cuda", generator=gen) * legal
+        acts = r.argmax(1).to(torch.int16)
+        if ply % 7 == 3:
+            acts[::5] = 0                                        # some illegal / occupied points: refused, state unchanged
+        la, da = a.step(acts)
+        lb, db = step(acts)
+        assert torch.equal(a.states, b.states) and torch.equal(la, lb) and torch.equal(da, db), ply
+        assert torch.equal(planes, a.encode()), ply

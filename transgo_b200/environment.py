@@ -167,6 +167,36 @@ class BatchedGoEnv:
                                         _lib.ptr(self.accepted), self.max_step, self.tile, self._s()), "tg_env_step")
         return self.legal, self.done
 
+    def make_step_graph(self, planes=None):
+        """Capture `step` (+ `encode` into ``planes`` when given) once as a CUDA graph and return ``replay(actions) -> (legal, done)``.
+        A ply-by-ply driver pays one graph launch per ply instead of one C-ABI call + kernel launch per kernel (the kernels of a ply
+        last a few microseconds at the BASELINE batch: the host side is what a stepwise loop waits for).  ``actions`` are copied
+        into a static buffer; ``legal`` / ``done`` / ``planes`` are the env's own tensors, overwritten by every replay."""
+        torch = self.torch
+        static_actions = torch.zeros([self.G], dtype=torch.int16, device=self.device)
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        keep = self.states.clone()
+        with torch.cuda.stream(side):                          # warm-up outside the capture (lazy initialisation)
+            self.step(static_actions)
+            if planes is not None:
+                self.encode(out=planes)
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        self.states.copy_(keep)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self.step(static_actions)
+            if planes is not None:
+                self.encode(out=planes)
+        self.states.copy_(keep)                                # the capture does not execute, but stay explicit
+
+        def replay(actions):
+            static_actions.copy_(actions, non_blocking=True)
+            graph.replay()
+            return self.legal, self.done
+        replay.graph = graph
+        return replay
+
     def legal_mask(self, no_eye=False, out=None):
         out = self.legal if out is None else out
         _lib.check(self.lib.tg_env_legal(self.n, _lib.ptr(self.states), self.G, _lib.ptr(out), int(no_eye), self.tile,
