@@ -129,6 +129,9 @@ class FusedTransGoInference:
         w["fc_val_own"] = nhwc_fc(m.fc_val_own, 2)
         w["fc_val"] = (m.fc_val.weight.detach().to(dt).contiguous(), m.fc_val.bias.detach().to(dt).contiguous())
         w["fc_own"] = (m.fc_own.weight.detach().to(dt).contiguous(), m.fc_own.bias.detach().to(dt).contiguous())
+        # value and ownership share their input: one GEMM with the rows stacked, output [1 + P, B] so that the value row is contiguous
+        w["fc_vo"] = (torch.cat([m.fc_val.weight.detach(), m.fc_own.weight.detach()], 0).to(dt).contiguous(),
+                      torch.cat([m.fc_val.bias.detach(), m.fc_own.bias.detach()], 0).to(dt).reshape(-1, 1).contiguous())
         w["act_attn"] = self._attn(m.attention_act)
         ac = _conv_bn(m.conv_act.conv[0], m.conv_act.conv[1], dt)
         w["act_conv"] = (F.pad(ac[0], (0, 0, 0, 0, 0, 0, 0, 4)).contiguous(memory_format=torch.channels_last),
@@ -245,12 +248,12 @@ class FusedTransGoInference:
         # value / ownership head (model.py:93-99)
         hv = self._head_conv(x, self.val_head, self.val_conv, 2)
         hv = F.relu(F.linear(hv, *self.fc_val_own))
-        value = torch.tanh(F.linear(hv, *self.fc_val).float()).reshape(-1)
-        own = torch.tanh(F.linear(hv, *self.fc_own).float())
+        vo = torch.tanh(torch.addmm(self.fc_vo[1], self.fc_vo[0], hv.t()).float())     # [1 + P, B]: tanh of (W . h^T + b), like the two
+        value, own = vo[0], vo[1:].t()                                                 # separate F.linear calls (same bf16 rounding)
         # policy head (model.py:103-111)
         xa, _ = self._attention(x, self.act_attn)
         ha = self._head_conv(xa, self.act_head, self.act_conv, 4)
-        policy = torch.softmax(F.linear(ha, *self.fc_act).float(), -1)
+        policy = torch.softmax(F.linear(ha, *self.fc_act), -1, dtype=torch.float32)     # the cast happens inside the softmax kernel
         return policy, value, own
 
 
