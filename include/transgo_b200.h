@@ -95,6 +95,15 @@ int tg_env_step(int n, void* states, int64_t G, const int16_t* actions, uint32_t
                 uint8_t* done_out, uint8_t* acc_out, int max_step, int tile, void* stream);
 
 /* go_env.cc:154-171 (no_eye = 0) / :178-188 (no_eye = 1) as dense masks */
+/* tg_env_step on the incremental engine (csrc/tg_inc.cuh): the atari set of every position travels beside it in `atari`
+ * (tg_env_atari_words(n) u32 per game: 4 for 9x9, 16 for 19x19; start from all zeros) so that a step does not re-derive it.
+ * The record carries a digest of the stones it belongs to: a record that does not match its position (never initialised, or the
+ * position was changed by something else) is rebuilt inside the same launch, so the buffer is a cache and can never make a result
+ * wrong.  Same arguments, outputs and semantics as tg_env_step otherwise. */
+int tg_env_atari_words(int n);
+int tg_env_step_inc(int n, void* states, uint32_t* atari, int64_t G, const int16_t* actions, uint32_t* legal_out, uint8_t* done_out,
+                    uint8_t* accepted_out, int max_step, void* stream);
+
 int tg_env_legal(int n, const void* states, int64_t G, uint32_t* legal_out, int no_eye, int tile, void* stream);
 
 /* go_env.cc:96-115 with encode_dim 10: planes float32[G][10][n][n], written in place (e.g. the net's input) */

@@ -126,13 +126,14 @@ def test_playout_matches_oracle(oracle_built, n, G, tile, no_eye):
         assert meta["step"][g] == o.getStep(s) and meta["player"][g] == o.getPlayer(s)
 
 
-@pytest.mark.parametrize("n,G,tile", [(9, 96, 32), (9, 96, 8), (9, 96, 1), (19, 8, 32)])
+@pytest.mark.parametrize("n,G,tile", [(9, 96, 32), (9, 96, 8), (9, 96, 1), (19, 8, 32), (9, 96, "inc"), (9, 131, "inc"), (19, 11, "inc")])
 def test_step_kernel_per_ply_against_oracle(oracle_built, n, G, tile):
-    """Per ply: tg_env_step with oracle-chosen (sometimes illegal / pass / resign) actions; legal mask, done, accepted,
-    planes, score and territory must match the oracle after every move."""
+    """Per ply: tg_env_step (tile = lanes per game) / tg_env_step_inc (tile = "inc": the incremental engine with the atari set kept
+    beside the positions) with oracle-chosen (sometimes illegal / pass / resign) actions; legal mask, done, accepted, planes, score
+    and territory must match the oracle after every move."""
     from transgo_b200.environment import BatchedGoEnv
     rng = np.random.default_rng(11)
-    env = BatchedGoEnv(G, board_size=n, tile=tile)
+    env = BatchedGoEnv(G, board_size=n, step_engine="incremental") if tile == "inc" else BatchedGoEnv(G, board_size=n, tile=tile, step_engine="analysis")
     o = _oracle(n)
     P = n * n
     states = [o.reset()[0] for _ in range(G)]
@@ -399,3 +400,32 @@ def test_step_graph_replays_equal_eager_steps():
         lb, db = step(acts)
         assert torch.equal(a.states, b.states) and torch.equal(la, lb) and torch.equal(da, db), ply
         assert torch.equal(planes, a.encode()), ply
+
+
+def test_incremental_step_survives_positions_changed_behind_its_back():
+    """The atari records of tg_env_step_inc are a cache keyed by a digest of the stones: after the positions were replaced by
+    something else (a playout, a copy from another env) the next step must rebuild them and agree with the analysis kernel."""
+    import torch
+    from transgo_b200.environment import BatchedGoEnv
+    for n, G in ((9, 1000), (19, 40)):
+        a = BatchedGoEnv(G, board_size=n, step_engine="incremental")
+        b = BatchedGoEnv(G, board_size=n, step_engine="analysis")
+        gen = torch.Generator(device="cuda"); gen.manual_seed(5)
+
+        def both(acts):
+            la, da = a.step(acts); lb, db = b.step(acts)
+            assert torch.equal(a.states, b.states) and torch.equal(la, lb) and torch.equal(da, db) and torch.equal(a.accepted, b.accepted)
+
+        def random_legal():
+            legal = b.unpack_legal(b.legal_mask())
+            return (torch.rand([G, n * n + 1], device="cuda", generator=gen) * legal).argmax(1).to(torch.int16)
+        for _ in range(6):
+            both(random_legal())
+        a.playout(30, seed=9); b.playout(30, seed=9)                      # the records of `a` are stale now
+        for _ in range(6):
+            both(random_legal())
+        other = BatchedGoEnv(G, board_size=n); other.playout(55, seed=4)
+        a.states.copy_(other.states); b.states.copy_(other.states)         # stale again, mid-game positions with kos and ataris
+        a.atari.random_(0, 2 ** 31 - 1)                                    # and garbage records on top
+        for _ in range(10):
+            both(random_legal())

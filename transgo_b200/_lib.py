@@ -25,6 +25,8 @@ def _declare(L):
     L.tg_set_board_size.restype = ctypes.c_bool
     L.tg_env_reset.argtypes = [ctypes.c_int, c_vp, c_i64, c_vp]
     L.tg_env_step.argtypes = [ctypes.c_int, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, ctypes.c_int, ctypes.c_int, c_vp]
+    L.tg_env_atari_words.argtypes = [ctypes.c_int]
+    L.tg_env_step_inc.argtypes = [ctypes.c_int, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, ctypes.c_int, c_vp]
     L.tg_env_legal.argtypes = [ctypes.c_int, c_vp, c_i64, c_vp, ctypes.c_int, ctypes.c_int, c_vp]
     L.tg_env_encode.argtypes = [ctypes.c_int, c_vp, c_i64, c_vp, ctypes.c_int, c_vp]
     L.tg_env_score.argtypes = [ctypes.c_int, c_vp, c_i64, ctypes.c_float, c_vp, c_vp, ctypes.c_int, c_vp]

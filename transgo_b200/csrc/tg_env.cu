@@ -259,6 +259,105 @@ k_playout_inc(uint4* __restrict__ states, long long G, int plies, int max_step, 
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Stepwise API on the incremental engine.  `tg_env_step` re-derives the atari classes of the groups it touches on every call; here
+// the atari set travels with the position as a SIDE RECORD (one record per game: the set as a dense bit string + a 32-bit digest of
+// the stones it belongs to), so a step is the legal-mask formula, at most five early-exit floods around the new stone and the
+// legal mask of the next position.  A record whose digest does not match the stones (the caller changed the position behind our
+// back, or never initialised it) is rebuilt from scratch inside the same launch -- the record is a cache, never a source of truth.
+template <int N> struct AtariRec {
+    static constexpr int NW = inc::DGeo<N>::NW;
+    static constexpr int Q = (NW + 1 + 3) / 4;                        // uint4 per game: NW words of the set + 1 digest word
+};
+template <int N> __device__ __forceinline__ uint32_t stones_digest(const inc::DS<N>& a, const inc::DS<N>& b) {
+    unsigned long long z = 0x9E3779B97F4A7C15ull;
+#pragma unroll
+    for (int i = 0; i < inc::DGeo<N>::NW; ++i) {
+        z = (z ^ a.w[i]) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 29) ^ ((unsigned long long)b.w[i] << 32)) * 0x94D049BB133111EBull;
+    }
+    return (uint32_t)(z >> 32) | 1u;                                  // never 0: an all-zero record of a non-empty board is stale
+}
+
+template <int N, int T>
+__global__ void __launch_bounds__(kThreads)
+k_step_inc(uint4* __restrict__ states, uint32_t* __restrict__ atari, long long G, const int16_t* __restrict__ actions,
+           uint32_t* __restrict__ legal_out, uint8_t* __restrict__ done_out, uint8_t* __restrict__ acc_out, int max_step) {
+    using namespace inc;
+    using GG = Geo<N>; using D = DGeo<N>;
+    constexpr int RW = AtariRec<N>::Q * 4;                            // u32 words per record
+    const long long g = (blockIdx.x * (long long)blockDim.x + threadIdx.x) / T;
+    const bool exists = g < G;
+    if (!__any_sync(0xffffffffu, exists)) return;
+    const int j = (int)(threadIdx.x & (T - 1));
+    const bool lead = j == 0;
+    const int sl = j == 0 ? 1 : (j == 2 ? D::STR : 0), sr = j == 1 ? 1 : (j == 3 ? D::STR : 0);
+    Pos<N> p0; pos_reset(p0); p0.terminated = 1;
+    if (exists) pos_load<N>(p0, states, g, G, 1);
+    Game<N> s;
+    const bool first_black = p0.player == kBlack;
+    s.a = to_dense<N>(bb_select(first_black, p0.stones[0], p0.stones[1]));          // the side to move
+    s.b = to_dense<N>(bb_select(first_black, p0.stones[1], p0.stones[0]));
+    s.last1 = p0.last1; s.last2 = p0.last2; s.ko_loc = p0.ko_loc; s.ko_age = p0.ko_age; s.step = p0.step; s.player = p0.player;
+    s.ko_color = p0.ko_color; s.terminated = p0.terminated; s.draw = 0;
+    // the side record: valid iff its digest matches these stones (an empty board with an all-zero record matches by convention)
+    const uint32_t dig = stones_digest<N>(first_black ? s.a : s.b, first_black ? s.b : s.a);
+    const bool board_empty = !dany<N>(s.a | s.b);
+    uint32_t* rec = atari + (exists ? g : 0) * RW;
+    TG_DW s.l1.w[i] = exists ? rec[i] : 0u;
+    const uint32_t have = exists ? rec[D::NW] : 0u;
+    const bool stale = exists && !(have == dig || (board_empty && have == 0u && !dany<N>(s.l1)));
+    if (__any_sync(0xffffffffu, stale)) {                             // rare: rebuild in lock step, keep the valid ones
+        const DS<N> fresh = atari_from_scratch<N, T>(s.a, s.b);
+        s.l1 = dsel<N>(stale, fresh, s.l1);
+    }
+    int action = exists ? (int)actions[g] : (int)kInvalid;
+    if (action == GG::P) action = kPass;                              // go_env.cc:56-57
+    const bool active = exists && !s.terminated;
+    bool acc = false, done = exists && s.terminated;                  // go_env.cc:52-55
+    const bool is_pass = active && (action == kPass || action == kResign);
+    const bool is_stone = active && action >= 0 && action < GG::P;
+    const DS<N> lg0 = dlegal<N>(s, s.a, s.b);
+    const int bit = is_stone ? action_to_bit<N>(action) : 0;
+    bool placing = false;
+    TG_DW placing = placing || (is_stone && i == (bit >> 5) && ((lg0.w[i] >> (bit & 31)) & 1u));
+    dplace<N, T>(s, s.a, s.b, bit, placing, max_step, sl, sr);        // every lane walks through (votes are warp-wide)
+    if (placing) { acc = true; done = s.terminated != 0; }
+    if (is_pass) {                                                    // board.cc:536-542, 554-558, 656-661; ko fields untouched
+        s.player = 3 - s.player; s.last2 = s.last1; s.last1 = action; s.step += 1;
+        const bool over = s.step > 1 && ((s.last1 == kPass && s.last2 == kPass) || s.last1 == kResign);
+        if (over || s.step > max_step) s.terminated = 1;
+        acc = true; done = over || s.terminated != 0;
+    }
+    // after an accepted move the roles swap: the side to move is now the old `op`
+    const DS<N> me2 = dsel<N>(acc, s.b, s.a), op2 = dsel<N>(acc, s.a, s.b);
+    const DS<N> lg = dlegal<N>(s, me2, op2);
+    if (exists && lead) {
+        const bool now_black = s.player == kBlack;
+        const DS<N> black = dsel<N>(now_black, me2, op2), white = dsel<N>(now_black, op2, me2);
+        if (acc) {
+            p0.stones[0] = from_dense<N>(black); p0.stones[1] = from_dense<N>(white);
+            p0.last1 = s.last1; p0.last2 = s.last2; p0.ko_loc = s.ko_loc; p0.ko_age = s.ko_age; p0.step = s.step; p0.player = s.player;
+            p0.ko_color = s.ko_color; p0.terminated = s.terminated;
+            pos_store<N>(p0, states, g, G, 1);
+        }
+        TG_DW rec[i] = s.l1.w[i];
+        rec[D::NW] = stones_digest<N>(black, white);
+        if (done_out) done_out[g] = done ? 1 : 0;
+        if (acc_out) acc_out[g] = acc ? 1 : 0;
+        if (legal_out) {
+            uint32_t d[GG::DQ * 4];
+#pragma unroll
+            for (int i = 0; i < GG::DQ * 4; ++i) d[i] = 0;
+            bb_to_dense<N>(from_dense<N>(lg), d);
+            if (!dany<N>(lg)) d[GG::P >> 5] |= 1u << (GG::P & 31);
+            uint4* o = reinterpret_cast<uint4*>(legal_out) + g * GG::DQ;
+#pragma unroll
+            for (int k = 0; k < GG::DQ; ++k) o[k] = make_uint4(d[4 * k], d[4 * k + 1], d[4 * k + 2], d[4 * k + 3]);
+        }
+    }
+}
+
 // Row-per-lane playout (tg_rows.cuh): 31 / (N+1) games per warp, one board row per lane.  Same move rule, same results.
 template <int N>
 __global__ void __launch_bounds__(kThreads)
@@ -465,6 +564,19 @@ int tg_env_step(int n, void* states, int64_t G, const int16_t* actions, uint32_t
     tile = snap_tile(tile, G);
     TG_DISPATCH(n, tile, launch_step, st, (uint4*)states, G, actions, legal_out, done_out, acc_out, max_step);
     return set_err((int)cudaGetLastError(), "tg_env_step");
+}
+
+int tg_env_atari_words(int n) { return n == 9 ? AtariRec<9>::Q * 4 : (n == 19 ? AtariRec<19>::Q * 4 : 0); }
+
+int tg_env_step_inc(int n, void* states, uint32_t* atari, int64_t G, const int16_t* actions, uint32_t* legal_out, uint8_t* done_out,
+                    uint8_t* accepted_out, int max_step, void* stream) {
+    if (!states || !atari || !actions || G <= 0) return set_err(-1, "tg_env_step_inc");
+    constexpr int T = 4;
+    const unsigned blocks = (unsigned)((G * T + kThreads - 1) / kThreads);
+    if (n == 9) k_step_inc<9, T><<<blocks, kThreads, 0, (cudaStream_t)stream>>>((uint4*)states, atari, G, actions, legal_out, done_out, accepted_out, max_step);
+    else if (n == 19) k_step_inc<19, T><<<blocks, kThreads, 0, (cudaStream_t)stream>>>((uint4*)states, atari, G, actions, legal_out, done_out, accepted_out, max_step);
+    else return set_err(-1, "board size must be 9 or 19");
+    return set_err((int)cudaGetLastError(), "tg_env_step_inc");
 }
 
 int tg_env_legal(int n, const void* states, int64_t G, uint32_t* legal_out, int no_eye, int tile, void* stream) {

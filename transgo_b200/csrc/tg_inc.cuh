@@ -359,5 +359,69 @@ __device__ __forceinline__ int ply(Game<N>& s, DS<N>& me, DS<N>& op, int max_ste
     return action;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// The same engine for the STEPWISE API (tg_env_step with a caller-chosen action): the legal mask of the side to move and the
+// placement of a given stone, i.e. ply() without its move draw.  (Kept apart from ply(): the playout kernel's code generation
+// is tuned and must not move.)
+template <int N>
+__device__ __forceinline__ DS<N> dlegal(const Game<N>& s, const DS<N>& me, const DS<N>& op) {
+    using D = DGeo<N>;
+    DS<N> empty; TG_DW empty.w[i] = ~(me.w[i] | op.w[i]) & D::mask(i);
+    DS<N> src; TG_DW src.w[i] = empty.w[i] | (me.w[i] & ~s.l1.w[i]) | (op.w[i] & s.l1.w[i]);
+    DS<N> lg = empty & dnbrs<N>(src);                                                          // board.cc:130-158, 437-464
+    const bool kocond = s.ko_age == 0 && s.ko_color == s.player && s.ko_loc >= 0 && s.ko_loc < D::P;   // board.cc:198-200
+    const int kb = kocond ? action_to_bit<N>(s.ko_loc) : -1;
+    TG_DW lg.w[i] &= ~((kb >> 5) == i ? (1u << (kb & 31)) : 0u);
+    return lg;
+}
+
+// Place a stone of the side `me` at dense bit `bit` (a legal point) when `placing`; a game that does not place still walks through
+// the lock-step votes with empty sets.  Captures, simple ko, atari-set repair and the bookkeeping of board.cc:546-653 / go_env.cc:67-73.
+template <int N, int T>
+__device__ __forceinline__ void dplace(Game<N>& s, DS<N>& me, DS<N>& op, int bit, bool placing, int max_step, int sl, int sr) {
+    using D = DGeo<N>;
+    static_assert(T >= 4, "dplace: one lane per neighbour direction");
+    DS<N> empty; TG_DW empty.w[i] = ~(me.w[i] | op.w[i]) & D::mask(i);
+    DS<N> pb; TG_DW pb.w[i] = (placing && i == (bit >> 5)) ? (1u << (bit & 31)) : 0u;
+    const DS<N> around = dnbrs<N>(pb);
+    DS<N> hit; TG_DW hit.w[i] = around.w[i] & op.w[i] & s.l1.w[i];                             // enemy neighbours in atari: they die
+    DS<N> mrg; TG_DW mrg.w[i] = around.w[i] & me.w[i] & s.l1.w[i];
+    const bool merge = dany<N>(mrg);
+    bool ko = false;
+    if (vany<T>(dany<N>(hit))) {
+        DS<N> free_or_own; TG_DW free_or_own.w[i] = around.w[i] & (empty.w[i] | me.w[i]);
+        if (dany<N>(hit) && !dany<N>(free_or_own)) {                                           // board.cc:163-194, 561-570
+            const DS<N> cand = dandn<N>(hit, dnbrs<N>(op));
+            ko = dcount<N>(cand) == 1;
+            if (ko) { s.ko_loc = bit_to_action<N>(dlowest<N>(cand)); s.ko_color = 3 - s.player; s.ko_age = 0; }
+        }
+        const DS<N> l1op = op & s.l1;
+        const DS<N> dead = dflood<N, T>(hit, l1op);
+        op = dandn<N>(op, dead);
+        s.l1 = dandn<N>(s.l1, dead);
+        const DS<N> l1me = me & s.l1;
+        const DS<N> freed = dflood<N, T>(dnbrs<N>(dead) & l1me, l1me);
+        s.l1 = dandn<N>(s.l1, freed);
+    }
+    if (placing) {
+        if (!ko) s.ko_age += 1;
+        TG_DW me.w[i] |= pb.w[i];
+        s.player = 3 - s.player; s.last2 = s.last1; s.last1 = bit_to_action<N>(bit); s.step += 1;
+        if (s.step > max_step) s.terminated = 1;                                               // go_env.cc:67-73
+    }
+    DS<N> empty2; TG_DW empty2.w[i] = ~(me.w[i] | op.w[i]) & D::mask(i);
+    const DS<N> sh = dsel<N>(sr != 0, dshr<N>(pb, sr), dshl<N>(pb, sl));
+    const DS<N> es = sh & op;
+    const bool enemy = dany<N>(es);
+    const DS<N> col = dsel<N>(enemy, op, me);
+    DS<N> g = dsel<N>(enemy, es, pb);
+    const bool whole = !enemy && merge;
+    int libs; bool complete;
+    dflood_group<N, T>(g, col, empty2, whole ? (1 << 20) : 2, libs, complete);
+    const bool is1 = complete && libs == 1 && dany<N>(g);
+    if (vany<T>(merge)) s.l1 = dandn<N>(s.l1, tile_or<N, T>(dsel<N>(whole, g, dzero<N>())));
+    if (vany<T>(is1)) s.l1 = s.l1 | tile_or<N, T>(dsel<N>(is1, g, dzero<N>()));
+}
+
 }  // namespace inc
 }  // namespace tg

@@ -126,7 +126,7 @@ class BatchedGoEnv:
     (tests/test_env_gpu.py).
     """
 
-    def __init__(self, num_games, board_size=9, max_step=None, komi=7.5, device="cuda", tile=0):
+    def __init__(self, num_games, board_size=9, max_step=None, komi=7.5, device="cuda", tile=0, step_engine="incremental"):
         import torch
         self.torch = torch
         if not torch.cuda.is_available():
@@ -148,6 +148,12 @@ class BatchedGoEnv:
         self.legal = torch.zeros([self.G, self.LW], dtype=torch.int32, device=self.device)
         self.done = torch.zeros([self.G], dtype=torch.uint8, device=self.device)
         self.accepted = torch.zeros([self.G], dtype=torch.uint8, device=self.device)
+        # step_engine "incremental" (default): tg_env_step_inc, the atari sets kept beside the positions in `self.atari` (a cache:
+        # records that do not match their position are rebuilt inside the launch, so writing to `states` directly stays safe);
+        # "analysis": tg_env_step, which re-derives what it needs on every call (the cross-check, and `tile` applies to it only)
+        assert step_engine in ("incremental", "analysis")
+        self.step_engine = step_engine
+        self.atari = torch.zeros([self.G, self.lib.tg_env_atari_words(board_size)], dtype=torch.int32, device=self.device)
         self._bitpos = None
         self.reset()
 
@@ -162,6 +168,11 @@ class BatchedGoEnv:
     def step(self, actions, want_legal=True):
         """actions: int16 [G] on the device.  Returns (legal mask int32 [G, LW] of the new positions, done uint8 [G])."""
         assert actions.dtype == self.torch.int16 and actions.is_cuda and actions.numel() == self.G
+        if self.step_engine == "incremental":
+            _lib.check(self.lib.tg_env_step_inc(self.n, _lib.ptr(self.states), _lib.ptr(self.atari), self.G, _lib.ptr(actions),
+                                                _lib.ptr(self.legal) if want_legal else None, _lib.ptr(self.done),
+                                                _lib.ptr(self.accepted), self.max_step, self._s()), "tg_env_step_inc")
+            return self.legal, self.done
         _lib.check(self.lib.tg_env_step(self.n, _lib.ptr(self.states), self.G, _lib.ptr(actions),
                                         _lib.ptr(self.legal) if want_legal else None, _lib.ptr(self.done),
                                         _lib.ptr(self.accepted), self.max_step, self.tile, self._s()), "tg_env_step")
