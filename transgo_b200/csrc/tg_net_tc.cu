@@ -5,7 +5,7 @@
 // (tg_net.cu keeps the mma.sync kernels: they are the cross-check, and the path for boards with more than 96 points.)
 //
 // One CTA = 256 threads: the 128 TMEM lanes = 128 operand rows (81 points padded), TWO threads per row that split the columns
-// (warps w and w + 4 see the same 32 lanes); two CTAs per SM (2 x 256 TMEM columns, 2 x 107 KB shared memory), each looping over
+// (warps w and w + 4 see the same 32 lanes); two CTAs per SM (2 x 256 TMEM columns, 2 x 109 KB shared memory), each looping over
 // positions with the next position's x tile fetched into registers a position ahead.  Per position:
 //   1. x tile  [128 x 128] bf16 -> shared memory (K-major panels)              D1[i][n] = sum_c x[i][c] w[n][c]     8 MMAs, N = 192
 //   2. the two threads of row i read it from TMEM (tcgen05.ld 32x32b), add the bias, round to bf16 and park q / k (K-major);
@@ -14,7 +14,8 @@
 //   3. softmax over the keys j of row i: each thread of the pair owns 48 columns, one exchange of (max, sum) through shared
 //      memory; p[i][:] -> shared memory as the MN-major A operand p^T           O[j][c]  = sum_i p[i][j] v[i][c]     6 MMAs, N = 128
 //   4. row j of O -> bf16 -> shared memory (over the dead v panels); then the junction as a COALESCED pass over the tile: 16 threads
-//      per row, x from global memory (an L2 hit, requested before the MMA wait), relu(bn(gamma * o + x)), 16-byte stores.
+//      per row, x from global memory (an L2 hit, requested before the MMA wait), relu(bn(gamma * o + x)), 16-byte stores -- run while
+//      the tensor core already projects the NEXT position; optionally a second output relu(bn1(out)) for the residual block that follows.
 // TMEM columns: D1 = v [0,128) | q [128,160) | k [160,192) (the weight rows are permuted on the way into shared memory),
 // S [128,224) over the parked q | k, O [0,128) over the parked v.
 // Shared-memory operand layout ("panels"): the canonical no-swizzle layout of the UMMA descriptors with all rows of a
