@@ -763,13 +763,18 @@ def mcts_bench(torch, dist, dev, rank, world, args):
     from transgo_b200.fused_net import make_fused_evaluator
     if rank == 0 and not args.quick:
         out["c1_single_game_facade"] = c1_facade(torch, net)
-    for name, dtype in (("e2e_net_bf16_fused", "fused"), ("e2e_net_bf16", torch.bfloat16), ("e2e_net_fp32", None)):
-        if args.quick and dtype is None:
+    for name, dtype in (("e2e_net_bf16_fused", "fused"), ("e2e_net_bf16", torch.bfloat16), ("e2e_net_fp32_folded", "folded32"),
+                        ("e2e_net_fp32", None)):
+        if args.quick and dtype in (None, "folded32"):
             continue
-        # fused: the whole wave (tree kernels + net) is one CUDA graph, the root batch has its own; eager nets: graph per forward
+        # fused: the whole wave (tree kernels + net) is one CUDA graph, the root batch has its own; eager nets: graph per forward.
+        # folded32: the fused SCHEDULE (BatchNorm folded, NHWC, one graph per wave) with float32 storage and library kernels -- the
+        # same precision as the reference's net (float32, TF32 convolutions as PyTorch runs them by default)
+        graphed = dtype in ("fused", "folded32")
         ev = make_fused_evaluator(net, cuda_graph="roots") if dtype == "fused" else \
+            make_fused_evaluator(net, dtype=torch.float32, cuda_graph="roots") if dtype == "folded32" else \
             make_evaluator(net, dtype=dtype, channels_last=dtype is not None, cuda_graph=True)
-        eng = BatchedMCTS(ev, G, num_simulation=sims, tie_seed=1, game_id0=rank * G, device=dev, graph_waves=dtype == "fused")
+        eng = BatchedMCTS(ev, G, num_simulation=sims, tie_seed=1, game_id0=rank * G, device=dev, graph_waves=graphed)
         for _ in range(3):                                     # warm-up waves: lazy initialisation and CUDA-graph capture happen here,
             eng.run_wave()                                     # outside the timed move (they only add visits to the fresh roots)
         rate, ms, n, waves = timed_moves(eng, 1)
@@ -777,7 +782,8 @@ def mcts_bench(torch, dist, dev, rank, world, args):
                      "net": "TransGoNetwork 2.97 M params random init (seed 0), eval mode, 0.457 GFLOP/position" +
                             ("; BN folded, NHWC bf16; hand-written: stem (tg_net_stem), residual junctions (tg_net_add_bn_relu), attention "
                              "blocks incl. their 1x1 convolutions (tg_net_attention_fused2: tcgen05), head convolutions "
-                             "(tg_net_conv3x3_head); the 18 trunk convolutions in cuDNN, the head GEMMs in cuBLAS" if dtype == "fused" else ""),
+                             "(tg_net_conv3x3_head); the 18 trunk convolutions in cuDNN, the head GEMMs in cuBLAS" if dtype == "fused" else
+                             "; BN folded, NHWC float32, library kernels only (float32 storage, TF32 convolutions)" if dtype == "folded32" else ""),
                      "net_tflops": rate * 0.457e9 / 1e12}
         del eng
     return out

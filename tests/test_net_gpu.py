@@ -240,6 +240,23 @@ def test_fused_forward_matches_fp32_module(attention, head_conv, stem_conv):
     assert bool((p1.argmax(1)[clear] == p0.argmax(1)[clear]).all())
 
 
+def test_folded_forward_in_float32_matches_the_module_closely():
+    """The same schedule with float32 storage (BatchNorm folded, NHWC, library kernels for the pieces the bf16 kernels cover): the
+    same-precision-as-the-reference route.  Tolerance: policy 2e-4, value / ownership 2e-3 (folding reorders float32 roundings; the
+    convolutions run on TF32 tensor cores in both, as PyTorch does by default)."""
+    from transgo_b200.fused_net import FusedTransGoInference
+    m = _perturbed_model(4)
+    fused = FusedTransGoInference(m, dtype=torch.float32)
+    g = torch.Generator(device="cuda"); g.manual_seed(6)
+    obs = (torch.rand([130, 10, 9, 9], device="cuda", generator=g) > 0.75).float()
+    with torch.no_grad():
+        p0, v0, o0 = m.main_prediction(obs)
+    p1, v1, o1 = fused(obs)
+    assert p1.dtype == torch.float32
+    assert float((p1 - p0).abs().max()) <= 2e-4, float((p1 - p0).abs().max())
+    assert float((v1 - v0.reshape(-1)).abs().max()) <= 2e-3 and float((o1 - o0).abs().max()) <= 2e-3
+
+
 def test_search_runs_on_the_fused_evaluator_and_graph_replay_is_stable():
     from transgo_b200.fused_net import make_fused_evaluator
     from transgo_b200.mcts import BatchedMCTS

@@ -154,6 +154,12 @@ class FusedTransGoInference:
     def _junction(self, x, y, alpha, scale, shift, want_sum, want_act, ybias=None):
         """x (+ alpha*(y + ybias)) -> (sum, relu(sum*scale+shift)); x, y: channels_last [B,C,n,n] bf16 (NHWC memory)"""
         B, C = x.shape[0], x.shape[1]
+        if self.dtype != torch.bfloat16:
+            # float32 / float16 copies of the same schedule (e.g. the same-precision-as-the-reference row of the bench): library
+            # elementwise ops; the hand-written kernels are bf16
+            s = x if y is None else x + alpha * (y if ybias is None else y + ybias.to(y.dtype).view(1, -1, 1, 1))
+            a = torch.relu(s * scale.to(s.dtype).view(1, -1, 1, 1) + shift.to(s.dtype).view(1, -1, 1, 1)) if want_act else None
+            return (s if want_sum else None), a
         rows = B * self.P
         s_out = torch.empty_like(x) if want_sum else None
         a_out = torch.empty_like(x) if want_act else None
