@@ -274,6 +274,9 @@ int tg_dirichlet(double* noise, const int32_t* root_k, int64_t G, int A, double 
  * i.e. a residual junction of model.py:208-262 / :286-314 with the next eval-mode BatchNorm folded to scale/shift (f32). */
 int tg_net_add_bn_relu(const void* x, const void* y, float alpha, const float* ybias, const float* scale, const float* shift,
                        void* sum_out, void* act_out, int64_t rows, int channels, void* stream);
+/* the same junction on float32 activations (channels % 4 == 0): the folded float32 schedule of fused_net.py */
+int tg_net_add_bn_relu_f32(const float* x, const float* y, float alpha, const float* ybias, const float* scale, const float* shift,
+                           float* sum_out, float* act_out, int64_t rows, int channels, void* stream);
 /* diagnostics: 1 walks the junction's tensors back to front (the tail of y is what L2 may still hold), 0 (default) front to back;
  * returns the previous setting */
 int tg_net_debug_reverse(int on);

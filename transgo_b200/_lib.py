@@ -41,6 +41,7 @@ def _declare(L):
     L.tg_traj_assemble.argtypes = [ctypes.c_int, ctypes.c_int, c_i64, c_i64] + [c_vp] * 11 + [c_i64, c_i64, ctypes.c_int, c_vp, c_vp]
     L.tg_dirichlet.argtypes = [c_vp, c_vp, c_i64, ctypes.c_int, ctypes.c_double, ctypes.c_uint64, ctypes.c_uint32, c_i64, c_vp]
     L.tg_net_add_bn_relu.argtypes = [c_vp, c_vp, ctypes.c_float, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, ctypes.c_int, c_vp]
+    L.tg_net_add_bn_relu_f32.argtypes = [c_vp, c_vp, ctypes.c_float, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, ctypes.c_int, c_vp]
     L.tg_net_attention.argtypes = [c_vp, c_vp, ctypes.c_float, c_vp, c_vp, c_vp, c_i64, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_vp]
     L.tg_net_attention_fused2.argtypes = [c_vp, c_vp, c_vp, ctypes.c_float, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_vp, c_vp]
     L.tg_net_stem.argtypes = [c_vp, ctypes.c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, ctypes.c_int, ctypes.c_int, c_vp]

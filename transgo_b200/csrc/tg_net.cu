@@ -76,8 +76,43 @@ k_add_bn_relu(const uint4* __restrict__ x, const uint4* __restrict__ y, float al
 
 }  // namespace tg
 
+// the same junction on float32 activations (the folded float32 schedule): one thread = 4 channels of one row
+__global__ void __launch_bounds__(256)
+k_add_bn_relu_f32(const float4* __restrict__ x, const float4* __restrict__ y, float alpha, const float* __restrict__ ybias,
+                  const float* __restrict__ scale, const float* __restrict__ shift, float4* __restrict__ sum_out, float4* __restrict__ act_out,
+                  long long n_vec, int cvec) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_vec; i += stride) {
+        const int c0 = (int)(i % cvec) * 4;
+        float4 a = x[i];
+        if (y) {
+            float4 b = y[i];
+            if (ybias) { const float4 bb = *reinterpret_cast<const float4*>(ybias + c0); b.x += bb.x; b.y += bb.y; b.z += bb.z; b.w += bb.w; }
+            a.x = a.x + alpha * b.x; a.y = a.y + alpha * b.y; a.z = a.z + alpha * b.z; a.w = a.w + alpha * b.w;
+        }
+        if (sum_out) sum_out[i] = a;
+        if (act_out) {
+            const float4 sc = *reinterpret_cast<const float4*>(scale + c0), sh = *reinterpret_cast<const float4*>(shift + c0);
+            act_out[i] = make_float4(fmaxf(a.x * sc.x + sh.x, 0.0f), fmaxf(a.y * sc.y + sh.y, 0.0f), fmaxf(a.z * sc.z + sh.z, 0.0f), fmaxf(a.w * sc.w + sh.w, 0.0f));
+        }
+    }
+}
+
 static int g_net_reverse = 0;
 extern "C" int tg_net_debug_reverse(int on) { const int old = g_net_reverse; g_net_reverse = on; return old; }
+
+extern "C" int tg_net_add_bn_relu_f32(const float* x, const float* y, float alpha, const float* ybias, const float* scale, const float* shift,
+                                       float* sum_out, float* act_out, int64_t rows, int channels, void* stream) {
+    using namespace tg;
+    if (!x || rows <= 0 || channels <= 0 || (channels & 3) || (!sum_out && !act_out) || (act_out && (!scale || !shift)))
+        return set_err(-1, "tg_net_add_bn_relu_f32");
+    const long long n_vec = rows * (long long)(channels / 4);
+    long long blocks = (n_vec + 255) / 256;
+    if (blocks > 148LL * 32) blocks = 148LL * 32;
+    k_add_bn_relu_f32<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const float4*)x, (const float4*)y, alpha, ybias, scale, shift,
+                                                                            (float4*)sum_out, (float4*)act_out, n_vec, channels / 4);
+    return set_err((int)cudaGetLastError(), "tg_net_add_bn_relu_f32");
+}
 
 extern "C" int tg_net_add_bn_relu(const void* x, const void* y, float alpha, const float* ybias, const float* scale, const float* shift,
                                    void* sum_out, void* act_out, int64_t rows, int channels, void* stream) {

@@ -154,9 +154,15 @@ class FusedTransGoInference:
     def _junction(self, x, y, alpha, scale, shift, want_sum, want_act, ybias=None):
         """x (+ alpha*(y + ybias)) -> (sum, relu(sum*scale+shift)); x, y: channels_last [B,C,n,n] bf16 (NHWC memory)"""
         B, C = x.shape[0], x.shape[1]
+        if self.dtype == torch.float32 and x.is_contiguous(memory_format=torch.channels_last) and (y is None or y.is_contiguous(memory_format=torch.channels_last)):
+            s_out = torch.empty_like(x) if want_sum else None            # the float32 twin of the junction kernel
+            a_out = torch.empty_like(x) if want_act else None
+            _lib.check(self.lib.tg_net_add_bn_relu_f32(_lib.ptr(x), _lib.ptr(y), float(alpha), _lib.ptr(ybias), _lib.ptr(scale), _lib.ptr(shift),
+                                                       _lib.ptr(s_out), _lib.ptr(a_out), B * self.P, C, _lib.stream_ptr(device=x.device)),
+                       "tg_net_add_bn_relu_f32")
+            return s_out, a_out
         if self.dtype != torch.bfloat16:
-            # float32 / float16 copies of the same schedule (e.g. the same-precision-as-the-reference row of the bench): library
-            # elementwise ops; the hand-written kernels are bf16
+            # other copies of the same schedule (float16, or float32 tensors that are not NHWC): library elementwise ops
             s = x if y is None else x + alpha * (y if ybias is None else y + ybias.to(y.dtype).view(1, -1, 1, 1))
             a = torch.relu(s * scale.to(s.dtype).view(1, -1, 1, 1) + shift.to(s.dtype).view(1, -1, 1, 1)) if want_act else None
             return (s if want_sum else None), a
