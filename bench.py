@@ -775,10 +775,14 @@ def mcts_bench(torch, dist, dev, rank, world, args):
             make_fused_evaluator(net, dtype=torch.float32, cuda_graph="roots") if dtype == "folded32" else \
             make_evaluator(net, dtype=dtype, channels_last=dtype is not None, cuda_graph=True)
         eng = BatchedMCTS(ev, G, num_simulation=sims, tie_seed=1, game_id0=rank * G, device=dev, graph_waves=graphed)
-        for _ in range(3):                                     # warm-up waves: lazy initialisation and CUDA-graph capture happen here,
-            eng.run_wave()                                     # outside the timed move (they only add visits to the fresh roots)
-        rate, ms, n, waves = timed_moves(eng, 1)
-        out[name] = {"value": rate, "unit": "MCTS sims/s", "ms": ms, "sims": n, "moves": 1, "waves": waves,
+        # warm-up waves: lazy initialisation and CUDA-graph capture happen here, outside the timed moves (they only add visits to the
+        # fresh roots); the graphed routes warm up for ~0.1-0.3 s so that the timed region does not start on clocks that are still
+        # ramping up after the host-bound phases before it (a 0.55 s measurement read 20 % low when it did)
+        for _ in range(60 if graphed else 3):
+            eng.run_wave()
+        nmoves = 2 if dtype == "fused" else 1
+        rate, ms, n, waves = timed_moves(eng, nmoves)
+        out[name] = {"value": rate, "unit": "MCTS sims/s", "ms": ms, "sims": n, "moves": nmoves, "waves": waves,
                      "net": "TransGoNetwork 2.97 M params random init (seed 0), eval mode, 0.457 GFLOP/position" +
                             ("; BN folded, NHWC bf16; hand-written: stem (tg_net_stem), residual junctions (tg_net_add_bn_relu), attention "
                              "blocks incl. their 1x1 convolutions (tg_net_attention_fused2: tcgen05), head convolutions "
