@@ -304,6 +304,49 @@ def test_evaluate_match_alternates_colours_and_counts_wins(oracle_built):
     assert out["win"] == int(((w == 1) & nb).sum() + ((w == 2) & ~nb).sum())
 
 
+def test_evaluate_match_equals_the_reference_procedure_on_the_oracle(oracle_built):
+    """SelfPlay.policy_evaluate (self_play.py:987-1040) move by move on the CPU oracle: colours alternate from game to game, every
+    move comes from a FRESH search of the side to move (select_action, :689-704: no root noise, temperature 0.12) with that side's
+    net, the game ends on two passes or max_step, the winner is the area score against komi.  evaluate_match must play the same
+    moves in every game (same stand-in nets, same uniform draws, first-maximum tie rule) and report the same winners."""
+    from oracle import provider
+    from oracle.go_oracle import OracleEnv
+    from oracle.mcts_oracle import OracleMCTS, MCTSConfig
+    from transgo_b200.selfplay import evaluate_match
+    G, sims, max_step, seed = 6, 32, 14, 5
+    seeds = {"new": (3, 6), "old": (4, 6)}
+    out = evaluate_match(cpu_provider(*seeds["new"]), cpu_provider(*seeds["old"]), n_games=G, num_simulation=sims, max_step=max_step,
+                         tie_mode="first", seed=seed, return_actions=True)
+    acts = out["actions"].cpu().numpy()                                   # [plies, G]
+    # the uniform draws of the batched match: per ply one vector per engine (new first, then old), slot k <-> k-th game of that side
+    gen = torch.Generator(device="cuda"); gen.manual_seed(seed)
+    half = G // 2
+    new_black = np.arange(G) % 2 == 0
+    idx_a, idx_b = np.nonzero(new_black)[0], np.nonzero(~new_black)[0]
+    oenv = OracleEnv(9, max_step=max_step)
+    states = [oenv.reset()[0] for _ in range(G)]
+    done = [False] * G
+    for ply in range(acts.shape[0]):
+        black_to_move = ply % 2 == 0
+        u_new = torch.rand([half], dtype=torch.float64, device="cuda", generator=gen).cpu().numpy()
+        u_old = torch.rand([half], dtype=torch.float64, device="cuda", generator=gen).cpu().numpy()
+        for who, idx, u in (("new", idx_a if black_to_move else idx_b, u_new), ("old", idx_b if black_to_move else idx_a, u_old)):
+            sd, sharp = seeds[who]
+            for k, g in enumerate(idx):
+                if done[g]:
+                    continue
+                ora = OracleMCTS(oenv, lambda o, sd=sd, sharp=sharp: provider.synth_eval_batch(o, seed=sd, sharp=sharp),
+                                 MCTSConfig(num_simulation=sims), u_fn=lambda m, u=u, k=k: float(u[k]))
+                ora.root = ora._root_expand(states[g])                     # select_action: root = Node_V(state) + expand (:691-700)
+                a, _, _ = ora.get_action_probs(is_selfplay=False)
+                assert a == int(acts[ply, g]), (ply, g, a, int(acts[ply, g]))
+                states[g], done[g] = oenv.step(states[g], a)
+    assert all(done)
+    winners = [1 if oenv.getScore(s) > 0 else 2 for s in states]          # environment.py:118-119
+    assert winners == out["winners"].cpu().tolist()
+    assert out["win"] == sum((w == 1) == nb for w, nb in zip(winners, new_black))
+
+
 def test_continuous_selfplay_restarts_finished_slots(oracle_built):
     """continuous_self_play (self_play.py:902-968) batched: slots restart as their games end; every returned position belongs
     to a finished game, first positions are empty boards with black to move, labels are +-1 from the mover's view."""

@@ -265,7 +265,7 @@ def _root_state_view(search):
     return search.ws.reshape(-1)[off:off + sq * search.G * 4].reshape(sq, search.G, 4)
 
 
-def evaluate_match(evaluator_new, evaluator_old, n_games=10, board_size=9, device="cuda", seed=0, **mcts_kw):
+def evaluate_match(evaluator_new, evaluator_old, n_games=10, board_size=9, device="cuda", seed=0, return_actions=False, **mcts_kw):
     """Batched form of SelfPlay.policy_evaluate (self_play.py:987-1040): `n_games` games between the newest weights and the
     "evaluate" weights, colours alternating from game to game (:1000, :1026), every move chosen by a FRESH search of the side
     to move from the current position (select_action, :689-704: no tree reuse, no root noise, temperature 0.12).
@@ -285,6 +285,7 @@ def evaluate_match(evaluator_new, evaluator_old, n_games=10, board_size=9, devic
     gen = torch.Generator(device=dev); gen.manual_seed(seed)
     fresh = BatchedGoEnv(1, board_size=board_size, device=device).states      # an empty board for finished slots
     ply = 0
+    played = []
     while not bool(env.done.all()) and ply <= env.max_step + 1:
         black_to_move = ply % 2 == 0                                      # every game alternates strictly (a pass is a move)
         actions = torch.zeros([G], dtype=torch.int16, device=dev)
@@ -298,10 +299,15 @@ def evaluate_match(evaluator_new, evaluator_old, n_games=10, board_size=9, devic
             u = torch.rand([half], dtype=torch.float64, device=dev, generator=gen)
             a, _, _ = eng.get_action_probs(is_selfplay=False, u=u)
             actions[idx] = a
+        if return_actions:
+            played.append(actions.clone())
         env.step(actions, want_legal=False)
         ply += 1
     score = env.score()
     winners = torch.where(score > 0, 1, 2)                                # environment.py:118-119
     new_won = torch.where(new_black, winners == 1, winners == 2)
     win = int(new_won.sum().item())
-    return dict(win=win, lose=G - win, win_ratio=win / G, winners=winners, new_plays_black=new_black, plies=ply)
+    out = dict(win=win, lose=G - win, win_ratio=win / G, winners=winners, new_plays_black=new_black, plies=ply)
+    if return_actions:
+        out["actions"] = torch.stack(played) if played else torch.zeros([0, G], dtype=torch.int16, device=dev)   # [plies, G]; finished games: ignored
+    return out
