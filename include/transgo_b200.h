@@ -289,6 +289,9 @@ int tg_net_debug_reverse(int on);
  * returns -1 otherwise (callers then use the library GEMM path). */
 int tg_net_attention(const void* qkv, const void* x, float gamma, const float* scale, const float* shift, void* out,
                      int64_t B, int P, int dq, int channels, void* stream);
+/* ... with the second output out2 = relu(out * scale2[c] + shift2[c]) of tg_net_attention_fused2 (out2 may be NULL) */
+int tg_net_attention2(const void* qkv, const void* x, float gamma, const float* scale, const float* shift, void* out,
+                      const float* scale2, const float* shift2, void* out2, int64_t B, int P, int dq, int channels, void* stream);
 
 
 /* The stem of the net (model.py:43, :81): 3x3 convolution from the feature planes to 128 channels, folded BatchNorm, ReLU, 9x9 boards.

@@ -148,6 +148,23 @@ def test_attention_tcgen05_second_output_is_the_next_blocks_activation():
     assert torch.equal(out, out_plain) and torch.equal(out2, ref2)
 
 
+@pytest.mark.parametrize("B,P", [(40, 81), (6, 361)])
+def test_attention_mma_second_output_is_the_next_blocks_activation(B, P):
+    """tg_net_attention2 (mma.sync kernels, both board sizes): out2 bit-equal to the junction kernel applied to out."""
+    from transgo_b200 import _lib
+    L = _lib.lib()
+    g = torch.Generator(device="cuda"); g.manual_seed(B + P)
+    qkv = (torch.randn([B, P, 192], device="cuda", generator=g) * 0.8).to(torch.bfloat16)
+    x = torch.randn([B, P, 128], device="cuda", generator=g).to(torch.bfloat16)
+    sc, sh, s2, t2 = (torch.rand([128], device="cuda", generator=g) + 0.5 for _ in range(4))
+    out = torch.empty_like(x); out2 = torch.full_like(x, float("nan")); plain = torch.empty_like(x); ref2 = torch.empty_like(x)
+    _lib.check(L.tg_net_attention2(_lib.ptr(qkv), _lib.ptr(x), 0.6, _lib.ptr(sc), _lib.ptr(sh), _lib.ptr(out), _lib.ptr(s2), _lib.ptr(t2), _lib.ptr(out2),
+                                   B, P, 32, 128, _lib.stream_ptr()))
+    _lib.check(L.tg_net_attention(_lib.ptr(qkv), _lib.ptr(x), 0.6, _lib.ptr(sc), _lib.ptr(sh), _lib.ptr(plain), B, P, 32, 128, _lib.stream_ptr()))
+    _lib.check(L.tg_net_add_bn_relu(_lib.ptr(out), None, 1.0, None, _lib.ptr(s2), _lib.ptr(t2), None, _lib.ptr(ref2), B * P, 128, _lib.stream_ptr()))
+    assert torch.equal(out, plain) and torch.equal(out2, ref2)
+
+
 def test_attention_tcgen05_kernel_agrees_with_the_mma_sync_kernel():
     """the tcgen05 block against the round-1 pair (library GEMM + tg_net_attention) on the same inputs: both round q, k, v, p
     and o to bf16 at the same points, so they differ by summation order only (|d| <= 2e-2 + 2e-2 |ref|, in practice bf16 ulps)."""

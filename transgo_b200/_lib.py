@@ -46,6 +46,7 @@ def _declare(L):
     L.tg_net_attention_fused2.argtypes = [c_vp, c_vp, c_vp, ctypes.c_float, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_vp, c_vp]
     L.tg_net_stem.argtypes = [c_vp, ctypes.c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, ctypes.c_int, ctypes.c_int, c_vp]
     L.tg_net_conv3x3_head.argtypes = [c_vp, c_vp, c_vp, c_vp, c_i64, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_vp]
+    L.tg_net_attention2.argtypes = [c_vp, c_vp, ctypes.c_float, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_vp]
     L.tg_net_attention_fused.argtypes = [c_vp, c_vp, c_vp, ctypes.c_float, c_vp, c_vp, c_vp, c_i64, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_vp, c_vp]
     # the reference's 15 symbols (go_env.h:23-71), typed exactly as GoEnv/environment.py:43-90 types them
     L.Init.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float]

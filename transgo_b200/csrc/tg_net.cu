@@ -174,7 +174,8 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 
 __global__ void __launch_bounds__(kAttWarps * 32)
 k_attention(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ x, float gamma,
-            const float* __restrict__ scale, const float* __restrict__ shift, __nv_bfloat16* __restrict__ out, int P) {
+            const float* __restrict__ scale, const float* __restrict__ shift, __nv_bfloat16* __restrict__ out, int P,
+            const float* __restrict__ scale2, const float* __restrict__ shift2, __nv_bfloat16* __restrict__ out2) {
     constexpr int QK_ELEMS = 2 * kAttP * kQS, AT_ELEMS = kAttP * kAS;
     __shared__ __align__(16) __nv_bfloat16 sA[QK_ELEMS > AT_ELEMS ? QK_ELEMS : AT_ELEMS];   // q | k first, att^T afterwards
     __shared__ __align__(16) __nv_bfloat16 sV[kAttP * kVS];
@@ -325,6 +326,16 @@ k_attention(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restri
                 ow[k] = pack_bf16(fmaxf(fmaf(s0, scv[2 * k], shv[2 * k]), 0.0f), fmaxf(fmaf(s1, scv[2 * k + 1], shv[2 * k + 1]), 0.0f));
             }
             *reinterpret_cast<uint4*>(out + off) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+            if (out2) {                                              // the next residual block's opening activation (like tg_net_add_bn_relu on `out`)
+                uint32_t o2[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ow[k]));
+                    o2[k] = pack_bf16(fmaxf(__fadd_rn(__fmul_rn(f.x, scale2[c + 2 * k]), shift2[c + 2 * k]), 0.0f),
+                                      fmaxf(__fadd_rn(__fmul_rn(f.y, scale2[c + 2 * k + 1]), shift2[c + 2 * k + 1]), 0.0f));
+                }
+                *reinterpret_cast<uint4*>(out2 + off) = make_uint4(o2[0], o2[1], o2[2], o2[3]);
+            }
         }
     }
 }
@@ -345,7 +356,8 @@ constexpr size_t kBigSmem = (size_t)kBigP * kQS * 2 * 2 + (size_t)kBigP * kVS * 
 
 __global__ void __launch_bounds__(kBigWarps * 32, 1)
 k_attention_big(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ x, float gamma,
-                const float* __restrict__ scale, const float* __restrict__ shift, __nv_bfloat16* __restrict__ out, int P) {
+                const float* __restrict__ scale, const float* __restrict__ shift, __nv_bfloat16* __restrict__ out, int P,
+            const float* __restrict__ scale2, const float* __restrict__ shift2, __nv_bfloat16* __restrict__ out2) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(smem_raw);
     __nv_bfloat16* sK = sQ + kBigP * kQS;
@@ -491,6 +503,16 @@ k_attention_big(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __re
                     ow[k] = pack_bf16(fmaxf(fmaf(s0, scv[2 * k], shv[2 * k]), 0.0f), fmaxf(fmaf(s1, scv[2 * k + 1], shv[2 * k + 1]), 0.0f));
                 }
                 *reinterpret_cast<uint4*>(out + off) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+            if (out2) {                                              // the next residual block's opening activation (like tg_net_add_bn_relu on `out`)
+                uint32_t o2[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ow[k]));
+                    o2[k] = pack_bf16(fmaxf(__fadd_rn(__fmul_rn(f.x, scale2[c + 2 * k]), shift2[c + 2 * k]), 0.0f),
+                                      fmaxf(__fadd_rn(__fmul_rn(f.y, scale2[c + 2 * k + 1]), shift2[c + 2 * k + 1]), 0.0f));
+                }
+                *reinterpret_cast<uint4*>(out2 + off) = make_uint4(o2[0], o2[1], o2[2], o2[3]);
+            }
             }
         }
     }
@@ -759,14 +781,14 @@ extern "C" int tg_net_stem(const float* obs, int cin, const void* w, const float
     return set_err((int)cudaGetLastError(), "tg_net_stem");
 }
 
-extern "C" int tg_net_attention(const void* qkv, const void* x, float gamma, const float* scale, const float* shift, void* out,
-                                int64_t B, int P, int dq, int channels, void* stream) {
+extern "C" int tg_net_attention2(const void* qkv, const void* x, float gamma, const float* scale, const float* shift, void* out,
+                                 const float* scale2, const float* shift2, void* out2, int64_t B, int P, int dq, int channels, void* stream) {
     using namespace tg;
-    if (!qkv || !x || !scale || !shift || !out || B <= 0 || P <= 0 || P > kBigP || dq != kAttDq || channels != kAttC)
+    if (!qkv || !x || !scale || !shift || !out || B <= 0 || P <= 0 || P > kBigP || dq != kAttDq || channels != kAttC || (out2 && (!scale2 || !shift2)))
         return set_err(-1, "tg_net_attention (supports P <= 368, 32 query channels, 128 value channels)");
     if (P <= kAttP) {
         k_attention<<<(unsigned)B, kAttWarps * 32, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)qkv, (const __nv_bfloat16*)x, gamma, scale,
-                                                                               shift, (__nv_bfloat16*)out, P);
+                                                                               shift, (__nv_bfloat16*)out, P, scale2, shift2, (__nv_bfloat16*)out2);
     } else {
         static unsigned long long attr_done = 0;             // one bit per device: the attribute is per device, not per process
         int dev = 0; cudaGetDevice(&dev);
@@ -775,7 +797,12 @@ extern "C" int tg_net_attention(const void* qkv, const void* x, float gamma, con
             attr_done |= 1ull << (dev & 63);
         }
         k_attention_big<<<(unsigned)B, kBigWarps * 32, kBigSmem, (cudaStream_t)stream>>>((const __nv_bfloat16*)qkv, (const __nv_bfloat16*)x, gamma,
-                                                                                          scale, shift, (__nv_bfloat16*)out, P);
+                                                                                          scale, shift, (__nv_bfloat16*)out, P, scale2, shift2, (__nv_bfloat16*)out2);
     }
     return set_err((int)cudaGetLastError(), "tg_net_attention");
+}
+
+extern "C" int tg_net_attention(const void* qkv, const void* x, float gamma, const float* scale, const float* shift, void* out,
+                                int64_t B, int P, int dq, int channels, void* stream) {
+    return tg_net_attention2(qkv, x, gamma, scale, shift, out, nullptr, nullptr, nullptr, B, P, dq, channels, stream);
 }

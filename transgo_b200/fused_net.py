@@ -194,9 +194,11 @@ class FusedTransGoInference:
         if self.P <= 368 and dq == 32 and C == 128 and self.dtype == torch.bfloat16:
             # scores, softmax, att^T . v and the junction in ONE hand-written kernel (csrc/tg_net.cu: k_attention)
             act = torch.empty_like(x)
-            _lib.check(self.lib.tg_net_attention(_lib.ptr(qkv), _lib.ptr(x), p["gamma"], _lib.ptr(p["s"]), _lib.ptr(p["t"]),
-                                                 _lib.ptr(act), B, self.P, dq, C, _lib.stream_ptr(device=x.device)), "tg_net_attention")
-            return act, None
+            act2 = torch.empty_like(x) if nxt is not None else None
+            _lib.check(self.lib.tg_net_attention2(_lib.ptr(qkv), _lib.ptr(x), p["gamma"], _lib.ptr(p["s"]), _lib.ptr(p["t"]), _lib.ptr(act),
+                                                  _lib.ptr(nxt[0]) if nxt else None, _lib.ptr(nxt[1]) if nxt else None, _lib.ptr(act2),
+                                                  B, self.P, dq, C, _lib.stream_ptr(device=x.device)), "tg_net_attention")
+            return act, act2
         q, k, v = qkv[..., :dq], qkv[..., dq:2 * dq], qkv[..., 2 * dq:]
         att = torch.softmax(torch.bmm(q, k.transpose(1, 2)), dim=-1)           # [B, P, P], rows = query position
         o = torch.bmm(att.transpose(1, 2), v)                                  # out[:, j] = sum_i att[i, j] * v[i]
